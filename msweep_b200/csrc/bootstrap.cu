@@ -1,0 +1,206 @@
+// bootstrap.cu — BootstrapSample on the device (src/BootstrapSample.cpp:33-73 and the replicate loop
+// src/mSWEEP.cpp:496-518 of the reference).
+//
+// The reference draws `bootstrap_count` categorical samples one at a time from
+// std::discrete_distribution<uint32_t>(class counts) driven by std::mt19937_64, i.e. per draw:
+// one 64-bit Mersenne-Twister output u, p = double(u) * 2^-64 (nextafter(1,0) if that rounds to 1),
+// class = lower_bound(cumulative probabilities, p).  In MSWB_RNG_LIBSTDCXX_EXACT mode the raw
+// generator stream is produced on the host (it is inherently sequential and costs ~2 ns per draw) and
+// the expensive part — bootstrap_count binary searches over N cumulative probabilities plus the
+// histogram — runs on the device, so the resampled counts are bit-identical to the reference's.
+// MSWB_RNG_PHILOX replaces the stream by a counter-based generator evaluated on the device.
+#include "handles.cuh"
+
+#include <cmath>
+#include <memory>
+#include <random>
+
+using namespace mswb;
+
+namespace mswb {
+
+__device__ __forceinline__ double canonical_from_u64(unsigned long long u) {
+  // std::generate_canonical<double, 53>(mt19937_64): one output, rounded to nearest, times 2^-64
+  double p = __ull2double_rn(u) * 0x1p-64;
+  return p >= 1.0 ? 0x1.fffffffffffffp-1 : p;
+}
+
+__device__ __forceinline__ unsigned long long lower_bound_idx(const double *__restrict__ cp, unsigned long long n, double p) {
+  unsigned long long lo = 0, hi = n;   // first index with cp[idx] >= p
+  while (lo < hi) {
+    const unsigned long long mid = (lo + hi) >> 1;
+    if (cp[mid] < p) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void resample_from_stream_kernel(const unsigned long long *__restrict__ stream, unsigned long long n_draws,
+                                            const double *__restrict__ cp, unsigned long long n_cp,
+                                            unsigned *__restrict__ hist) {
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_draws;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long idx = n_cp ? lower_bound_idx(cp, n_cp, canonical_from_u64(stream[i])) : 0ull;
+    atomicAdd(&hist[idx], 1u);
+  }
+}
+
+// Philox-4x32-10 keyed by (seed, replicate), counter = draw index / 2; two 64-bit outputs per block.
+__device__ __forceinline__ void philox_round(unsigned (&c)[4], unsigned (&k)[2]) {
+  const unsigned long long p0 = 0xD2511F53ull * c[0], p1 = 0xCD9E8D57ull * c[2];
+  const unsigned n0 = (unsigned)(p1 >> 32) ^ c[1] ^ k[0], n1 = (unsigned)p1;
+  const unsigned n2 = (unsigned)(p0 >> 32) ^ c[3] ^ k[1], n3 = (unsigned)p0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+}
+__global__ void resample_philox_kernel(unsigned long long seed, unsigned long long replicate, unsigned long long n_draws,
+                                       const double *__restrict__ cp, unsigned long long n_cp, unsigned *__restrict__ hist) {
+  const unsigned long long n_blocks = (n_draws + 1) / 2;
+  for (unsigned long long b = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; b < n_blocks;
+       b += (unsigned long long)gridDim.x * blockDim.x) {
+    unsigned c[4] = {(unsigned)b, (unsigned)(b >> 32), (unsigned)replicate, (unsigned)(replicate >> 32)};
+    unsigned k[2] = {(unsigned)seed, (unsigned)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c, k);
+    const unsigned long long u0 = ((unsigned long long)c[1] << 32) | c[0], u1 = ((unsigned long long)c[3] << 32) | c[2];
+    atomicAdd(&hist[n_cp ? lower_bound_idx(cp, n_cp, canonical_from_u64(u0)) : 0ull], 1u);
+    if (2 * b + 1 < n_draws) atomicAdd(&hist[n_cp ? lower_bound_idx(cp, n_cp, canonical_from_u64(u1)) : 0ull], 1u);
+  }
+}
+
+__global__ void u32_to_double_kernel(const unsigned *in, double *out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+
+} // namespace mswb
+
+// declared in vi.cu: a run whose class counts already sit on the device
+int mswb_vi_run_dev_counts(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const double *counts_dev,
+                           double sum_counts, const mswb_vi_opts *opts, double *theta, mswb_vi_stat *stat);
+
+namespace {
+
+struct Resampler {
+  mswb_ctx *ctx;
+  uint64_t N = 0, draws = 0;
+  int rng_mode;
+  uint64_t seed64 = 0;
+  std::mt19937_64 gen;
+  DevBuf<double> cp;           // cumulative probabilities (empty when N < 2, as in libstdc++)
+  uint64_t n_cp = 0;
+  DevBuf<unsigned long long> stream_dev;
+  PinnedBuf<unsigned long long> stream_host;
+  static constexpr uint64_t CHUNK = 1u << 22;
+
+  Resampler(mswb_ctx *c, const mswb_lik *lik, int32_t seed, uint64_t bootstrap_count, int mode) : ctx(c), rng_mode(mode) {
+    MSWB_REQUIRE(mode == MSWB_RNG_LIBSTDCXX_EXACT || mode == MSWB_RNG_PHILOX, "unknown rng mode");
+    MSWB_REQUIRE(lik->N == lik->N_total, "bootstrap needs the whole class table on this GPU (use a world_size == 1 context per replica)");
+    N = lik->N;
+    cudaStream_t s = ctx->stream;
+    // src/BootstrapSample.cpp:38-44: uint32_t weights -> libstdc++ discrete_distribution::_M_initialize
+    std::vector<double> c_host(N);
+    d2h(c_host.data(), lik->counts.p, N, s);
+    MSWB_CUDA(cudaStreamSynchronize(s));
+    uint64_t total = 0;
+    std::vector<double> prob(N);
+    for (uint64_t i = 0; i < N; ++i) { const uint32_t w = (uint32_t)c_host[i]; prob[i] = (double)w; total += (uint64_t)c_host[i]; }
+    draws = bootstrap_count == 0 ? total : bootstrap_count;          // src/BootstrapSample.cpp:56
+    if (N >= 2) {
+      double sum = 0.0;
+      for (uint64_t i = 0; i < N; ++i) sum += prob[i];
+      MSWB_REQUIRE(sum > 0.0, "all class counts are zero");
+      for (uint64_t i = 0; i < N; ++i) prob[i] /= sum;
+      double run = 0.0;
+      for (uint64_t i = 0; i < N; ++i) { run += prob[i]; prob[i] = run; }   // std::partial_sum
+      prob[N - 1] = 1.0;
+      cp.alloc(N);
+      h2d(cp.p, prob.data(), N, s);
+      MSWB_CUDA(cudaStreamSynchronize(s));
+      n_cp = N;
+    }
+    // src/BootstrapSample.cpp:48-53 (seed narrowed to int32_t by include/Sample.hpp:163-169)
+    if (seed == 26012023) { std::random_device rd; seed64 = rd(); gen = std::mt19937_64(seed64); }
+    else { gen = std::mt19937_64(seed); seed64 = (uint64_t)(int64_t)seed; }
+    if (mode == MSWB_RNG_LIBSTDCXX_EXACT) { stream_dev.alloc(CHUNK); stream_host.alloc(2 * CHUNK); }
+  }
+
+  void skip() { if (rng_mode == MSWB_RNG_LIBSTDCXX_EXACT) gen.discard(draws); }
+
+  // hist_dev[N] (zeroed here) receives the resampled class counts of the next replicate
+  void next(uint64_t replicate, unsigned *hist_dev) {
+    cudaStream_t s = ctx->stream;
+    MSWB_CUDA(cudaMemsetAsync(hist_dev, 0, std::max<uint64_t>(N, 1) * sizeof(unsigned), s));
+    const int grid = ctx->n_sms * 8;
+    if (rng_mode == MSWB_RNG_PHILOX) {
+      if (draws) { resample_philox_kernel<<<grid, 256, 0, s>>>(seed64, replicate, draws, cp.p, n_cp, hist_dev); MSWB_LAUNCHED(); }
+      return;
+    }
+    // double-buffered: the host fills chunk c+1 while the device consumes chunk c
+    cudaEvent_t ev[2];
+    MSWB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    MSWB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    bool used[2] = {false, false};
+    int slot = 0;
+    for (uint64_t done = 0; done < draws; done += CHUNK, slot ^= 1) {
+      const uint64_t n = std::min<uint64_t>(CHUNK, draws - done);
+      unsigned long long *hbuf = stream_host.p + (size_t)slot * CHUNK;
+      if (used[slot]) MSWB_CUDA(cudaEventSynchronize(ev[slot]));
+      for (uint64_t i = 0; i < n; ++i) hbuf[i] = gen();
+      // the single device buffer is safe: copy and kernel are ordered on one stream
+      h2d(stream_dev.p, hbuf, n, s);
+      MSWB_CUDA(cudaEventRecord(ev[slot], s));
+      used[slot] = true;
+      resample_from_stream_kernel<<<grid, 256, 0, s>>>(stream_dev.p, n, cp.p, n_cp, hist_dev);
+      MSWB_LAUNCHED();
+    }
+    MSWB_CUDA(cudaStreamSynchronize(s));
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+  }
+};
+
+} // namespace
+
+extern "C" {
+
+int mswb_bootstrap_resample(mswb_ctx *ctx, const mswb_lik *lik, int32_t seed, uint64_t bootstrap_count,
+                            int rng_mode, uint64_t n_replicates, uint32_t *out) {
+  return guarded([&] {
+    MSWB_REQUIRE(ctx && lik && out, "NULL argument");
+    MSWB_CUDA(cudaSetDevice(ctx->device));
+    Resampler rs(ctx, lik, seed, bootstrap_count, rng_mode);
+    DevBuf<unsigned> hist;
+    hist.alloc(rs.N);
+    for (uint64_t r = 0; r < n_replicates; ++r) {
+      rs.next(r, hist.p);
+      d2h((unsigned *)out + r * rs.N, hist.p, rs.N, ctx->stream);
+      MSWB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+  });
+}
+
+int mswb_bootstrap_run(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const mswb_vi_opts *opts,
+                       uint64_t n_replicates, uint64_t bootstrap_count, int32_t seed, int rng_mode,
+                       int replica_rank, int replica_world, double *thetas, mswb_vi_stat *stats) {
+  return guarded([&] {
+    MSWB_REQUIRE(ctx && lik && alpha0 && opts && thetas, "NULL argument");
+    MSWB_REQUIRE(replica_world >= 1 && replica_rank >= 0 && replica_rank < replica_world, "bad replica rank / world");
+    MSWB_CUDA(cudaSetDevice(ctx->device));
+    Resampler rs(ctx, lik, seed, bootstrap_count, rng_mode);
+    DevBuf<unsigned> hist;
+    DevBuf<double> counts;
+    hist.alloc(rs.N);
+    counts.alloc(rs.N);
+    for (uint64_t r = 0; r < n_replicates; ++r) {
+      if ((int)(r % (uint64_t)replica_world) != replica_rank) { rs.skip(); continue; }   // another GPU's replicate
+      rs.next(r, hist.p);
+      u32_to_double_kernel<<<ctx->n_sms * 2, 256, 0, ctx->stream>>>(hist.p, counts.p, rs.N);
+      MSWB_LAUNCHED();
+      // the reference feeds log(count) with -inf for unsampled classes (src/BootstrapSample.cpp:67-72);
+      // the sweeps multiply by the count itself, so a zero count simply drops the class.
+      if (mswb_vi_run_dev_counts(ctx, lik, alpha0, counts.p, (double)rs.draws, opts, thetas + r * lik->K,
+                                 stats ? stats + r : nullptr))
+        throw Error(std::string("bootstrap replicate ") + std::to_string(r) + ": " + mswb_last_error());
+    }
+  });
+}
+
+} // extern "C"

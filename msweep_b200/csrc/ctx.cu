@@ -1,0 +1,135 @@
+// ctx.cu — context, error state, NCCL binding (loaded lazily so that single-GPU use never needs it).
+#include "common.cuh"
+
+#include <dlfcn.h>
+#include <cstring>
+#include <mutex>
+
+namespace mswb {
+static thread_local std::string t_last_error;
+void set_last_error(const std::string &msg) { t_last_error = msg; }
+std::atomic<uint64_t> g_launches{0};
+} // namespace mswb
+
+// ---- NCCL, resolved at run time -----------------------------------------------------------------
+// Only the five entry points the data path needs.  The ABI below is NCCL 2.x's (ncclUniqueId is 128
+// opaque bytes passed BY VALUE; ncclDataType_t: ncclUint64 = 5, ncclFloat64 = 8; ncclSum = 0).
+struct NcclUniqueId { char internal[MSWB_NCCL_ID_BYTES]; };
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+  int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+
+static NcclApi &nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // Inside a torch process the already-loaded libnccl.so.2 (torch's bundled build) is reused.
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) return;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+  });
+  MSWB_REQUIRE(api.handle && api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce,
+               "NCCL (libnccl.so.2) could not be loaded; multi-GPU contexts are unavailable");
+  return api;
+}
+
+#define MSWB_NCCL(expr)                                                                              \
+  do {                                                                                               \
+    int _r = (expr);                                                                                 \
+    if (_r != 0)                                                                                     \
+      throw ::mswb::Error(std::string("NCCL error: ") +                                               \
+                          (nccl().GetErrorString ? nccl().GetErrorString(_r) : "?") + " (" #expr ")"); \
+  } while (0)
+
+void mswb_ctx::allreduce_sum(double *buf_dev, size_t count) {
+  if (world == 1 || count == 0) return;
+  MSWB_NCCL(nccl().AllReduce(buf_dev, buf_dev, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, nccl_comm, stream));
+}
+void mswb_ctx::allreduce_sum_u64(unsigned long long *buf_dev, size_t count) {
+  if (world == 1 || count == 0) return;
+  MSWB_NCCL(nccl().AllReduce(buf_dev, buf_dev, count, /*ncclUint64*/ 5, /*ncclSum*/ 0, nccl_comm, stream));
+}
+
+extern "C" {
+
+const char *mswb_last_error(void) { return mswb::t_last_error.c_str(); }
+const char *mswb_version(void) { return "msweep-b200 0.1.0 (sm_100a)"; }
+uint64_t mswb_launch_count(void) { return mswb::g_launches.load(); }
+
+int mswb_nccl_unique_id(void *out_id) {
+  return mswb::guarded([&] {
+    MSWB_REQUIRE(out_id, "out_id is NULL");
+    NcclUniqueId id;
+    MSWB_NCCL(nccl().GetUniqueId(&id));
+    std::memcpy(out_id, &id, sizeof(id));
+  });
+}
+
+int mswb_ctx_create(int device, int rank, int world_size, const void *nccl_id, void *cuda_stream, mswb_ctx **out) {
+  return mswb::guarded([&] {
+    MSWB_REQUIRE(out, "out is NULL");
+    MSWB_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "bad rank / world_size");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    MSWB_REQUIRE(e == cudaSuccess && n_dev > 0,
+                 "no CUDA device available: msweep_b200 has no CPU fallback (this backend needs an sm_100a GPU)");
+    MSWB_REQUIRE(device >= 0 && device < n_dev, "device index out of range");
+    MSWB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MSWB_CUDA(cudaGetDeviceProperties(&prop, device));
+    MSWB_REQUIRE(prop.major == 10, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                       "; this library carries sm_100a code only");
+    std::unique_ptr<mswb_ctx> ctx(new mswb_ctx);
+    ctx->device = device; ctx->rank = rank; ctx->world = world_size;
+    ctx->n_sms = prop.multiProcessorCount;
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    else { MSWB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    if (world_size > 1) {
+      MSWB_REQUIRE(nccl_id, "nccl_id is required when world_size > 1");
+      NcclUniqueId id;
+      std::memcpy(&id, nccl_id, sizeof(id));
+      MSWB_NCCL(nccl().CommInitRank(&ctx->nccl_comm, world_size, id, rank));
+    }
+    *out = ctx.release();
+  });
+}
+
+void mswb_ctx_destroy(mswb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->nccl_comm) nccl().CommDestroy(ctx->nccl_comm);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int mswb_ctx_sync(mswb_ctx *ctx) {
+  return mswb::guarded([&] {
+    MSWB_REQUIRE(ctx, "ctx is NULL");
+    MSWB_CUDA(cudaSetDevice(ctx->device));
+    MSWB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int mswb_shard_range(const mswb_ctx *ctx, uint64_t n_ecs, uint64_t *begin, uint64_t *end) {
+  return mswb::guarded([&] {
+    MSWB_REQUIRE(ctx && begin && end, "NULL argument");
+    // contiguous, balanced to within one class: rank r owns [floor(N r / W), floor(N (r+1) / W))
+    *begin = (uint64_t)((unsigned __int128)n_ecs * ctx->rank / ctx->world);
+    *end = (uint64_t)((unsigned __int128)n_ecs * (ctx->rank + 1) / ctx->world);
+  });
+}
+
+} // extern "C"

@@ -1,0 +1,62 @@
+// handles.cuh — the opaque objects behind the C ABI (device-resident state).
+#pragma once
+#include "common.cuh"
+
+// Equivalence-class table, replicated on every rank (include/mSWEEP_alignment.hpp:137-215 products).
+struct mswb_aln {
+  mswb_ctx *ctx = nullptr;
+  uint64_t n_reads = 0, n_targets = 0, n_ecs = 0, n_aligned = 0, pat_nnz = 0;
+  mswb::DevBuf<uint64_t> hash;        // [n_ecs] ascending
+  mswb::DevBuf<uint64_t> count;       // [n_ecs] reads per class
+  mswb::DevBuf<uint32_t> rep_read;    // [n_ecs] smallest read id of the class
+  mswb::DevBuf<uint64_t> pat_ptr;     // [n_ecs+1] CSR over the representative patterns
+  mswb::DevBuf<uint32_t> pat_targets; // [pat_nnz]
+  mswb::DevBuf<uint64_t> read_ptr;    // [n_ecs+1] CSR over member reads
+  mswb::DevBuf<uint32_t> read_ids;    // [n_aligned] ascending inside each class
+};
+
+// Likelihood of the rank's EC shard plus the optimiser's persistent state.
+//
+// Device layout (private): EC-major.  Row j = class j of the shard, `Kp` elements per row
+// (K rounded up so every row starts 16-byte aligned), padding columns hold 0.  This is the
+// transpose of the reference's group-major seamat matrix: a VI pass then streams whole rows with
+// 128-bit loads, the per-class logsumexp is a reduction along the row, and the per-group sums
+// accumulate in registers down the rows.
+struct mswb_lik {
+  mswb_ctx *ctx = nullptr;
+  uint32_t K_all = 0;          // groups in the grouping
+  uint32_t K = 0;              // groups kept after --min-hits (rows of the reference's matrix)
+  uint32_t Kp = 0;             // device row stride in elements
+  uint64_t N = 0;              // classes in this rank's shard
+  uint64_t ec_begin = 0;       // first global class index of the shard
+  uint64_t N_total = 0;        // classes over all ranks
+  int storage = MSWB_STORE_F64;
+  double sum_counts_total = 0; // sum of class counts over ALL ranks
+
+  std::vector<uint8_t> mask;   // [K_all] groups_considered()
+  std::vector<uint64_t> hits;  // [K_all] --min-hits tallies (empty when min_hits == 0)
+  std::vector<uint32_t> kept;  // [K] original id of kept group g'
+
+  // inputs kept for on-demand exports / rebuilds of the shard
+  mswb::DevBuf<uint64_t> pat_ptr;          // [N+1] rebased to 0
+  mswb::DevBuf<uint32_t> pat_targets;
+  mswb::DevBuf<uint32_t> group_of_target;  // [T]
+  mswb::DevBuf<uint32_t> kept_dev;         // [K]
+  mswb::DevBuf<uint64_t> lut_off;          // [K+1] ragged LUT offsets
+  mswb::DevBuf<double> lut;                // LUT[g'][c], c = 0..size(g')
+  uint64_t n_targets = 0;
+  bool from_patterns = false;
+
+  mswb::DevBuf<double> counts;   // [N] class counts c_j as doubles
+  mswb::DevBuf<double> logl;     // [N x Kp] log-likelihood (RCG, exports); may be empty in F32 storage
+  mswb::DevBuf<double> rowmax;   // [N] M_j = max_k logl(j, k)              (linear-domain EM)
+  mswb::DevBuf<double> P64;      // [N x Kp] exp(logl - M_j)                 (EM, F64 storage)
+  mswb::DevBuf<float> P32;       // [N x Kp4] same in fp32                   (EM, F32 storage)
+  uint32_t Kp32 = 0;             // row stride of P32 (K rounded up to 4)
+
+  // optimiser state that outlives a run (posterior export)
+  mswb::DevBuf<double> gamma;    // [N x Kp] RCG log-responsibilities
+  mswb::DevBuf<double> step;     // [N x Kp] RCG search direction
+  mswb::DevBuf<double> last_dg;  // [K] digamma(N_k) of the last EM pass (posteriors on demand)
+  int last_algo = -1;
+};

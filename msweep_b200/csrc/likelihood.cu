@@ -1,0 +1,428 @@
+// likelihood.cu — LL_WOR21 on the device (include/Likelihood.hpp:92-207 of the reference):
+// per-(class, group) hit counts from the class patterns, the --min-hits mask, the beta-binomial
+// lookup table and the dense gather, written EC-major straight into the layout the VI sweeps read.
+#include "handles.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+using namespace mswb;
+
+namespace mswb {
+
+// One warp owns one class at a time and a private row of K_all counters in shared memory.
+// Counting is O(pattern length); the counters are zeroed again by walking the same pattern, so the
+// O(K_all) cost per class is paid only by the kernels that have to emit a dense row anyway.
+constexpr int LIK_NT = 256;
+constexpr int LIK_WARPS = LIK_NT / 32;
+
+__device__ __forceinline__ void count_pattern(unsigned *row, const uint32_t *__restrict__ tg, unsigned long long a,
+                                              unsigned long long b, const uint32_t *__restrict__ group_of_target, int lane) {
+  for (unsigned long long p = a + lane; p < b; p += 32) atomicAdd(&row[group_of_target[tg[p]]], 1u);
+  __syncwarp();
+}
+
+// --min-hits tallies: hits[g] += ec_count[i] once per (class, group) with c(g,i) > 0
+// (include/Likelihood.hpp:149-154).  atomicExch hands each distinct group to exactly one lane and
+// leaves the counter row clean for the next class.
+__global__ void __launch_bounds__(LIK_NT)
+group_hits_kernel(const uint64_t *__restrict__ pat_ptr, const uint32_t *__restrict__ pat_targets,
+                  const uint32_t *__restrict__ group_of_target, const double *__restrict__ counts,
+                  unsigned long long N, int K_all, int active_warps, unsigned long long *__restrict__ hits) {
+  extern __shared__ unsigned s_rows[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= active_warps) return;   // (no block-wide barrier below: warps are independent)
+  unsigned *row = s_rows + (size_t)warp * K_all;
+  for (int k = lane; k < K_all; k += 32) row[k] = 0;
+  __syncwarp();
+  const unsigned long long n_warps = (unsigned long long)gridDim.x * active_warps;
+  for (unsigned long long j = (unsigned long long)blockIdx.x * active_warps + warp; j < N; j += n_warps) {
+    const unsigned long long a = pat_ptr[j], b = pat_ptr[j + 1];
+    count_pattern(row, pat_targets, a, b, group_of_target, lane);
+    const unsigned long long c = (unsigned long long)counts[j];
+    for (unsigned long long p = a + lane; p < b; p += 32) {
+      const uint32_t g = group_of_target[pat_targets[p]];
+      if (atomicExch(&row[g], 0u) > 0u) atomicAdd(&hits[g], c);
+    }
+    __syncwarp();
+  }
+}
+
+// Dense rows.  MODE 0: logl (fp64).  MODE 1: P = exp(logl - rowmax) fp64 + rowmax.  MODE 2: same in fp32.
+// MODE 3: raw hit counts as uint32 (parity export; row stride K_all, all groups).
+template <int MODE, typename OT>
+__global__ void __launch_bounds__(LIK_NT)
+lik_fill_kernel(const uint64_t *__restrict__ pat_ptr, const uint32_t *__restrict__ pat_targets,
+                const uint32_t *__restrict__ group_of_target, const uint32_t *__restrict__ kept,
+                const uint64_t *__restrict__ lut_off, const double *__restrict__ lut, unsigned long long N,
+                int K_all, int K, int ld, int active_warps, double l0, OT *__restrict__ out, double *__restrict__ rowmax) {
+  extern __shared__ unsigned s_rows[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= active_warps) return;
+  unsigned *row = s_rows + (size_t)warp * K_all;
+  for (int k = lane; k < K_all; k += 32) row[k] = 0;
+  __syncwarp();
+  const unsigned long long n_warps = (unsigned long long)gridDim.x * active_warps;
+  for (unsigned long long j = (unsigned long long)blockIdx.x * active_warps + warp; j < N; j += n_warps) {
+    const unsigned long long a = pat_ptr[j], b = pat_ptr[j + 1];
+    count_pattern(row, pat_targets, a, b, group_of_target, lane);
+    OT *orow = out + j * (unsigned long long)ld;
+    if (MODE == 3) {
+      for (int k = lane; k < K_all; k += 32) orow[k] = (OT)row[k];
+    } else {
+      // LUT[g][0] = log(zero_inflation) = l0 for every group, and almost every (class, group) pair has
+      // no hit: only the few non-zero counters go to the table (and, in the linear modes, through exp).
+      double m = -INFINITY, e0 = 0.0;
+      if (MODE != 0) {
+        for (int k = lane; k < K; k += 32) {
+          const unsigned c = row[kept[k]];
+          m = fmax(m, c == 0 ? l0 : lut[lut_off[k] + c]);
+        }
+        m = warp_max(m);
+        if (lane == 0) rowmax[j] = m;
+        e0 = exp(l0 - m);
+      }
+      for (int k = lane; k < ld; k += 32) {
+        double v = 0.0;
+        if (k < K) {
+          const unsigned c = row[kept[k]];
+          if (MODE == 0) v = c == 0 ? l0 : lut[lut_off[k] + c];
+          else v = c == 0 ? e0 : exp(lut[lut_off[k] + c] - m);
+        }
+        orow[k] = (OT)v;
+      }
+    }
+    __syncwarp();
+    for (unsigned long long p = a + lane; p < b; p += 32) row[group_of_target[pat_targets[p]]] = 0;
+    __syncwarp();
+  }
+}
+
+__global__ void u64_to_double_kernel(const uint64_t *in, double *out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+__global__ void rebase_ptr_kernel(const uint64_t *in, uint64_t *out, size_t n, uint64_t base) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i] - base;
+}
+
+// in: rows x cols row-major  ->  out: cols x rows row-major with row stride ld_out (padding zeroed by the caller)
+template <typename TI, typename TO>
+__global__ void transpose_kernel(const TI *__restrict__ in, size_t rows, size_t cols, size_t ld_in,
+                                 TO *__restrict__ out, size_t ld_out) {
+  __shared__ TI tile[32][33];
+  const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const size_t r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = in[r * ld_in + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const size_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[c * ld_out + r] = (TO)tile[threadIdx.x][i];
+  }
+}
+
+template <typename TI, typename TO>
+void transpose(const TI *in, size_t rows, size_t cols, size_t ld_in, TO *out, size_t ld_out, cudaStream_t s) {
+  if (rows == 0 || cols == 0) return;
+  // gridDim.y is limited to 65535 blocks: walk the row dimension in slabs
+  const size_t slab = (size_t)65535 * 32;
+  for (size_t r0 = 0; r0 < rows; r0 += slab) {
+    const size_t nr = std::min(slab, rows - r0);
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(nr, 32));
+    transpose_kernel<TI, TO><<<grid, dim3(32, 8), 0, s>>>(in + r0 * ld_in, nr, cols, ld_in, out + r0, ld_out);
+    MSWB_LAUNCHED();
+  }
+}
+
+} // namespace mswb
+
+namespace {
+
+// include/Likelihood.hpp:47-60, 92-107, 198-207 evaluated on the host with the same libm calls the
+// reference makes; K'(S+1) values, negligible next to the matrix.  The table is ragged: group g' owns
+// lut_off[g'] .. lut_off[g'] + size(g'), so one huge group does not inflate the others' rows.
+double lbeta_h(double x, double y) { return std::lgamma(x) + std::lgamma(y) - std::lgamma(x + y); }
+double ldbb_scaled_h(uint64_t k, uint64_t n, double alpha, double beta) {
+  const double lbc = std::lgamma((double)n + 1.0) - std::lgamma((double)k + 1.0) - std::lgamma((double)(n - k) + 1.0);
+  return lbc + lbeta_h((double)k + alpha, (double)(n - k) + beta) - lbeta_h((double)n + alpha, beta);
+}
+
+void build_lut(const std::vector<uint64_t> &sizes, double q, double e, double zi, std::vector<uint64_t> *off, std::vector<double> *lut) {
+  off->assign(sizes.size() + 1, 0);
+  for (size_t g = 0; g < sizes.size(); ++g) (*off)[g + 1] = (*off)[g] + sizes[g] + 1;
+  lut->assign(off->back(), 0.0);
+  const double l0 = std::log(zi), l1 = std::log1p(-zi);
+  for (size_t g = 0; g < sizes.size(); ++g) {
+    const double n = (double)sizes[g];
+    const double mean = n * q;                       // update_bb_parameters, bb_constants = {q, e}
+    const double phi = 1.0 / (n - mean + e);
+    const double beta = phi * (n - mean);
+    const double alpha = (mean * beta) / (n - mean);
+    double *row = lut->data() + (*off)[g];
+    row[0] = l0;
+    for (uint64_t c = 1; c <= sizes[g]; ++c) row[c] = ldbb_scaled_h(c, sizes[g], alpha, beta) + l1;
+  }
+}
+
+// Warps of a CTA that get a counter row: as many as fit in ~200 KB of shared memory.
+int lik_active_warps(uint32_t K_all) {
+  const size_t per_row = (size_t)K_all * sizeof(unsigned);
+  MSWB_REQUIRE(per_row <= 200 * 1024, "too many groups for the shared-memory hit counters (max 51200)");
+  return (int)std::min<size_t>(mswb::LIK_WARPS, (200 * 1024) / per_row);
+}
+size_t lik_smem_bytes(uint32_t K_all) { return (size_t)lik_active_warps(K_all) * K_all * sizeof(unsigned); }
+
+template <class Kern> void prepare_fill_kernel(Kern kern, size_t smem) {
+  MSWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+
+int fill_grid(mswb_ctx *ctx, uint64_t N, uint32_t K_all) {
+  const uint64_t want = ceil_div(N, (uint64_t)lik_active_warps(K_all));
+  const uint64_t per_sm = std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(1, lik_smem_bytes(K_all))));
+  return (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->n_sms * per_sm));
+}
+
+} // namespace
+
+extern "C" {
+
+int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_target, uint32_t n_groups,
+                   const uint64_t *group_sizes, double q, double e, double zero_inflation, uint64_t min_hits,
+                   int storage, mswb_lik **out) {
+  return guarded([&] {
+    MSWB_REQUIRE(ctx && aln && group_of_target && group_sizes && out, "NULL argument");
+    MSWB_REQUIRE(aln->ctx == ctx, "alignment belongs to another context");
+    MSWB_REQUIRE(storage == MSWB_STORE_F64 || storage == MSWB_STORE_F32, "unknown storage");
+    MSWB_REQUIRE(n_groups >= 1, "the grouping has no groups");
+    MSWB_REQUIRE(zero_inflation > 0.0 && zero_inflation < 1.0, "zero inflation must lie in (0, 1)");
+    MSWB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint64_t T = aln->n_targets;
+    for (uint64_t t = 0; t < T; ++t) MSWB_REQUIRE(group_of_target[t] < n_groups, "group indicator out of range");
+
+    std::unique_ptr<mswb_lik> L(new mswb_lik);
+    L->ctx = ctx;
+    L->K_all = n_groups;
+    L->storage = storage;
+    L->N_total = aln->n_ecs;
+    uint64_t lo, hi;
+    MSWB_REQUIRE(mswb_shard_range(ctx, aln->n_ecs, &lo, &hi) == 0, mswb_last_error());
+    L->ec_begin = lo;
+    L->N = hi - lo;
+    L->n_targets = T;
+    L->from_patterns = true;
+
+    // shard of the pattern CSR, rebased
+    uint64_t p_lo = 0, p_hi = 0;
+    d2h(&p_lo, aln->pat_ptr.p + lo, 1, s);
+    d2h(&p_hi, aln->pat_ptr.p + hi, 1, s);
+    MSWB_CUDA(cudaStreamSynchronize(s));
+    L->pat_ptr.alloc(L->N + 1);
+    rebase_ptr_kernel<<<ctx->n_sms * 2, 256, 0, s>>>(aln->pat_ptr.p + lo, L->pat_ptr.p, L->N + 1, p_lo);
+    MSWB_LAUNCHED();
+    L->pat_targets.alloc(p_hi - p_lo);
+    if (p_hi > p_lo)
+      MSWB_CUDA(cudaMemcpyAsync(L->pat_targets.p, aln->pat_targets.p + p_lo, (p_hi - p_lo) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    L->group_of_target.alloc(T);
+    h2d(L->group_of_target.p, group_of_target, T, s);
+    L->counts.alloc(L->N);
+    u64_to_double_kernel<<<ctx->n_sms * 2, 256, 0, s>>>(aln->count.p + lo, L->counts.p, L->N);
+    MSWB_LAUNCHED();
+    L->sum_counts_total = (double)aln->n_aligned;   // every read with >= 1 hit sits in exactly one class
+
+    const size_t smem = lik_smem_bytes(n_groups);
+    const int grid = fill_grid(ctx, L->N, n_groups);
+    const int aw = lik_active_warps(n_groups);
+
+    // ---- --min-hits mask (include/Likelihood.hpp:141-171) ---------------------------------------
+    L->mask.assign(n_groups, min_hits > 0 ? 0 : 1);
+    if (min_hits > 0) {
+      DevBuf<unsigned long long> hits_dev;
+      hits_dev.alloc(n_groups);
+      MSWB_CUDA(cudaMemsetAsync(hits_dev.p, 0, n_groups * sizeof(unsigned long long), s));
+      prepare_fill_kernel(group_hits_kernel, smem);
+      group_hits_kernel<<<grid, LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->counts.p,
+                                                   L->N, (int)n_groups, aw, hits_dev.p);
+      MSWB_LAUNCHED();
+      ctx->allreduce_sum_u64(hits_dev.p, n_groups);
+      L->hits.resize(n_groups);
+      static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+      d2h((unsigned long long *)L->hits.data(), hits_dev.p, n_groups, s);
+      MSWB_CUDA(cudaStreamSynchronize(s));
+      for (uint32_t g = 0; g < n_groups; ++g) L->mask[g] = L->hits[g] >= min_hits ? 1 : 0;
+    }
+    std::vector<uint64_t> kept_sizes;
+    for (uint32_t g = 0; g < n_groups; ++g)
+      if (L->mask[g]) { L->kept.push_back(g); kept_sizes.push_back(group_sizes[g]); }
+    L->K = (uint32_t)L->kept.size();
+    MSWB_REQUIRE(L->K >= 1, "--min-hits removed every group");
+    L->Kp = (uint32_t)round_up(L->K, 2);
+    L->kept_dev.alloc(L->K);
+    h2d(L->kept_dev.p, L->kept.data(), L->K, s);
+
+    // ---- lookup table (include/Likelihood.hpp:92-107) --------------------------------------------
+    std::vector<uint64_t> off;
+    std::vector<double> lut;
+    build_lut(kept_sizes, q, e, zero_inflation, &off, &lut);
+    L->lut_off.alloc(off.size());
+    L->lut.alloc(lut.size());
+    h2d(L->lut_off.p, off.data(), off.size(), s);
+    h2d(L->lut.p, lut.data(), lut.size(), s);
+
+    // ---- dense gather (include/Likelihood.hpp:176-185), EC-major ---------------------------------
+    if (storage == MSWB_STORE_F64) {
+      L->logl.alloc((size_t)L->N * L->Kp);
+      auto kern = lik_fill_kernel<0, double>;
+      prepare_fill_kernel(kern, smem);
+      kern<<<grid, LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->kept_dev.p, L->lut_off.p,
+                                      L->lut.p, L->N, (int)n_groups, (int)L->K, (int)L->Kp, aw, std::log(zero_inflation), L->logl.p, nullptr);
+    } else {
+      // fp32 storage exists for matrices that do not fit as fp64: go straight to the linear form.
+      L->Kp32 = (uint32_t)round_up(L->K, 4);
+      L->P32.alloc((size_t)L->N * L->Kp32);
+      L->rowmax.alloc(L->N);
+      auto kern = lik_fill_kernel<2, float>;
+      prepare_fill_kernel(kern, smem);
+      kern<<<grid, LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->kept_dev.p, L->lut_off.p,
+                                      L->lut.p, L->N, (int)n_groups, (int)L->K, (int)L->Kp32, aw, std::log(zero_inflation), L->P32.p, L->rowmax.p);
+    }
+    MSWB_LAUNCHED();
+    MSWB_CUDA(cudaStreamSynchronize(s));   // host vectors above go out of scope
+    *out = L.release();
+  });
+}
+
+int mswb_lik_from_dense(mswb_ctx *ctx, const double *logl, uint32_t n_groups, uint64_t n_ecs_local,
+                        const double *log_counts, int storage, mswb_lik **out) {
+  return guarded([&] {
+    MSWB_REQUIRE(ctx && logl && log_counts && out, "NULL argument");
+    MSWB_REQUIRE(storage == MSWB_STORE_F64 || storage == MSWB_STORE_F32, "unknown storage");
+    MSWB_REQUIRE(n_groups >= 1, "the matrix has no groups");
+    MSWB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    std::unique_ptr<mswb_lik> L(new mswb_lik);
+    L->ctx = ctx;
+    L->K_all = L->K = n_groups;
+    L->Kp = (uint32_t)round_up(n_groups, 2);
+    L->N = n_ecs_local;
+    L->storage = storage;
+    L->mask.assign(n_groups, 1);
+    L->kept.resize(n_groups);
+    for (uint32_t g = 0; g < n_groups; ++g) L->kept[g] = g;
+
+    // global class bookkeeping over the ranks
+    DevBuf<double> tmp;
+    tmp.alloc(ctx->world + 1);
+    std::vector<double> sizes(ctx->world, 0.0);
+    sizes[ctx->rank] = (double)n_ecs_local;
+    h2d(tmp.p, sizes.data(), ctx->world, s);
+    ctx->allreduce_sum(tmp.p, ctx->world);
+    d2h(sizes.data(), tmp.p, ctx->world, s);
+    MSWB_CUDA(cudaStreamSynchronize(s));
+    for (int r = 0; r < ctx->world; ++r) { if (r < ctx->rank) L->ec_begin += (uint64_t)sizes[r]; L->N_total += (uint64_t)sizes[r]; }
+
+    // K x N group-major on the host -> N x Kp EC-major on the device
+    const size_t n_el = (size_t)n_groups * n_ecs_local;
+    DevBuf<double> staging;
+    staging.alloc(n_el);
+    h2d(staging.p, logl, n_el, s);
+    L->logl.alloc((size_t)L->N * L->Kp);
+    MSWB_CUDA(cudaMemsetAsync(L->logl.p, 0, L->logl.bytes(), s));
+    transpose<double, double>(staging.p, n_groups, n_ecs_local, n_ecs_local, L->logl.p, L->Kp, s);
+
+    // counts = exp(log_counts) rounded back to the integer they came from when they are one
+    std::vector<double> c(n_ecs_local);
+    long double total = 0.0L;
+    for (uint64_t j = 0; j < n_ecs_local; ++j) {
+      double v = std::exp(log_counts[j]);
+      const double r = std::nearbyint(v);
+      if (std::fabs(v - r) < 1e-9 * std::max(1.0, r)) v = r;
+      c[j] = v;
+      total += v;
+    }
+    L->counts.alloc(n_ecs_local);
+    h2d(L->counts.p, c.data(), n_ecs_local, s);
+    double tot = (double)total;
+    h2d(tmp.p, &tot, 1, s);
+    ctx->allreduce_sum(tmp.p, 1);
+    d2h(&L->sum_counts_total, tmp.p, 1, s);
+    MSWB_CUDA(cudaStreamSynchronize(s));
+    *out = L.release();
+  });
+}
+
+int mswb_lik_info(const mswb_lik *lik, uint32_t *n_groups_all, uint32_t *n_groups_kept, uint64_t *n_ecs_local,
+                  uint64_t *ec_begin, uint64_t *n_ecs_total) {
+  return guarded([&] {
+    MSWB_REQUIRE(lik, "lik is NULL");
+    if (n_groups_all) *n_groups_all = lik->K_all;
+    if (n_groups_kept) *n_groups_kept = lik->K;
+    if (n_ecs_local) *n_ecs_local = lik->N;
+    if (ec_begin) *ec_begin = lik->ec_begin;
+    if (n_ecs_total) *n_ecs_total = lik->N_total;
+  });
+}
+
+int mswb_lik_mask(const mswb_lik *lik, uint8_t *mask, uint64_t *hits) {
+  return guarded([&] {
+    MSWB_REQUIRE(lik, "lik is NULL");
+    if (mask) std::memcpy(mask, lik->mask.data(), lik->K_all);
+    if (hits) {
+      MSWB_REQUIRE(!lik->hits.empty(), "no --min-hits tallies were computed (min_hits == 0)");
+      std::memcpy(hits, lik->hits.data(), lik->K_all * sizeof(uint64_t));
+    }
+  });
+}
+
+int mswb_lik_export_hit_counts(const mswb_lik *lik, uint32_t *out) {
+  return guarded([&] {
+    MSWB_REQUIRE(lik && out, "NULL argument");
+    MSWB_REQUIRE(lik->from_patterns, "this likelihood was not built from class patterns");
+    mswb_ctx *ctx = lik->ctx;
+    MSWB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t n_el = (size_t)lik->N * lik->K_all;
+    if (n_el == 0) return;
+    DevBuf<uint32_t> ecmajor, gmajor;
+    ecmajor.alloc(n_el);
+    gmajor.alloc(n_el);
+    auto kern = lik_fill_kernel<3, uint32_t>;
+    const size_t smem = lik_smem_bytes(lik->K_all);
+    prepare_fill_kernel(kern, smem);
+    kern<<<fill_grid(ctx, lik->N, lik->K_all), LIK_NT, smem, s>>>(lik->pat_ptr.p, lik->pat_targets.p, lik->group_of_target.p, nullptr,
+                                                                  nullptr, nullptr, lik->N, (int)lik->K_all, (int)lik->K_all, (int)lik->K_all,
+                                                                  lik_active_warps(lik->K_all), 0.0, ecmajor.p, nullptr);
+    MSWB_LAUNCHED();
+    transpose<uint32_t, uint32_t>(ecmajor.p, lik->N, lik->K_all, lik->K_all, gmajor.p, lik->N, s);
+    d2h(out, gmajor.p, n_el, s);
+    MSWB_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int mswb_lik_export_logl(const mswb_lik *lik, double *out) {
+  return guarded([&] {
+    MSWB_REQUIRE(lik && out, "NULL argument");
+    MSWB_REQUIRE(lik->logl.p, "the fp64 log-likelihood is not resident (fp32 storage keeps only the linear form)");
+    mswb_ctx *ctx = lik->ctx;
+    MSWB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t n_el = (size_t)lik->N * lik->K;
+    if (n_el == 0) return;
+    DevBuf<double> gmajor;
+    gmajor.alloc(n_el);
+    transpose<double, double>(lik->logl.p, lik->N, lik->K, lik->Kp, gmajor.p, lik->N, s);
+    d2h(out, gmajor.p, n_el, s);
+    MSWB_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+void mswb_lik_destroy(mswb_lik *lik) {
+  if (!lik) return;
+  cudaSetDevice(lik->ctx->device);
+  delete lik;
+}
+
+} // extern "C"

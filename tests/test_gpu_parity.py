@@ -1,0 +1,246 @@
+"""GPU: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs and
+against the frozen fixtures.  Integer artefacts are compared bit-exactly; floating point within the
+tolerances BASELINE.json's north_star states (theta 1e-6 absolute, ELBO 1e-9 relative, fp64)."""
+import os
+
+import numpy as np
+import pytest
+
+from msweep_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+THETA_TOL = 1e-6      # north_star: abundances within 1e-6 absolute
+ELBO_RTOL = 1e-9      # north_star: ELBO within 1e-9 relative (fp64)
+
+
+def _ec_equal(dev, ref):
+    assert np.array_equal(dev.hash, ref.hash)
+    assert np.array_equal(dev.count, ref.count)
+    assert np.array_equal(dev.rep_read, ref.rep_read)
+    assert np.array_equal(dev.pat_ptr, ref.pat_ptr)
+    assert np.array_equal(dev.pat_targets, ref.pat_targets)
+    assert np.array_equal(dev.read_ptr, ref.read_ptr)
+    assert np.array_equal(dev.read_ids, ref.read_ids)
+
+
+CASES = {
+    "tiny": dict(n_reads=64, n_targets=12, n_groups=3, n_present=2, n_templates=4, p_noise=0.1, seed=1),
+    "small": dict(n_reads=5000, n_targets=150, n_groups=10, n_present=3, n_templates=80, p_noise=0.05, seed=2),
+    "oddK": dict(n_reads=8000, n_targets=301, n_groups=7, n_present=4, n_templates=100, p_noise=0.02, seed=3),
+    "wideK": dict(n_reads=6000, n_targets=3000, n_groups=300, n_present=6, n_templates=60, p_noise=0.02, seed=4),
+    "c1_like": dict(n_reads=60000, n_targets=3000, n_groups=50, n_present=5, n_templates=400, p_noise=0.02, seed=5),
+}
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request, oracle, mswb, ctx):
+    wl = synth.generate(**CASES[request.param])
+    ec = oracle.ec_build_csr(wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    aln = mswb.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    return request.param, wl, ec, aln
+
+
+def test_ec_table_bit_exact(case):
+    _, wl, ec, aln = case
+    assert aln.n_ecs == ec.n_ecs and aln.n_reads == wl.n_reads
+    assert aln.n_aligned == int(ec.count.sum())
+    _ec_equal(aln.export(), ec)
+
+
+def test_hit_counts_and_logl(case, oracle, mswb, ctx):
+    _, wl, ec, aln = case
+    ref = oracle.lik_build(ec, wl.group_of_target, wl.group_sizes, keep_hit_counts=True)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+    assert (lik.n_groups_all, lik.n_groups, lik.n_ecs) == (wl.n_groups, ref.n_groups, ec.n_ecs)
+    assert np.array_equal(lik.export_hit_counts(), ref.hit_counts)          # integers: bit-exact
+    got = lik.export_logl()
+    assert np.array_equal(got, ref.logl)       # same libm calls on the host-built table: identical doubles
+    assert np.all(lik.mask() == 1)
+
+
+@pytest.mark.parametrize("min_hits", [1, 3, 50])
+def test_min_hits_mask(case, oracle, mswb, ctx, min_hits):
+    _, wl, ec, aln = case
+    ref = oracle.lik_build(ec, wl.group_of_target, wl.group_sizes, min_hits=min_hits)
+    if ref.n_groups == 0:
+        with pytest.raises(mswb.MswbError, match="removed every group"):
+            mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, min_hits=min_hits)
+        return
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, min_hits=min_hits)
+    mask, hits = lik.mask(want_hits=True)
+    assert np.array_equal(hits, ref.hits)
+    assert np.array_equal(mask, ref.mask)
+    assert lik.n_groups == ref.n_groups
+    assert np.array_equal(lik.export_logl(), ref.logl)
+
+
+@pytest.mark.parametrize("algo", ["rcg", "em"])
+def test_vi_parity(case, oracle, mswb, ctx, algo):
+    name, wl, ec, aln = case
+    ref_l = oracle.lik_build(ec, wl.group_of_target, wl.group_sizes)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+    ref = oracle.vi_run(algo, ref_l.logl, ref_l.log_counts, tol=1e-6, max_iters=5000)
+    got = lik.vi_run(mswb.ALGO_RCG if algo == "rcg" else mswb.ALGO_EM, tol=1e-6, max_iters=5000)
+    assert got.converged == ref.converged
+    assert got.iters == ref.iters, (got.iters, ref.iters)
+    assert np.max(np.abs(got.theta - ref.theta)) < THETA_TOL
+    assert abs(got.bound - ref.bound) <= ELBO_RTOL * abs(ref.bound)
+    assert got.theta.sum() == pytest.approx(1.0, abs=1e-12)
+
+
+def test_rcg_trajectory_and_posteriors(case, oracle, mswb, ctx):
+    """Same trajectory, not just same optimum: bound per iteration, restarts, final log-posteriors."""
+    name, wl, ec, aln = case
+    ref_l = oracle.lik_build(ec, wl.group_of_target, wl.group_sizes)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+    ref = oracle.vi_run("rcg", ref_l.logl, ref_l.log_counts, tol=1e-6, max_iters=40, want_gamma=True)
+    s = lik.vi_begin(mswb.ALGO_RCG, tol=1e-6, max_iters=40)
+    s.step(40)
+    tb, tg, tr = s.trace()
+    got = s.finish()
+    assert got.iters == ref.iters
+    assert np.array_equal(tr, ref.trace_reset)
+    assert np.max(np.abs(tb - ref.trace_bound) / np.abs(ref.trace_bound)) < ELBO_RTOL
+    assert np.allclose(tg, ref.trace_gnorm, rtol=1e-6, atol=1e-9)
+    gam = lik.posteriors()
+    big = ref.gamma > -30            # log-posteriors of any weight; far tails are exp-underflow noise
+    assert np.max(np.abs(gam[big] - ref.gamma[big])) < 1e-8
+    assert np.max(np.abs(np.exp(gam) - np.exp(ref.gamma))) < 1e-9
+    assert np.max(np.abs(got.N_k - ref.N_k)) < 1e-6 * max(1.0, ref.N_k.max())
+
+
+def test_em_posteriors(case, oracle, mswb, ctx):
+    name, wl, ec, aln = case
+    ref_l = oracle.lik_build(ec, wl.group_of_target, wl.group_sizes)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+    ref = oracle.vi_run("em", ref_l.logl, ref_l.log_counts, tol=1e-6, max_iters=25, want_gamma=True)
+    got = lik.vi_run(mswb.ALGO_EM, tol=1e-6, max_iters=25)
+    assert got.iters == ref.iters
+    gam = lik.posteriors()
+    assert np.max(np.abs(np.exp(gam) - np.exp(ref.gamma))) < 1e-9
+
+
+def test_fp32_storage_tolerance(case, oracle, mswb, ctx):
+    """fp32 storage of the linear-domain likelihood (EM only), fp64 accumulation across classes.
+    Tolerance stated separately, as north_star asks: theta 1e-6 absolute, ELBO 1e-7 relative."""
+    name, wl, ec, aln = case
+    ref_l = oracle.lik_build(ec, wl.group_of_target, wl.group_sizes)
+    ref = oracle.vi_run("em", ref_l.logl, ref_l.log_counts, tol=1e-6, max_iters=60)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=mswb.STORE_F32)
+    got = lik.vi_run(mswb.ALGO_EM, tol=1e-6, max_iters=60)
+    assert np.max(np.abs(got.theta - ref.theta)) < 1e-6
+    assert abs(got.bound - ref.bound) <= 1e-7 * abs(ref.bound)
+    with pytest.raises(mswb.MswbError, match="RCG needs"):
+        lik.vi_run(mswb.ALGO_RCG)
+
+
+def test_golden_fixture(mswb, ctx):
+    """The frozen numbers (no oracle at run time)."""
+    g = np.load(os.path.join(GOLD, "small_case.npz"))
+    aln = mswb.Alignment(ctx, int(g["n_reads"]), int(g["n_targets"]), g["row_ptr"], g["targets"])
+    e = aln.export()
+    assert np.array_equal(e.hash, g["ec_hash"]) and np.array_equal(e.count, g["ec_count"])
+    assert np.array_equal(e.rep_read, g["ec_rep_read"]) and np.array_equal(e.pat_targets, g["ec_pat_targets"])
+    assert np.array_equal(e.read_ids, g["ec_read_ids"])
+    lik = mswb.Likelihood.build(ctx, aln, g["group_of_target"], g["group_sizes"])
+    assert np.array_equal(lik.export_hit_counts(), g["hit_counts"])
+    assert np.array_equal(lik.export_logl(), g["logl"])
+    lik1 = mswb.Likelihood.build(ctx, aln, g["group_of_target"], g["group_sizes"], min_hits=1)
+    m, h = lik1.mask(want_hits=True)
+    assert np.array_equal(m, g["mask_minhits1"]) and np.array_equal(h, g["hits_minhits1"])
+    r = lik.vi_run(mswb.ALGO_RCG)
+    assert r.iters == int(g["rcg_iters"])
+    assert np.max(np.abs(r.theta - g["rcg_theta"])) < THETA_TOL
+    assert abs(r.bound - float(g["rcg_bound"])) <= ELBO_RTOL * abs(float(g["rcg_bound"]))
+    em = lik.vi_run(mswb.ALGO_EM)
+    assert em.iters == int(g["em_iters"])
+    assert np.max(np.abs(em.theta - g["em_theta"])) < THETA_TOL
+    assert np.array_equal(lik.bootstrap_resample(int(g["boot_seed"]), 3), g["boot_counts"])
+
+
+# ---- edge cases ---------------------------------------------------------------------------------
+def test_empty_and_degenerate_inputs(oracle, mswb, ctx):
+    # all reads unaligned
+    aln = mswb.Alignment(ctx, 5, 9, np.zeros(6, np.uint64), np.zeros(0, np.uint32))
+    assert (aln.n_ecs, aln.n_aligned, aln.n_reads) == (0, 0, 5)
+    # zero reads
+    aln = mswb.Alignment(ctx, 0, 9, np.zeros(1, np.uint64), np.zeros(0, np.uint32))
+    assert aln.n_ecs == 0
+    # a single read, single target
+    aln = mswb.Alignment(ctx, 1, 9, np.array([0, 1], np.uint64), np.array([4], np.uint32))
+    e = aln.export()
+    assert list(e.hash) == [oracle.pattern_hash([4])] and list(e.count) == [1]
+    # unsorted row is rejected, not silently mis-hashed
+    with pytest.raises(mswb.MswbError, match="ascending"):
+        mswb.Alignment(ctx, 1, 9, np.array([0, 2], np.uint64), np.array([5, 3], np.uint32))
+    with pytest.raises(mswb.MswbError, match="ascending"):
+        mswb.Alignment(ctx, 1, 9, np.array([0, 1], np.uint64), np.array([9], np.uint32))
+
+
+def test_equal_patterns_far_apart_merge(oracle, mswb, ctx):
+    rng = np.random.default_rng(3)
+    rows = [sorted(rng.choice(500, size=int(n), replace=False).tolist()) for n in rng.integers(0, 30, size=4000)]
+    for i in range(0, 4000, 7):
+        rows[i] = rows[(i * 13) % 4000]
+    ptr = np.cumsum([0] + [len(r) for r in rows]).astype(np.uint64)
+    tg = np.array([t for r in rows for t in r], np.uint32)
+    _ec_equal(mswb.Alignment(ctx, len(rows), 500, ptr, tg).export(), oracle.ec_build_csr(len(rows), 500, ptr, tg))
+
+
+@pytest.mark.parametrize("K,N", [(1, 37), (2, 1), (3, 1000), (33, 513), (65, 2049), (129, 700), (257, 300), (600, 200),
+                                 (1100, 150), (2100, 64)])
+def test_dense_entry_all_tile_shapes(oracle, mswb, ctx, K, N):
+    """mswb_lik_from_dense over every compiled tile shape, ragged N, non-uniform prior, zero-count classes."""
+    rng = np.random.default_rng(K * 1000 + N)
+    logl = rng.normal(-6.0, 2.5, size=(K, N))
+    logl[rng.integers(0, K, size=N), np.arange(N)] = rng.normal(-0.5, 0.2, size=N)   # every class has a likely group
+    counts = rng.integers(1, 50, size=N).astype(np.float64)
+    lc = np.log(counts)
+    if N > 10:
+        lc[::5] = -np.inf                       # bootstrap-style unobserved classes
+    alpha0 = rng.uniform(0.5, 2.0, size=K)
+    lik = mswb.Likelihood.from_dense(ctx, logl, np.where(np.isfinite(lc), lc, 0.0))
+    assert np.array_equal(lik.export_logl(), logl)
+    for algo, code in (("rcg", mswb.ALGO_RCG), ("em", mswb.ALGO_EM)):
+        if algo == "rcg" and K == 1:
+            continue
+        ref = oracle.vi_run(algo, logl, lc, alpha0=alpha0, tol=1e-7, max_iters=30)
+        got = lik.vi_run(code, alpha0=alpha0, log_counts=lc, tol=1e-7, max_iters=30)
+        assert got.iters == ref.iters
+        assert np.max(np.abs(got.theta - ref.theta)) < THETA_TOL
+        assert abs(got.bound - ref.bound) <= ELBO_RTOL * abs(ref.bound)
+
+
+def test_bootstrap_counts_bit_exact(oracle, mswb, ctx):
+    wl = synth.generate(20000, 200, 10, n_present=3, n_templates=300, seed=8)
+    ec = oracle.ec_build_csr(wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    aln = mswb.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+    for seed in (1, 42, -7):
+        assert np.array_equal(lik.bootstrap_resample(seed, 4), oracle.bootstrap_resample(ec.count, seed, 4))
+    assert np.array_equal(lik.bootstrap_resample(5, 2, bootstrap_count=777), oracle.bootstrap_resample(ec.count, 5, 2, 777))
+    ph = lik.bootstrap_resample(5, 2, rng_mode=mswb.RNG_PHILOX)
+    assert list(ph.sum(axis=1)) == [int(ec.count.sum())] * 2 and not np.array_equal(ph[0], ph[1])
+
+
+def test_bootstrap_run_matches_reference_loop(oracle, mswb, ctx):
+    """src/mSWEEP.cpp:496-518: resample, re-estimate from a cold start, once per replicate."""
+    wl = synth.generate(8000, 120, 6, n_present=3, n_templates=80, seed=12)
+    ec = oracle.ec_build_csr(wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    ref_l = oracle.lik_build(ec, wl.group_of_target, wl.group_sizes)
+    aln = mswb.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+    B = 5
+    thetas, iters = lik.bootstrap_run(B, seed=99)
+    counts = oracle.bootstrap_resample(ec.count, 99, B)
+    for r in range(B):
+        with np.errstate(divide="ignore"):
+            ref = oracle.vi_run("rcg", ref_l.logl, np.log(counts[r].astype(np.float64)))
+        assert iters[r] == ref.iters
+        assert np.max(np.abs(thetas[r] - ref.theta)) < THETA_TOL
+    # replicas spread over two "GPUs": each computes its own rows, the union equals the single run
+    t0, _ = lik.bootstrap_run(B, seed=99, replica_rank=0, replica_world=2)
+    t1, _ = lik.bootstrap_run(B, seed=99, replica_rank=1, replica_world=2)
+    merged = np.where(np.isnan(t0), t1, t0)
+    assert np.array_equal(merged, thetas)
