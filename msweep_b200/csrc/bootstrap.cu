@@ -188,7 +188,8 @@ int mswb_bootstrap_run(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const
     DevBuf<unsigned> hist;
     DevBuf<double> counts;
     hist.alloc(rs.N);
-    counts.alloc(rs.N);
+    counts.alloc(lik->N_pad);
+    MSWB_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes(), ctx->stream));
     for (uint64_t r = 0; r < n_replicates; ++r) {
       if ((int)(r % (uint64_t)replica_world) != replica_rank) { rs.skip(); continue; }   // another GPU's replicate
       rs.next(r, hist.p);

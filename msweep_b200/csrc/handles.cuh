@@ -28,6 +28,7 @@ struct mswb_lik {
   uint32_t K = 0;              // groups kept after --min-hits (rows of the reference's matrix)
   uint32_t Kp = 0;             // device row stride in elements
   uint64_t N = 0;              // classes in this rank's shard
+  uint64_t N_pad = 0;          // N rounded up to ROW_PAD (64): counts / rowmax / P carry zero rows up to here
   uint64_t ec_begin = 0;       // first global class index of the shard
   uint64_t N_total = 0;        // classes over all ranks
   int storage = MSWB_STORE_F64;
@@ -47,7 +48,7 @@ struct mswb_lik {
   uint64_t n_targets = 0;
   bool from_patterns = false;
 
-  mswb::DevBuf<double> counts;   // [N] class counts c_j as doubles
+  mswb::DevBuf<double> counts;   // [N_pad] class counts c_j as doubles (0 in the padding)
   mswb::DevBuf<double> logl;     // [N x Kp] log-likelihood (RCG, exports); may be empty in F32 storage
   mswb::DevBuf<double> rowmax;   // [N] M_j = max_k logl(j, k)              (linear-domain EM)
   mswb::DevBuf<double> P64;      // [N x Kp] exp(logl - M_j)                 (EM, F64 storage)

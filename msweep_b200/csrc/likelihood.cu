@@ -212,6 +212,7 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
     MSWB_REQUIRE(mswb_shard_range(ctx, aln->n_ecs, &lo, &hi) == 0, mswb_last_error());
     L->ec_begin = lo;
     L->N = hi - lo;
+    L->N_pad = round_up(L->N, 64);
     L->n_targets = T;
     L->from_patterns = true;
 
@@ -228,7 +229,8 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
       MSWB_CUDA(cudaMemcpyAsync(L->pat_targets.p, aln->pat_targets.p + p_lo, (p_hi - p_lo) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     L->group_of_target.alloc(T);
     h2d(L->group_of_target.p, group_of_target, T, s);
-    L->counts.alloc(L->N);
+    L->counts.alloc(L->N_pad);
+    MSWB_CUDA(cudaMemsetAsync(L->counts.p, 0, L->counts.bytes(), s));
     u64_to_double_kernel<<<ctx->n_sms * 2, 256, 0, s>>>(aln->count.p + lo, L->counts.p, L->N);
     MSWB_LAUNCHED();
     L->sum_counts_total = (double)aln->n_aligned;   // every read with >= 1 hit sits in exactly one class
@@ -282,8 +284,11 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
     } else {
       // fp32 storage exists for matrices that do not fit as fp64: go straight to the linear form.
       L->Kp32 = (uint32_t)round_up(L->K, 4);
-      L->P32.alloc((size_t)L->N * L->Kp32);
-      L->rowmax.alloc(L->N);
+      L->P32.alloc((size_t)L->N_pad * L->Kp32);
+      L->rowmax.alloc(L->N_pad);
+      if (L->N_pad > L->N)
+        MSWB_CUDA(cudaMemsetAsync(L->P32.p + (size_t)L->N * L->Kp32, 0, (size_t)(L->N_pad - L->N) * L->Kp32 * sizeof(float), s));
+      MSWB_CUDA(cudaMemsetAsync(L->rowmax.p, 0, L->rowmax.bytes(), s));
       auto kern = lik_fill_kernel<2, float>;
       prepare_fill_kernel(kern, smem);
       kern<<<grid, LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->kept_dev.p, L->lut_off.p,
@@ -308,6 +313,7 @@ int mswb_lik_from_dense(mswb_ctx *ctx, const double *logl, uint32_t n_groups, ui
     L->K_all = L->K = n_groups;
     L->Kp = (uint32_t)round_up(n_groups, 2);
     L->N = n_ecs_local;
+    L->N_pad = round_up(n_ecs_local, 64);
     L->storage = storage;
     L->mask.assign(n_groups, 1);
     L->kept.resize(n_groups);
@@ -343,7 +349,8 @@ int mswb_lik_from_dense(mswb_ctx *ctx, const double *logl, uint32_t n_groups, ui
       c[j] = v;
       total += v;
     }
-    L->counts.alloc(n_ecs_local);
+    L->counts.alloc(L->N_pad);
+    MSWB_CUDA(cudaMemsetAsync(L->counts.p, 0, L->counts.bytes(), s));
     h2d(L->counts.p, c.data(), n_ecs_local, s);
     double tot = (double)total;
     h2d(tmp.p, &tot, 1, s);

@@ -115,7 +115,8 @@ __global__ void rcg_ctl_a_kernel(ViArrays a, ViCtl *ctl, int K, const double *pa
     ctl->newnorm = nn;
     ctl->oldnorm = nn;
     ctl->beta = beta;
-    ctl->use_old = (!ctl->didreset && beta > 0.0) ? 1 : 0;
+    // the direction memory is empty before the first accepted step (the reference starts it at zero)
+    ctl->use_old = (!ctl->didreset && beta > 0.0 && ctl->iter > 0) ? 1 : 0;
     ctl->didreset = 0;
   }
 }
@@ -284,25 +285,50 @@ struct mswb_vi {
 namespace {
 
 // ---- tile dispatch ---------------------------------------------------------------------------------
-// slots = 16-byte vectors per row.  (TPR, KITER) is the smallest shape that covers the row; R trades
-// registers for loads in flight (EM keeps one array live, the RCG sweeps two or three).
-#define MSWB_TILE_DISPATCH(slots, RA, RB, ...)                                               \
+// slots = 16-byte vectors per row.  (TPR, KITER) is the smallest shape that covers the row; R (rows per
+// thread group and batch) trades registers and stage size for fewer row reductions: RS for narrow rows
+// (several row groups per CTA), RM for the 256x4 shape, RL for KITER = 8.
+#define MSWB_TILE_DISPATCH(slots, RS, RM, RL, ...)                                            \
   do {                                                                                       \
-    if ((slots) <= 32) { using TL = Tile<32, 1, RA>; __VA_ARGS__; }                                 \
-    else if ((slots) <= 64) { using TL = Tile<32, 2, RA>; __VA_ARGS__; }                            \
-    else if ((slots) <= 128) { using TL = Tile<32, 4, RA>; __VA_ARGS__; }                           \
-    else if ((slots) <= 256) { using TL = Tile<64, 4, RA>; __VA_ARGS__; }                           \
-    else if ((slots) <= 512) { using TL = Tile<128, 4, RA>; __VA_ARGS__; }                          \
-    else if ((slots) <= 1024) { using TL = Tile<256, 4, RA>; __VA_ARGS__; }                         \
-    else if ((slots) <= 2048) { using TL = Tile<256, 8, RB>; __VA_ARGS__; }                         \
-    else if ((slots) <= 4096) { using TL = Tile<512, 8, RB>; __VA_ARGS__; }                         \
-    else if ((slots) <= 8192) { using TL = Tile<1024, 8, RB>; __VA_ARGS__; }                        \
+    if ((slots) <= 32) { using TL = Tile<32, 1, RS>; __VA_ARGS__; }                          \
+    else if ((slots) <= 64) { using TL = Tile<32, 2, RS>; __VA_ARGS__; }                     \
+    else if ((slots) <= 128) { using TL = Tile<32, 4, RS>; __VA_ARGS__; }                    \
+    else if ((slots) <= 256) { using TL = Tile<64, 4, RS>; __VA_ARGS__; }                    \
+    else if ((slots) <= 512) { using TL = Tile<128, 4, RS>; __VA_ARGS__; }                   \
+    else if ((slots) <= 1024) { using TL = Tile<256, 4, RM>; __VA_ARGS__; }                  \
+    else if ((slots) <= 2048) { using TL = Tile<256, 8, RL>; __VA_ARGS__; }                  \
+    else if ((slots) <= 4096) { using TL = Tile<512, 8, 1>; __VA_ARGS__; }                   \
+    else if ((slots) <= 8192) { using TL = Tile<1024, 8, 1>; __VA_ARGS__; }                  \
     else throw Error("too many groups for the compiled tile shapes (max 16384 in fp64)");   \
   } while (0)
 
-template <class Kern> int persistent_grid(mswb_ctx *ctx, Kern kern, int nt, uint64_t n_batches, int max_grid) {
+constexpr size_t SMEM_BUDGET = 200 * 1024;   // dynamic shared memory for the stage ring (of 227 KB per CTA)
+
+// Stage ring geometry for a sweep that streams `nsrc` arrays with rows of `row_bytes`, consumed in
+// units of `unit_rows` (= G*R).  stages == 0: the rows are too long to stage, use the direct kernel.
+PipeGeom pipe_geometry(size_t row_bytes, int unit_rows, int nsrc, int tpr) {
+  PipeGeom g{0, 0, 0};
+  if (tpr > 256) return g;
+  if (const char *e = getenv("MSWB_NO_TMA")) { if (e[0] == '1') return g; }
+  const size_t unit_bytes = (size_t)unit_rows * row_bytes;
+  size_t target = 32 * 1024;
+  if (const char *e = getenv("MSWB_STAGE_KB")) target = (size_t)atoi(e) * 1024;
+  const int units = (int)std::max<size_t>(1, target / unit_bytes);
+  g.stage_rows = unit_rows * units;
+  g.stage_pitch = (unsigned)round_up((size_t)g.stage_rows * row_bytes, 128);
+  const size_t per_stage = (size_t)nsrc * g.stage_pitch + 8;
+  int stages = (int)std::min<size_t>(8, SMEM_BUDGET / per_stage);
+  if (const char *e = getenv("MSWB_STAGES")) stages = std::min(stages, atoi(e));
+  g.stages = stages >= 2 ? stages : 0;
+  return g;
+}
+size_t pipe_smem_bytes(const PipeGeom &g, int nsrc) { return (size_t)g.stages * nsrc * g.stage_pitch + (size_t)g.stages * 8; }
+
+// Persistent grid: as many CTAs as are resident at once (one per SM for the staged kernels).
+template <class Kern> int persistent_grid(mswb_ctx *ctx, Kern kern, int nt, size_t smem, uint64_t n_batches, int max_grid) {
+  if (smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
-  MSWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, 0));
+  MSWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
   if (per_sm < 1) per_sm = 1;
   uint64_t g = (uint64_t)ctx->n_sms * per_sm;
   if (g > n_batches) g = n_batches;
@@ -333,40 +359,68 @@ void launch_finalize(mswb_vi *vi, int nvals, int only_if_reset) {
   MSWB_LAUNCHED();
 }
 
+// Launch one sweep: the staged (TMA) instantiation when the geometry allows, else the direct one.
+// KERN(PIPE) names the kernel template instantiation; ARGS are its arguments before the PipeGeom.
+#define MSWB_LAUNCH_SWEEP(KERN_PIPE, KERN_DIRECT, ROW_BYTES, NSRC, ...)                                        \
+  do {                                                                                                         \
+    const PipeGeom geom = pipe_geometry((ROW_BYTES), TL::G * TL::R, (NSRC), TL::TPR);                          \
+    if (geom.stages) {                                                                                         \
+      auto kern = KERN_PIPE;                                                                                   \
+      const size_t smem = pipe_smem_bytes(geom, (NSRC));                                                       \
+      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N, (uint64_t)geom.stage_rows), vi->max_grid); \
+      kern<<<vi->grid, TL::NT, smem, s>>>(__VA_ARGS__, geom);                                                  \
+    } else {                                                                                                   \
+      auto kern = KERN_DIRECT;                                                                                 \
+      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, ceil_div(L->N, (uint64_t)TL::G * TL::R), vi->max_grid); \
+      kern<<<vi->grid, TL::NT, 0, s>>>(__VA_ARGS__, geom);                                                     \
+    }                                                                                                          \
+    MSWB_LAUNCHED();                                                                                           \
+  } while (0)
+
+// EM sweep launch: staged (TMA) when asked for and possible, else direct + register prefetch.
+#define MSWB_LAUNCH_EM(ST, PTR, LD)                                                                            \
+  do {                                                                                                         \
+    PipeGeom geom = want_pipe ? pipe_geometry((size_t)(LD) * sizeof(ST), TL::G * TL::R, 1, TL::TPR) : PipeGeom{0, 0, 0}; \
+    if (geom.stages) {                                                                                         \
+      auto kern = em_lin_pass_kernel<ST, TL, true>;                                                      \
+      const size_t smem = pipe_smem_bytes(geom, 1);                                                            \
+      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N_pad, (uint64_t)geom.stage_rows), vi->max_grid); \
+      kern<<<vi->grid, TL::NT, smem, s>>>(PTR, (int)(LD), L->rowmax.p, vi->counts, vi->w.p, vi->ctl.p, vi->partials.p, \
+                                          vi->pstride, L->N_pad, K, geom);                                      \
+    } else {                                                                                                   \
+      auto kern = em_lin_pass_kernel<ST, TL, false>;                                                     \
+      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, L->N_pad / (TL::G * TL::R), vi->max_grid);            \
+      kern<<<vi->grid, TL::NT, 0, s>>>(PTR, (int)(LD), L->rowmax.p, vi->counts, vi->w.p, vi->ctl.p, vi->partials.p, \
+                                       vi->pstride, L->N_pad, K, geom);                                         \
+    }                                                                                                          \
+    MSWB_LAUNCHED();                                                                                           \
+  } while (0)
+
 void em_iteration(mswb_vi *vi) {
   mswb_lik *L = vi->lik;
   cudaStream_t s = vi->ctx->stream;
   const int K = vi->K;
   PassTimer timer(vi);
+  // Measured on B200 (1e6 x 2000, profiles/): direct loads + register prefetch beat the staged (TMA) form
+  // for this sweep (6.5-6.7 vs 5.2 TB/s); MSWB_EM_TMA=1 / MSWB_EM_R select the alternatives for experiments.
+  int rsel = 0;
+  bool want_pipe = false;
+  if (const char *e = getenv("MSWB_EM_R")) rsel = atoi(e);
+  if (const char *e = getenv("MSWB_EM_TMA")) want_pipe = e[0] == '1';
   if (vi->linear && L->storage == MSWB_STORE_F32) {
-    const int slots = L->Kp32 / 4;
-    MSWB_TILE_DISPATCH(slots, 4, 2, {
-      auto kern = em_lin_pass_kernel<float, TL>;
-      const uint64_t nb = ceil_div(L->N, (uint64_t)TL::G * TL::R);
-      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, nb, vi->max_grid);
-      kern<<<vi->grid, TL::NT, 0, s>>>(L->P32.p, (int)L->Kp32, L->rowmax.p, vi->counts, vi->w.p, vi->ctl.p, vi->partials.p,
-                                       vi->pstride, L->N, K);
-    });
+    if (rsel == 1) MSWB_TILE_DISPATCH(L->Kp32 / 4, 1, 1, 1, MSWB_LAUNCH_EM(float, L->P32.p, L->Kp32));
+    else if (rsel == 2) MSWB_TILE_DISPATCH(L->Kp32 / 4, 2, 2, 1, MSWB_LAUNCH_EM(float, L->P32.p, L->Kp32));
+    else MSWB_TILE_DISPATCH(L->Kp32 / 4, 4, 4, 2, MSWB_LAUNCH_EM(float, L->P32.p, L->Kp32));
   } else if (vi->linear) {
-    const int slots = L->Kp / 2;
-    MSWB_TILE_DISPATCH(slots, 4, 2, {
-      auto kern = em_lin_pass_kernel<double, TL>;
-      const uint64_t nb = ceil_div(L->N, (uint64_t)TL::G * TL::R);
-      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, nb, vi->max_grid);
-      kern<<<vi->grid, TL::NT, 0, s>>>(L->P64.p, (int)L->Kp, L->rowmax.p, vi->counts, vi->w.p, vi->ctl.p, vi->partials.p,
-                                       vi->pstride, L->N, K);
-    });
+    if (rsel == 1) MSWB_TILE_DISPATCH(L->Kp / 2, 1, 1, 1, MSWB_LAUNCH_EM(double, L->P64.p, L->Kp));
+    else if (rsel == 4) MSWB_TILE_DISPATCH(L->Kp / 2, 4, 4, 2, MSWB_LAUNCH_EM(double, L->P64.p, L->Kp));
+    else MSWB_TILE_DISPATCH(L->Kp / 2, 4, 2, 2, MSWB_LAUNCH_EM(double, L->P64.p, L->Kp));
   } else {
-    const int slots = L->Kp / 2;
-    MSWB_TILE_DISPATCH(slots, 2, 1, {
-      auto kern = rcg_sweep_b_kernel<TL, 1, false>;
-      const uint64_t nb = ceil_div(L->N, (uint64_t)TL::G * TL::R);
-      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, nb, vi->max_grid);
-      kern<<<vi->grid, TL::NT, 0, s>>>(L->logl.p, nullptr, nullptr, (int)L->Kp, vi->dg.p, vi->counts, vi->ctl.p,
-                                       vi->partials.p, vi->pstride, L->N, K, 0);
-    });
+    MSWB_TILE_DISPATCH(L->Kp / 2, 2, 1, 1,
+      MSWB_LAUNCH_SWEEP((rcg_sweep_b_kernel<TL, 1, false, true>), (rcg_sweep_b_kernel<TL, 1, false, false>), (size_t)L->Kp * 8, 3,
+                        L->logl.p, (double *)nullptr, (double *)nullptr, (int)L->Kp, vi->dg.p, vi->counts, vi->ctl.p,
+                        vi->partials.p, vi->pstride, L->N, K, 0));
   }
-  MSWB_LAUNCHED();
   timer.stop();
   launch_finalize(vi, K + 1, 0);
   vi->ctx->allreduce_sum(vi->red.p, K + 1);
@@ -381,16 +435,13 @@ void rcg_iteration(mswb_vi *vi) {
   const int K = vi->K;
   const int slots = L->Kp / 2;
   const int ld = (int)L->Kp;
+  const size_t row_bytes = (size_t)L->Kp * 8;
   // sweep A: gradient norm
   {
     PassTimer timer(vi);
-    MSWB_TILE_DISPATCH(slots, 2, 1, {
-      auto kern = rcg_sweep_a_kernel<TL>;
-      const uint64_t nb = ceil_div(L->N, (uint64_t)TL::G * TL::R);
-      vi->grid = persistent_grid(ctx, kern, TL::NT, nb, vi->max_grid);
-      kern<<<vi->grid, TL::NT, 0, s>>>(L->logl.p, L->gamma.p, ld, vi->dg.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N, K);
-    });
-    MSWB_LAUNCHED();
+    MSWB_TILE_DISPATCH(slots, 2, 2, 1,
+      MSWB_LAUNCH_SWEEP((rcg_sweep_a_kernel<TL, true>), (rcg_sweep_a_kernel<TL, false>), row_bytes, 2,
+                        L->logl.p, L->gamma.p, ld, vi->dg.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N, K));
     timer.stop();
   }
   if (ctx->world > 1) {
@@ -405,14 +456,10 @@ void rcg_iteration(mswb_vi *vi) {
   // sweep B: step, renormalise, N_k, bound
   {
     PassTimer timer(vi);
-    MSWB_TILE_DISPATCH(slots, 2, 1, {
-      auto kern = rcg_sweep_b_kernel<TL, 0, true>;
-      const uint64_t nb = ceil_div(L->N, (uint64_t)TL::G * TL::R);
-      vi->grid = persistent_grid(ctx, kern, TL::NT, nb, vi->max_grid);
-      kern<<<vi->grid, TL::NT, 0, s>>>(L->logl.p, L->gamma.p, L->step.p, ld, vi->dg.p, vi->counts, vi->ctl.p,
-                                       vi->partials.p, vi->pstride, L->N, K, 0);
-    });
-    MSWB_LAUNCHED();
+    MSWB_TILE_DISPATCH(slots, 2, 1, 1,
+      MSWB_LAUNCH_SWEEP((rcg_sweep_b_kernel<TL, 0, true, true>), (rcg_sweep_b_kernel<TL, 0, true, false>), row_bytes, 3,
+                        L->logl.p, L->gamma.p, L->step.p, ld, vi->dg.p, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride,
+                        L->N, K, 0));
     timer.stop();
   }
   launch_finalize(vi, K + 1, 0);
@@ -420,14 +467,10 @@ void rcg_iteration(mswb_vi *vi) {
   rcg_ctl_b_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, 0);
   MSWB_LAUNCHED();
   // restart sweep: runs only when the control block says so (device-side decision, no host round trip)
-  MSWB_TILE_DISPATCH(slots, 2, 1, {
-    auto kern = rcg_sweep_b_kernel<TL, 1, true>;
-    const uint64_t nb = ceil_div(L->N, (uint64_t)TL::G * TL::R);
-    vi->grid = persistent_grid(ctx, kern, TL::NT, nb, vi->max_grid);
-    kern<<<vi->grid, TL::NT, 0, s>>>(L->logl.p, L->gamma.p, L->step.p, ld, vi->dg.p, vi->counts, vi->ctl.p,
-                                     vi->partials.p, vi->pstride, L->N, K, 1);
-  });
-  MSWB_LAUNCHED();
+  MSWB_TILE_DISPATCH(slots, 2, 1, 1,
+    MSWB_LAUNCH_SWEEP((rcg_sweep_b_kernel<TL, 1, true, true>), (rcg_sweep_b_kernel<TL, 1, true, false>), row_bytes, 3,
+                      L->logl.p, L->gamma.p, L->step.p, ld, vi->dg.p, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride,
+                      L->N, K, 1));
   launch_finalize(vi, K + 1, 1);
   ctx->allreduce_sum(vi->red.p, K + 1);
   rcg_ctl_b_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, 1);
@@ -450,19 +493,26 @@ double device_sum(mswb_vi *vi, const double *c, size_t n) {
 
 void ensure_linear(mswb_lik *L) {
   mswb_ctx *ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
   if (L->storage == MSWB_STORE_F32) {
     if (L->P32.p) return;
     MSWB_REQUIRE(L->logl.p, "likelihood holds neither logl nor P");
     L->Kp32 = (uint32_t)round_up(L->K, 4);
-    L->P32.alloc((size_t)L->N * L->Kp32);
-    L->rowmax.alloc(L->N);
-    to_linear_kernel<float><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(L->logl.p, (int)L->Kp, L->P32.p, (int)L->Kp32, L->rowmax.p, L->N, (int)L->K);
+    L->P32.alloc((size_t)L->N_pad * L->Kp32);
+    L->rowmax.alloc(L->N_pad);
+    if (L->N_pad > L->N)
+      MSWB_CUDA(cudaMemsetAsync(L->P32.p + (size_t)L->N * L->Kp32, 0, (size_t)(L->N_pad - L->N) * L->Kp32 * sizeof(float), s));
+    MSWB_CUDA(cudaMemsetAsync(L->rowmax.p, 0, L->rowmax.bytes(), s));
+    to_linear_kernel<float><<<ctx->n_sms * 8, 256, 0, s>>>(L->logl.p, (int)L->Kp, L->P32.p, (int)L->Kp32, L->rowmax.p, L->N, (int)L->K);
   } else {
     if (L->P64.p) return;
     MSWB_REQUIRE(L->logl.p, "likelihood holds neither logl nor P");
-    L->P64.alloc((size_t)L->N * L->Kp);
-    L->rowmax.alloc(L->N);
-    to_linear_kernel<double><<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(L->logl.p, (int)L->Kp, L->P64.p, (int)L->Kp, L->rowmax.p, L->N, (int)L->K);
+    L->P64.alloc((size_t)L->N_pad * L->Kp);
+    L->rowmax.alloc(L->N_pad);
+    if (L->N_pad > L->N)
+      MSWB_CUDA(cudaMemsetAsync(L->P64.p + (size_t)L->N * L->Kp, 0, (size_t)(L->N_pad - L->N) * L->Kp * sizeof(double), s));
+    MSWB_CUDA(cudaMemsetAsync(L->rowmax.p, 0, L->rowmax.bytes(), s));
+    to_linear_kernel<double><<<ctx->n_sms * 8, 256, 0, s>>>(L->logl.p, (int)L->Kp, L->P64.p, (int)L->Kp, L->rowmax.p, L->N, (int)L->K);
   }
   MSWB_LAUNCHED();
 }
@@ -547,7 +597,8 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
       DevBuf<double> lc;
       lc.alloc(lik->N);
       h2d(lc.p, log_counts, lik->N, s);
-      vi->own_counts.alloc(lik->N);
+      vi->own_counts.alloc(lik->N_pad);
+      MSWB_CUDA(cudaMemsetAsync(vi->own_counts.p, 0, vi->own_counts.bytes(), s));
       const int nb = 296;
       vi->block_sums.ensure(nb + 1);
       counts_from_log_kernel<<<nb, 256, 0, s>>>(lc.p, vi->own_counts.p, lik->N, vi->block_sums.p);
