@@ -73,6 +73,15 @@ MSWB_API int  mswb_shard_range(const mswb_ctx *ctx, uint64_t n_ecs, uint64_t *be
  * (an empty row = unaligned read, counted in n_reads but in no class).  Replicated on every rank. */
 MSWB_API int  mswb_ec_build(mswb_ctx *ctx, uint64_t n_reads, uint64_t n_targets, const uint64_t *row_ptr,
                    const uint32_t *targets, mswb_aln **out);
+/* Same, but the reads given are ONLY this rank's partition of the alignment: the host has routed reads
+ * to ranks by ascending ranges of the pattern hash (mswb_pattern_hash), rank 0 owning the lowest range.
+ * The global class table is then the concatenation of the ranks' tables, no class straddles two
+ * ranks, and mswb_lik_build keeps the whole local table as this rank's shard. */
+MSWB_API int  mswb_ec_build_partitioned(mswb_ctx *ctx, uint64_t n_reads_local, uint64_t n_targets,
+                               const uint64_t *row_ptr, const uint32_t *targets, mswb_aln **out);
+/* The reference's pattern hash (include/mSWEEP_alignment.hpp:150-155) of one ascending target list,
+ * for hosts that partition reads by hash range. */
+MSWB_API uint64_t mswb_pattern_hash(const uint32_t *targets, uint64_t n);
 MSWB_API int  mswb_ec_info(const mswb_aln *aln, uint64_t *n_ecs, uint64_t *n_reads, uint64_t *n_aligned,
                   uint64_t *pattern_nnz);
 /* Parity export; any pointer may be NULL.  hash/count/rep_read: n_ecs; pat_ptr/read_ptr: n_ecs+1;
@@ -120,7 +129,7 @@ typedef struct {
   uint64_t resets;       /* RCG restarts taken                                                     */
   double   pass_ms_sum;  /* time_kernels: summed device time of the pass kernels, and their count  */
   uint64_t pass_launches;
-  uint64_t pass_bytes;   /* algorithmic HBM bytes of ONE pass kernel launch on this rank           */
+  uint64_t pass_bytes;   /* algorithmic HBM bytes of the sweep(s) of ONE iteration on this rank      */
 } mswb_vi_stat;
 typedef void (*mswb_iter_cb)(void *user, uint64_t iter, double bound, double gnorm);
 

@@ -53,6 +53,7 @@ def lib() -> C.CDLL:
         L.mswb_last_error.restype = C.c_char_p
         L.mswb_version.restype = C.c_char_p
         L.mswb_launch_count.restype = C.c_uint64
+        L.mswb_pattern_hash.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -117,13 +118,15 @@ class EcExport:
 class Alignment:
     """mswb_ec_build: equivalence classes from the strand-merged pseudoalignment (CSR over reads)."""
 
-    def __init__(self, ctx: Context, n_reads: int, n_targets: int, row_ptr: np.ndarray, targets: np.ndarray):
+    def __init__(self, ctx: Context, n_reads: int, n_targets: int, row_ptr: np.ndarray, targets: np.ndarray,
+                 partitioned: bool = False):
         self.ctx = ctx
         self.h = C.c_void_p()
         rp = np.ascontiguousarray(row_ptr, np.uint64)
         tg = np.ascontiguousarray(targets, np.uint32)
         assert len(rp) == n_reads + 1
-        _check(lib().mswb_ec_build(ctx.h, C.c_uint64(n_reads), C.c_uint64(n_targets), _p(rp), _p(tg) if len(tg) else None,
+        fn = lib().mswb_ec_build_partitioned if partitioned else lib().mswb_ec_build
+        _check(fn(ctx.h, C.c_uint64(n_reads), C.c_uint64(n_targets), _p(rp), _p(tg) if len(tg) else None,
                                    C.byref(self.h)))
         v = [C.c_uint64() for _ in range(4)]
         _check(lib().mswb_ec_info(self.h, *[C.byref(x) for x in v]))

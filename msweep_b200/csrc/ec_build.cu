@@ -85,10 +85,8 @@ __global__ void gather_patterns_kernel(const uint64_t *__restrict__ row_ptr, con
 
 } // namespace mswb
 
-extern "C" {
-
-int mswb_ec_build(mswb_ctx *ctx, uint64_t n_reads, uint64_t n_targets, const uint64_t *row_ptr,
-                  const uint32_t *targets, mswb_aln **out) {
+static int ec_build_impl(mswb_ctx *ctx, uint64_t n_reads, uint64_t n_targets, const uint64_t *row_ptr,
+                         const uint32_t *targets, bool partitioned, mswb_aln **out) {
   return guarded([&] {
     MSWB_REQUIRE(ctx && row_ptr && out, "NULL argument");
     MSWB_REQUIRE(n_reads <= 0xFFFFFFFFull, "more than 2^32 reads (the reference stores read ids as uint32_t, mSWEEP_alignment.hpp:45)");
@@ -100,7 +98,7 @@ int mswb_ec_build(mswb_ctx *ctx, uint64_t n_reads, uint64_t n_targets, const uin
     const int grid = ctx->n_sms * 8;
 
     std::unique_ptr<mswb_aln> A(new mswb_aln);
-    A->ctx = ctx; A->n_reads = R; A->n_targets = n_targets;
+    A->ctx = ctx; A->n_reads = R; A->n_targets = n_targets; A->partitioned = partitioned;
 
     DevBuf<uint64_t> d_row_ptr, d_hash, d_keys_in, d_keys_out, d_pat_len;
     DevBuf<uint32_t> d_targets, d_ids, d_ids_in, d_ids_out, d_head, d_ec_of;
@@ -183,6 +181,22 @@ int mswb_ec_build(mswb_ctx *ctx, uint64_t n_reads, uint64_t n_targets, const uin
     MSWB_CUDA(cudaStreamSynchronize(s));
     *out = A.release();
   });
+}
+
+extern "C" {
+
+int mswb_ec_build(mswb_ctx *ctx, uint64_t n_reads, uint64_t n_targets, const uint64_t *row_ptr,
+                  const uint32_t *targets, mswb_aln **out) {
+  return ec_build_impl(ctx, n_reads, n_targets, row_ptr, targets, false, out);
+}
+int mswb_ec_build_partitioned(mswb_ctx *ctx, uint64_t n_reads_local, uint64_t n_targets, const uint64_t *row_ptr,
+                              const uint32_t *targets, mswb_aln **out) {
+  return ec_build_impl(ctx, n_reads_local, n_targets, row_ptr, targets, true, out);
+}
+uint64_t mswb_pattern_hash(const uint32_t *targets, uint64_t n) {
+  uint64_t h = 0;
+  for (uint64_t a = 0; a < n; ++a) h ^= (uint64_t)targets[a] + 0x517cc1b727220a95ULL + (h << 6) + (h >> 2);
+  return h;
 }
 
 int mswb_ec_info(const mswb_aln *aln, uint64_t *n_ecs, uint64_t *n_reads, uint64_t *n_aligned, uint64_t *pattern_nnz) {

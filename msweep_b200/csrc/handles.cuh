@@ -6,6 +6,7 @@
 struct mswb_aln {
   mswb_ctx *ctx = nullptr;
   uint64_t n_reads = 0, n_targets = 0, n_ecs = 0, n_aligned = 0, pat_nnz = 0;
+  bool partitioned = false;           // true: the table covers only this rank's hash range of the reads
   mswb::DevBuf<uint64_t> hash;        // [n_ecs] ascending
   mswb::DevBuf<uint64_t> count;       // [n_ecs] reads per class
   mswb::DevBuf<uint32_t> rep_read;    // [n_ecs] smallest read id of the class

@@ -207,10 +207,27 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
     L->ctx = ctx;
     L->K_all = n_groups;
     L->storage = storage;
-    L->N_total = aln->n_ecs;
     uint64_t lo, hi;
-    MSWB_REQUIRE(mswb_shard_range(ctx, aln->n_ecs, &lo, &hi) == 0, mswb_last_error());
-    L->ec_begin = lo;
+    double n_aligned_total = (double)aln->n_aligned;
+    if (aln->partitioned) {
+      // every rank built the classes of its own hash range: the shard is the whole local table
+      DevBuf<double> tmp;
+      tmp.alloc(ctx->world + 1);
+      std::vector<double> v(ctx->world + 1, 0.0);
+      v[ctx->rank] = (double)aln->n_ecs;
+      v[ctx->world] = (double)aln->n_aligned;
+      h2d(tmp.p, v.data(), v.size(), s);
+      ctx->allreduce_sum(tmp.p, v.size());
+      d2h(v.data(), tmp.p, v.size(), s);
+      MSWB_CUDA(cudaStreamSynchronize(s));
+      for (int r = 0; r < ctx->world; ++r) { if (r < ctx->rank) L->ec_begin += (uint64_t)v[r]; L->N_total += (uint64_t)v[r]; }
+      n_aligned_total = v[ctx->world];
+      lo = 0; hi = aln->n_ecs;
+    } else {
+      L->N_total = aln->n_ecs;
+      MSWB_REQUIRE(mswb_shard_range(ctx, aln->n_ecs, &lo, &hi) == 0, mswb_last_error());
+      L->ec_begin = lo;
+    }
     L->N = hi - lo;
     L->N_pad = round_up(L->N, 64);
     L->n_targets = T;
@@ -233,7 +250,7 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
     MSWB_CUDA(cudaMemsetAsync(L->counts.p, 0, L->counts.bytes(), s));
     u64_to_double_kernel<<<ctx->n_sms * 2, 256, 0, s>>>(aln->count.p + lo, L->counts.p, L->N);
     MSWB_LAUNCHED();
-    L->sum_counts_total = (double)aln->n_aligned;   // every read with >= 1 hit sits in exactly one class
+    L->sum_counts_total = n_aligned_total;   // every read with >= 1 hit sits in exactly one class
 
     const size_t smem = lik_smem_bytes(n_groups);
     const int grid = fill_grid(ctx, L->N, n_groups);

@@ -3,6 +3,7 @@
 #include "oracle.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <limits>
 #include <map>
@@ -277,6 +278,11 @@ double digamma_series(double x) {
 
 namespace {
 
+struct Stopwatch {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double seconds() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 constexpr uint64_t kColBlock = 512;   // columns handled together by one thread (cache blocking)
 
 // gamma(., j) -= logsumexp_k gamma(k, j); lse[j] receives the subtracted value ("oldm").
@@ -375,6 +381,7 @@ double negnatgrad(const double *gamma, const double *N_k, const double *logl, ui
 ViResult rcg_optl(const double *logl, uint32_t K, uint64_t N, const double *log_counts,
                   const double *alpha0, double tol, uint64_t max_iters) {
   const size_t KN = (size_t)K * N;
+  const Stopwatch clock;
   ViResult res;
   res.gamma.assign(KN, std::log(1.0 / (double)K));
   std::vector<double> step(KN, 0.0), oldstep(KN, 0.0), oldm(N, 0.0);
@@ -422,6 +429,7 @@ ViResult rcg_optl(const double *logl, uint32_t K, uint64_t N, const double *log_
     res.trace.bound.push_back((double)bound);
     res.trace.gnorm.push_back(newnorm);
     res.trace.reset.push_back(didreset ? 1 : 0);
+    res.trace.t_end.push_back(clock.seconds());
     res.iters = it + 1;
     if (bound - oldbound < tol && !didreset) { res.converged = true; break; }
   }
@@ -436,6 +444,7 @@ ViResult rcg_optl(const double *logl, uint32_t K, uint64_t N, const double *log_
 ViResult em_optl(const double *logl, uint32_t K, uint64_t N, const double *log_counts,
                  const double *alpha0, double tol, uint64_t max_iters) {
   const size_t KN = (size_t)K * N;
+  const Stopwatch clock;
   ViResult res;
   res.gamma.assign(KN, std::log(1.0 / (double)K));
   res.N_k.assign(K, 0.0);
@@ -456,6 +465,7 @@ ViResult em_optl(const double *logl, uint32_t K, uint64_t N, const double *log_c
     res.trace.bound.push_back((double)bound);
     res.trace.gnorm.push_back(0.0);
     res.trace.reset.push_back(0);
+    res.trace.t_end.push_back(clock.seconds());
     res.iters = it + 1;
     if (it > 0 && std::fabs((double)(bound - oldbound)) < tol) { res.converged = true; break; }
   }

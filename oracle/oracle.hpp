@@ -100,7 +100,7 @@ Likelihood build_likelihood(const EcTable &ecs, const Grouping &grouping, double
 // ---------------------------------------------------------------------------------------------
 double digamma_series(double x);   // same series as src/Sample.cpp:87-97
 
-struct ViTrace { std::vector<double> bound, gnorm; std::vector<uint8_t> reset; };
+struct ViTrace { std::vector<double> bound, gnorm, t_end /* seconds since entry, per iteration */; std::vector<uint8_t> reset; };
 struct ViResult {
   std::vector<double> gamma;   // K x N group-major log-posteriors (what rcg_optl_* returns)
   std::vector<double> N_k;     // alpha0 + expected counts at exit

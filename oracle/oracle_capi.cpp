@@ -144,7 +144,7 @@ void orc_lik_free(void *h) { delete (Likelihood*)h; }
 // stats: [0]=bound, [1]=iters, [2]=converged.  trace_* may be NULL, else capacity max_iters.
 int orc_vi_run(int algo, const double *logl, uint32_t K, uint64_t N, const double *log_counts, const double *alpha0,
                double tol, uint64_t max_iters, double *theta, double *N_k, double *gamma, double *stats,
-               double *trace_bound, double *trace_gnorm, uint8_t *trace_reset) {
+               double *trace_bound, double *trace_gnorm, uint8_t *trace_reset, double *trace_t_end) {
   return guarded([&] {
     ViResult r = algo == 0 ? rcg_optl(logl, K, N, log_counts, alpha0, tol, max_iters)
                            : em_optl(logl, K, N, log_counts, alpha0, tol, max_iters);
@@ -152,7 +152,7 @@ int orc_vi_run(int algo, const double *logl, uint32_t K, uint64_t N, const doubl
     copy_out(r.N_k, N_k);
     copy_out(r.gamma, gamma);
     if (stats) { stats[0] = r.bound; stats[1] = (double)r.iters; stats[2] = r.converged ? 1.0 : 0.0; }
-    copy_out(r.trace.bound, trace_bound); copy_out(r.trace.gnorm, trace_gnorm); copy_out(r.trace.reset, trace_reset);
+    copy_out(r.trace.bound, trace_bound); copy_out(r.trace.gnorm, trace_gnorm); copy_out(r.trace.reset, trace_reset); copy_out(r.trace.t_end, trace_t_end);
   });
 }
 

@@ -63,7 +63,7 @@ class _Lib:
         L.orc_lik_build.argtypes = [C.c_void_p, _u32p, C.c_uint64, C.c_uint32, _u64p, C.c_double, C.c_double,
                                     C.c_double, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
         L.orc_lik_export.argtypes = [C.c_void_p] + [C.c_void_p] * 6
-        L.orc_vi_run.argtypes = [C.c_int, _f64p, C.c_uint32, C.c_uint64, _f64p, _f64p, C.c_double, C.c_uint64] + [C.c_void_p] * 7
+        L.orc_vi_run.argtypes = [C.c_int, _f64p, C.c_uint32, C.c_uint64, _f64p, _f64p, C.c_double, C.c_uint64] + [C.c_void_p] * 8
         L.orc_bootstrap_resample.argtypes = [_u64p, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, _u32p]
         L.orc_set_num_threads.argtypes = [C.c_int]
 
@@ -124,6 +124,7 @@ class ViResult:
     trace_bound: np.ndarray
     trace_gnorm: np.ndarray
     trace_reset: np.ndarray
+    trace_t_end: np.ndarray | None = None   # seconds since entry at the end of each iteration
 
 
 def pattern_hash(targets) -> int:
@@ -261,11 +262,11 @@ def vi_run(algo: str, logl, log_counts, alpha0=None, tol=1e-6, max_iters=5000, w
     a0 = np.ones(K) if alpha0 is None else np.ascontiguousarray(alpha0, np.float64)
     theta, Nk, stats = np.zeros(K), np.zeros(K), np.zeros(3)
     gamma = np.zeros((K, N)) if want_gamma else None
-    tb, tg, tr = np.zeros(max_iters), np.zeros(max_iters), np.zeros(max_iters, np.uint8)
+    tb, tg, tr, tt = np.zeros(max_iters), np.zeros(max_iters), np.zeros(max_iters, np.uint8), np.zeros(max_iters)
     L.check(L.lib.orc_vi_run(0 if algo == "rcg" else 1, logl, K, N, lc, a0, tol, max_iters, _opt(theta), _opt(Nk),
-                             _opt(gamma), _opt(stats), _opt(tb), _opt(tg), _opt(tr)))
+                             _opt(gamma), _opt(stats), _opt(tb), _opt(tg), _opt(tr), _opt(tt)))
     it = int(stats[1])
-    return ViResult(theta, Nk, gamma, float(stats[0]), it, bool(stats[2]), tb[:it], tg[:it], tr[:it])
+    return ViResult(theta, Nk, gamma, float(stats[0]), it, bool(stats[2]), tb[:it], tg[:it], tr[:it], tt[:it])
 
 
 def bootstrap_resample(ec_counts, seed: int, n_replicates: int, bootstrap_count: int = 0) -> np.ndarray:
