@@ -54,6 +54,7 @@ def lib() -> C.CDLL:
         L.mswb_version.restype = C.c_char_p
         L.mswb_launch_count.restype = C.c_uint64
         L.mswb_pattern_hash.restype = C.c_uint64
+        L.mswb_pattern_hash.argtypes = [C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
 
@@ -65,6 +66,12 @@ def _check(rc: int) -> None:
 
 def _p(arr, ctype=C.c_void_p):
     return None if arr is None else arr.ctypes.data_as(ctype)
+
+
+def pattern_hash(targets) -> int:
+    """mswb_pattern_hash of one ascending target list (host-side; for hash-range partitioning of reads)."""
+    t = np.ascontiguousarray(targets, np.uint32)
+    return int(lib().mswb_pattern_hash(t.ctypes.data if len(t) else None, len(t)))
 
 
 def launch_count() -> int:

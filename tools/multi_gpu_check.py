@@ -29,8 +29,7 @@ mask_mh, hits_mh = lik_mh.mask(want_hits=True)
 
 # hash-partitioned reads: rank r owns hash range [r, r+1) * 2^64 / world
 rp = wl.row_ptr.astype(np.int64)
-from ctypes import c_uint64
-h = np.array([M.lib().mswb_pattern_hash(wl.targets[rp[i]:rp[i + 1]].ctypes.data, c_uint64(int(rp[i + 1] - rp[i]))) for i in range(wl.n_reads)], np.uint64)
+h = np.array([M.pattern_hash(wl.targets[rp[i]:rp[i + 1]]) for i in range(wl.n_reads)], np.uint64)
 owner = (h.astype(np.float64) / 2.0 ** 64 * world).astype(np.int64).clip(0, world - 1)
 lens = np.diff(rp)
 owner[lens == 0] = np.arange(wl.n_reads)[lens == 0] % world       # unaligned reads: anywhere
