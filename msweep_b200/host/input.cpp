@@ -1,0 +1,211 @@
+// input.cpp — see input.hpp.  Semantics follow the reference line by line; the implementation does not:
+// the reference tokenises with getline/stringstream/stoul on one thread into a compressed bit vector,
+// here every strand is read into memory once, cut at line boundaries into one slice per thread, scanned
+// with a hand-rolled integer parser into (row, column) pairs, bucketed by row and merged as sorted lists.
+#include "input.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <unordered_map>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace b200 {
+
+Grouping read_grouping(const std::string &path, char delimiter, size_t column) {
+  std::ifstream in(path);
+  if (!in.good()) throw std::runtime_error("Could not read cluster indicators.");     // src/Reference.cpp:40-42
+  Grouping g;
+  std::unordered_map<std::string, uint32_t> ids;
+  std::string line, field;
+  while (std::getline(in, line)) {
+    std::stringstream ss(line);
+    size_t col = 0;
+    bool found = false;
+    while (std::getline(ss, field, delimiter)) {
+      if (col == column) found = true;
+      if (found && col == column) break;
+      ++col;
+    }
+    {   // number of groupings = max number of columns on a line (include/Reference.hpp:75-80)
+      size_t ncol = (size_t)std::count(line.begin(), line.end(), delimiter) + (line.empty() ? 0 : 1);
+      g.n_groupings = std::max(g.n_groupings, ncol);
+    }
+    if (!found) continue;
+    auto it = ids.find(field);
+    if (it == ids.end()) {
+      it = ids.emplace(field, (uint32_t)g.names.size()).first;
+      g.names.push_back(field);
+      g.sizes.push_back(0);
+    }
+    g.sizes[it->second] += 1;
+    g.group_of_target.push_back(it->second);
+  }
+  if (g.group_of_target.empty()) throw std::runtime_error("The grouping contains 0 reference sequences");   // Reference.hpp:90-92
+  return g;
+}
+
+namespace {
+
+struct Strand {
+  uint64_t n_lines = 0;
+  std::vector<uint64_t> row_ptr;       // rows 0 .. n_rows-1, ascending unique columns
+  std::vector<uint32_t> cols;
+};
+
+std::string slurp(const std::string &path) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in.good()) throw std::runtime_error("Could not open " + path);
+  in.seekg(0, std::ios::end);
+  const std::streamoff n = in.tellg();
+  in.seekg(0);
+  std::string buf((size_t)n, '\0');
+  in.read(&buf[0], n);
+  return buf;
+}
+
+// std::stoul semantics on a space-delimited token: optional leading whitespace, then digits; junk after
+// the digits is ignored; no digits at all is an error.
+inline bool parse_token(const char *&p, const char *end, uint64_t &out) {
+  while (p < end && (*p == '\t' || *p == '\r' || *p == '\v' || *p == '\f')) ++p;
+  if (p < end && *p == '+') ++p;
+  if (p >= end || *p < '0' || *p > '9') return false;
+  uint64_t v = 0;
+  while (p < end && *p >= '0' && *p <= '9') v = v * 10 + (uint64_t)(*p++ - '0');
+  while (p < end && *p != ' ') ++p;     // trailing junk inside the token
+  out = v;
+  return true;
+}
+
+Strand parse_strand(const std::string &buf, uint64_t T, int n_threads) {
+  if (buf.find(',') != std::string::npos && buf.find(',') < buf.find('\n'))
+    throw std::runtime_error("compact (alignment-writer) pseudoalignments are not supported by this backend; "
+                             "convert to Themisto plaintext");
+  const char *base = buf.data();
+  const size_t n = buf.size();
+  std::vector<size_t> cut(n_threads + 1, n);
+  cut[0] = 0;
+  for (int t = 1; t < n_threads; ++t) {
+    size_t p = n * (size_t)t / n_threads;
+    const void *nl = p < n ? memchr(base + p, '\n', n - p) : nullptr;
+    cut[t] = nl ? (size_t)((const char *)nl - base) + 1 : n;
+  }
+  for (int t = 1; t <= n_threads; ++t) cut[t] = std::max(cut[t], cut[t - 1]);
+
+  std::vector<std::vector<uint64_t>> keys(n_threads);       // flat bit index read_id*T + target (mSWEEP_alignment.hpp:64)
+  std::vector<uint64_t> lines(n_threads, 0), bad_line(n_threads, 0);
+  std::vector<std::string> bad_text(n_threads);
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
+  for (int t = 0; t < n_threads; ++t) {
+    const char *p = base + cut[t], *end = base + cut[t + 1];
+    std::vector<uint64_t> &out = keys[t];
+    out.reserve((size_t)(end - p) / 5);
+    while (p < end) {
+      const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+      if (!eol) eol = end;
+      ++lines[t];
+      const char *q = p;
+      uint64_t read_id = 0, tgt = 0;
+      bool ok = parse_token(q, eol, read_id);
+      while (ok && q < eol) {
+        ++q;                                       // the single ' ' delimiter
+        if (q > eol) break;
+        if (q == eol) { break; }                   // trailing delimiter: getline yields no further token
+        ok = parse_token(q, eol, tgt);
+        if (ok) out.push_back(read_id * T + tgt);
+      }
+      if (!ok && !bad_line[t]) { bad_line[t] = lines[t]; bad_text[t].assign(p, eol); }
+      p = eol + 1;
+    }
+  }
+  uint64_t before = 0;
+  for (int t = 0; t < n_threads; ++t) {
+    if (bad_line[t]) throw std::runtime_error("File format not supported on line " + std::to_string(before + bad_line[t]) +
+                                              " with content: " + bad_text[t]);
+    before += lines[t];
+  }
+  Strand s;
+  s.n_lines = before;
+  // bucket by row (= flat / T); rows at or beyond the line count are never visited by collapse()
+  const uint64_t R = s.n_lines;
+  s.row_ptr.assign(R + 1, 0);
+  for (auto &v : keys) for (uint64_t k : v) { const uint64_t r = k / T; if (r < R) ++s.row_ptr[r + 1]; }
+  for (uint64_t r = 0; r < R; ++r) s.row_ptr[r + 1] += s.row_ptr[r];
+  s.cols.resize(s.row_ptr[R]);
+  std::vector<uint64_t> fill(s.row_ptr.begin(), s.row_ptr.end() - 1);
+  for (auto &v : keys) { for (uint64_t k : v) { const uint64_t r = k / T; if (r < R) s.cols[fill[r]++] = (uint32_t)(k % T); } std::vector<uint64_t>().swap(v); }
+  // ascending + unique inside each row (a bit can only be set once)
+  std::vector<uint64_t> len(R);
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+  for (uint64_t r = 0; r < R; ++r) {
+    uint32_t *a = s.cols.data() + s.row_ptr[r], *b = s.cols.data() + s.row_ptr[r + 1];
+    if (!std::is_sorted(a, b)) std::sort(a, b);
+    len[r] = (uint64_t)(std::unique(a, b) - a);
+  }
+  uint64_t w = 0;
+  for (uint64_t r = 0; r < R; ++r) {          // compact away duplicates
+    const uint64_t a = s.row_ptr[r];
+    if (w != a) std::memmove(s.cols.data() + w, s.cols.data() + a, len[r] * sizeof(uint32_t));
+    s.row_ptr[r] = w;
+    w += len[r];
+  }
+  s.row_ptr[R] = w;
+  s.cols.resize(w);
+  return s;
+}
+
+} // namespace
+
+ReadTable read_themisto(const std::vector<std::string> &paths, uint64_t n_targets, const std::string &merge_mode, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  ReadTable out;
+  out.n_targets = n_targets;
+  Strand acc;
+  for (size_t i = 0; i < paths.size(); ++i) {
+    Strand s = parse_strand(slurp(paths[i]), n_targets, n_threads);
+    if (i == 0) { acc = std::move(s); continue; }
+    const bool isect = merge_mode == "intersection";
+    if (!isect && merge_mode != "union")
+      throw std::runtime_error("Unrecognized option `" + merge_mode + "` for --themisto-mode");   // mSWEEP_alignment.hpp:130-132
+    // bit_and / bit_or of the two strands; n_queries follows the LAST strand (:121)
+    const uint64_t R = s.n_lines, Ra = acc.n_lines;
+    Strand m;
+    m.n_lines = R;
+    m.row_ptr.assign(R + 1, 0);
+    std::vector<uint64_t> len(R, 0);
+    auto row = [](const Strand &x, uint64_t r, const uint32_t *&a, const uint32_t *&b) {
+      if (r < x.n_lines) { a = x.cols.data() + x.row_ptr[r]; b = x.cols.data() + x.row_ptr[r + 1]; } else { a = b = nullptr; }
+    };
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+    for (uint64_t r = 0; r < R; ++r) {
+      const uint32_t *a0, *a1, *b0, *b1;
+      row(acc, r, a0, a1); row(s, r, b0, b1);
+      uint64_t c = 0;
+      if (isect) { while (a0 < a1 && b0 < b1) { if (*a0 < *b0) ++a0; else if (*b0 < *a0) ++b0; else { ++c; ++a0; ++b0; } } }
+      else { while (a0 < a1 && b0 < b1) { if (*a0 < *b0) ++a0; else if (*b0 < *a0) ++b0; else { ++a0; ++b0; } ++c; } c += (uint64_t)(a1 - a0) + (uint64_t)(b1 - b0); }
+      len[r] = c;
+    }
+    for (uint64_t r = 0; r < R; ++r) m.row_ptr[r + 1] = m.row_ptr[r] + len[r];
+    m.cols.resize(m.row_ptr[R]);
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+    for (uint64_t r = 0; r < R; ++r) {
+      const uint32_t *a0, *a1, *b0, *b1;
+      row(acc, r, a0, a1); row(s, r, b0, b1);
+      uint32_t *o = m.cols.data() + m.row_ptr[r];
+      if (isect) std::set_intersection(a0, a1, b0, b1, o); else std::set_union(a0, a1, b0, b1, o);
+    }
+    (void)Ra;
+    acc = std::move(m);
+  }
+  out.n_reads = acc.n_lines;
+  out.row_ptr = std::move(acc.row_ptr);
+  out.targets = std::move(acc.cols);
+  if (out.row_ptr.empty()) out.row_ptr.assign(1, 0);
+  return out;
+}
+
+} // namespace b200

@@ -1,0 +1,348 @@
+// main.cpp — mSWEEP_b200: the reference's command line for the abundance-estimation path
+// (src/mSWEEP.cpp:68-160, 207-567), driving the B200 backend through the C ABI.
+//
+// Kept from the reference: the flags of the hot path with their defaults and meaning, the order of the
+// stages, the messages and exit codes of the failure sites, and the <prefix>_abundances.txt format
+// (src/PlainSample.cpp:32-71, src/BootstrapSample.cpp:75-130).  Not here (out of scope):
+// read binning, probability / likelihood dumps, RATE, output compression, the compact alignment format.
+// New: --algorithm takes the B200 backends (rcgb200 | emb200; the reference's rcggpu / emgpu are accepted
+// as aliases and rcgcpu is refused: there is no CPU path in this binary), and --gpus N.
+#include "input.hpp"
+#include "msweep_b200.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <thread>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef MSWEEP_BUILD_VERSION
+#define MSWEEP_BUILD_VERSION "b200-0.1.0"
+#endif
+
+namespace {
+
+struct Args {
+  std::map<std::string, std::string> kv;
+  std::set<std::string> flags;
+  bool has(const std::string &k) const { return kv.count(k) || flags.count(k); }
+  std::string str(const std::string &k, const std::string &dflt) const { auto it = kv.find(k); return it == kv.end() ? dflt : it->second; }
+  template <typename T> T num(const std::string &k, T dflt) const {
+    auto it = kv.find(k);
+    if (it == kv.end()) return dflt;
+    std::istringstream ss(it->second);
+    T v;
+    if (!(ss >> v)) throw std::runtime_error("Could not parse the value of --" + k + ": " + it->second);
+    return v;
+  }
+};
+
+const std::set<std::string> kBool = {"verbose", "version", "cite", "help", "no-fit-model", "print-timings"};
+const std::set<std::string> kValued = {"themisto-1", "themisto-2", "themisto", "i", "o", "themisto-mode", "t", "max-iters", "tol",
+                                       "algorithm", "emprecision", "iters", "seed", "bootstrap-count", "q", "e", "alphas",
+                                       "zero-inflation", "min-hits", "gpus", "rng", "dump-alignment"};
+const std::set<std::string> kUnsupported = {"bin-reads", "target-groups", "min-abundance", "write-probs", "print-probs",
+                                            "write-likelihood", "write-likelihood-bitseq", "compress", "compression-level",
+                                            "read-likelihood", "run-rate"};
+
+Args parse(int argc, char **argv) {
+  Args a;
+  for (int i = 1; i < argc; ++i) {
+    std::string tok = argv[i];
+    if (tok.size() < 2 || tok[0] != '-') throw std::runtime_error("Unexpected argument: " + tok);
+    std::string key = tok.substr(tok[1] == '-' ? 2 : 1), val;
+    const size_t eq = key.find('=');
+    bool has_val = false;
+    if (eq != std::string::npos) { val = key.substr(eq + 1); key = key.substr(0, eq); has_val = true; }
+    if (kUnsupported.count(key)) throw std::runtime_error("--" + key + " is outside the scope of the B200 abundance-estimation backend");
+    if (kBool.count(key)) { a.flags.insert(key); continue; }
+    if (!kValued.count(key)) throw std::runtime_error("Unknown argument: " + tok);
+    if (!has_val) {
+      if (i + 1 >= argc) throw std::runtime_error("Argument " + tok + " needs a value");
+      val = argv[++i];
+    }
+    a.kv[key] = val;
+  }
+  return a;
+}
+
+std::vector<std::string> split(const std::string &s, char d) {
+  std::vector<std::string> out;
+  std::stringstream ss(s);
+  std::string part;
+  while (std::getline(ss, part, d)) out.push_back(part);
+  return out;
+}
+
+const char *kHelp =
+    "Usage: mSWEEP_b200 --themisto-1 <forwardPseudoalignments> --themisto-2 <reversePseudoalignments> -i <groupIndicatorsFile>\n\n"
+    "  --themisto-1, --themisto-2   Themisto pseudoalignments of the two strands (plaintext)\n"
+    "  --themisto a[,b]             single file or comma separated list\n"
+    "  -i                           group indicators, one line per reference sequence (required)\n"
+    "  -o                           output prefix (default: print to cout)\n"
+    "  --themisto-mode              intersection | union (default: intersection)\n"
+    "  -t                           host threads for parsing (default: 1)\n"
+    "  --gpus                       number of B200s to use (default: 1)\n"
+    "  --algorithm                  rcgb200 | emb200 (aliases: rcggpu, emgpu; default: rcgb200)\n"
+    "  --emprecision                float | double, for emb200 (default: double)\n"
+    "  --max-iters                  optimiser iteration cap (default: 5000)\n"
+    "  --tol                        stop when the bound changes by less than this (default: 0.000001)\n"
+    "  --iters                      bootstrap replicates (default: 0)\n"
+    "  --seed                       bootstrap seed (default: random)\n"
+    "  --bootstrap-count            pseudoalignments to resample per replicate (default: number of aligned reads)\n"
+    "  --rng                        exact | philox bootstrap generator (default: exact = std::mt19937_64 stream)\n"
+    "  -q, -e                       beta-binomial mean and dispersion (defaults: 0.65, 0.01)\n"
+    "  --alphas                     comma separated prior counts (default: all 1.0)\n"
+    "  --zero-inflation             likelihood of zero hits against a group (default: 0.01)\n"
+    "  --min-hits                   only consider groups with at least this many aligned reads (default: 0)\n"
+    "  --no-fit-model, --verbose, --version, --cite, --help, --print-timings\n";
+
+void cite() {
+  std::cerr << "Please cite us as:\n"
+            << "\tMäklin T, Kallonen T, David S et al. High-resolution sweep\n"
+            << "\tmetagenomics using fast probabilistic inference [version 2;\n"
+            << "\tpeer review: 2 approved]. Wellcome Open Res 2021, 5:14\n"
+            << "\t(https://doi.org/10.12688/wellcomeopenres.15639.2)" << std::endl;
+}
+
+// src/PlainSample.cpp:32-71 and src/BootstrapSample.cpp:75-130: default ostream formatting throughout.
+void write_abundances(std::ostream &of, uint64_t n_reads, uint64_t n_aligned, const std::vector<std::string> &estimated,
+                      const std::vector<std::string> &zero, const std::vector<std::vector<double>> &results, uint64_t iters) {
+  if (!of.good()) throw std::runtime_error(iters ? "Could not write to abundances file." : "Can't write to abundances file.");
+  of << "#mSWEEP_version:" << '\t' << MSWEEP_BUILD_VERSION << '\n';
+  of << "#num_reads:" << '\t' << n_reads << '\n';
+  of << "#num_aligned:" << '\t' << n_aligned << '\n';
+  if (iters) {
+    of << "#bootstrap_iters:" << '\t' << iters << '\n';
+    of << "#c_id" << '\t' << "mean_theta" << '\t' << "bootstrap_mean_thetas" << '\n';
+  } else {
+    of << "#c_id" << '\t' << "mean_theta" << '\n';
+  }
+  for (size_t i = 0; i < estimated.size() + zero.size(); ++i) {
+    const bool est = i < estimated.size();
+    of << (est ? estimated[i] : zero[i - estimated.size()]) << '\t' << (est ? results[0][i] : 0.0);
+    for (uint64_t b = 0; b < iters; ++b) of << '\t' << (est ? results[b + 1][i] : 0.0);
+    of << '\n';
+  }
+  of.flush();
+}
+
+struct Timer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double lap() { auto t1 = std::chrono::steady_clock::now(); double s = std::chrono::duration<double>(t1 - t0).count(); t0 = t1; return s; }
+};
+
+} // namespace
+
+int main(int argc, char *argv[]) {
+  bool verbose = false;
+  for (int i = 1; i < argc; ++i) verbose = verbose || std::strcmp(argv[i], "--verbose") == 0;
+  auto log = [&](const std::string &m) { if (verbose) std::cerr << m << '\n'; };
+  log(std::string("mSWEEP-") + MSWEEP_BUILD_VERSION + " abundance estimation");
+
+  Args args;
+  try {
+    log("Parsing arguments");
+    args = parse(argc, argv);
+    if (args.has("help")) std::cerr << "\n" << kHelp << "\n\n";
+    if (args.has("version")) std::cerr << "mSWEEP-" << MSWEEP_BUILD_VERSION << std::endl;
+    if (args.has("cite")) cite();
+    if (args.has("help") || args.has("version") || args.has("cite")) return 0;
+    if (!args.has("i")) throw std::runtime_error("Required argument -i was not given");
+    if (args.has("themisto-1") != args.has("themisto-2")) throw std::runtime_error("--themisto-1 and --themisto-2 must be given together");
+    if (!args.has("themisto") && !args.has("themisto-1")) throw std::runtime_error("No pseudoalignment files were given (--themisto-1/--themisto-2 or --themisto)");
+    const std::string o = args.str("o", "");
+    if (o.find('/') != std::string::npos) {
+      std::string dir = o.substr(0, o.rfind('/'));
+      std::ofstream probe(dir + "/.mSWEEP_b200_probe");
+      if (!probe.good()) throw std::runtime_error("Directory " + dir + " does not seem to exist.");
+      probe.close();
+      std::remove((dir + "/.mSWEEP_b200_probe").c_str());
+    }
+  } catch (const std::exception &e) {
+    std::cerr << "Error in parsing arguments:\n  " << e.what() << "\nexiting\n";
+    return 1;
+  }
+
+  const int n_threads = (int)std::max<size_t>(1, args.num<size_t>("t", 1));
+#ifdef _OPENMP
+  omp_set_num_threads(n_threads);
+#endif
+  const int n_gpus = std::max(1, args.num<int>("gpus", 1));
+  const bool timings = args.has("print-timings");
+  Timer timer;
+
+  // ---- group indicators (src/mSWEEP.cpp:258-273) ---------------------------------------------------
+  b200::Grouping grouping;
+  log("Reading the input files");
+  try {
+    log("  reading group indicators");
+    grouping = b200::read_grouping(args.str("i", ""));
+    if (grouping.n_groupings > 1)
+      throw std::runtime_error("multiple groupings per indicator file are outside the scope of this backend (use a single column)");
+    log("  read " + std::to_string(grouping.group_of_target.size()) + " group indicators");
+  } catch (std::exception &e) {
+    std::cerr << "Reading group indicators failed:\n  " << e.what() << "\nexiting\n";
+    return 1;
+  }
+  const double t_grouping = timer.lap();
+
+  // ---- algorithm selection (src/mSWEEP.cpp:127, 192-203; unknown strings are refused, not run as EM) ---
+  b200::ViOptions vi;
+  int storage = MSWB_STORE_F64;
+  try {
+    const std::string algo = args.str("algorithm", "rcgb200");
+    if (algo == "rcgb200" || algo == "rcggpu") vi.algo = MSWB_ALGO_RCG;
+    else if (algo == "emb200" || algo == "emgpu") vi.algo = MSWB_ALGO_EM;
+    else if (algo == "rcgcpu") throw std::runtime_error("--algorithm rcgcpu: this binary is the B200 backend and has no CPU path");
+    else throw std::runtime_error("Unknown --algorithm `" + algo + "` (one of rcgb200, emb200)");
+    const std::string prec = args.str("emprecision", "double");
+    if (prec == "float") { if (vi.algo == MSWB_ALGO_EM) storage = MSWB_STORE_F32; }
+    else if (prec != "double") throw std::runtime_error("Unknown --emprecision `" + prec + "` (one of float, double)");
+    vi.tol = args.num<double>("tol", 1e-6);
+    vi.max_iters = args.num<uint64_t>("max-iters", 5000);
+  } catch (std::exception &e) {
+    std::cerr << "Error in parsing arguments:\n  " << e.what() << "\nexiting\n";
+    return 1;
+  }
+
+  // ---- pseudoalignments (src/mSWEEP.cpp:296-331) -------------------------------------------------------
+  b200::ReadTable reads;
+  try {
+    log("  reading pseudoalignments");
+    std::vector<std::string> paths;
+    if (args.has("themisto")) paths = split(args.str("themisto", ""), ',');
+    else paths = {args.str("themisto-1", ""), args.str("themisto-2", "")};
+    reads = b200::read_themisto(paths, grouping.group_of_target.size(), args.str("themisto-mode", "intersection"), n_threads);
+    log("  read alignments for " + std::to_string(reads.n_reads) + " reads");
+  } catch (std::exception &e) {
+    std::cerr << "Reading the pseudoalignments failed:\n  " << e.what() << "\nexiting\n";
+    return 1;
+  }
+  const double t_parse = timer.lap();
+  if (args.has("dump-alignment")) {   // debugging aid: the strand-merged alignment as CSR (u64 R, u64 T, row_ptr, targets)
+    std::ofstream of(args.str("dump-alignment", ""), std::ios::binary);
+    const uint64_t hdr[2] = {reads.n_reads, reads.n_targets};
+    of.write((const char *)hdr, sizeof(hdr));
+    of.write((const char *)reads.row_ptr.data(), (std::streamsize)(reads.row_ptr.size() * sizeof(uint64_t)));
+    of.write((const char *)reads.targets.data(), (std::streamsize)(reads.targets.size() * sizeof(uint32_t)));
+    return 0;
+  }
+
+  const uint64_t iters = args.num<uint64_t>("iters", 0);
+  if (iters > 65535) { std::cerr << "Error in parsing arguments:\n  --iters is limited to 65535 replicates\nexiting\n"; return 1; }   // uint16_t loop, src/mSWEEP.cpp:498
+  const bool bootstrap = iters > 0;
+  const uint64_t min_hits = args.num<uint64_t>("min-hits", 0);
+  const double q = args.num<double>("q", 0.65), e_disp = args.num<double>("e", 0.01), zi = args.num<double>("zero-inflation", 0.01);
+  const int32_t seed = (int32_t)args.num<size_t>("seed", 26012023);     // narrowed as in include/Sample.hpp:163-169
+  const uint64_t bootstrap_count = args.num<uint64_t>("bootstrap-count", 0);
+  const int rng_mode = args.str("rng", "exact") == "philox" ? MSWB_RNG_PHILOX : MSWB_RNG_LIBSTDCXX_EXACT;
+
+  // One host thread per GPU.  Plain estimate: classes sharded over the GPUs (world = n_gpus, one NCCL
+  // all-reduce per pass).  Bootstrap: every GPU holds the whole likelihood and takes replicates r % n_gpus.
+  const int world = bootstrap ? 1 : n_gpus;
+  std::vector<unsigned char> nccl_id(MSWB_NCCL_ID_BYTES, 0);
+  if (world > 1 && mswb_nccl_unique_id(nccl_id.data())) { std::cerr << "Initialising the GPUs failed:\n  " << mswb_last_error() << "\nexiting\n"; return 1; }
+
+  std::vector<std::vector<std::vector<double>>> results_by_gpu(n_gpus);   // [gpu][0 = plain, 1.. = replicates][group]
+  std::vector<std::string> errors(n_gpus);
+  std::vector<int> failed_stage(n_gpus, 0);   // 1 = EC/likelihood, 2 = estimation, 3 = bootstrap
+  std::vector<bool> mask;
+  uint64_t n_ecs = 0, n_aligned = 0, n_reads = 0;
+  double t_ec = 0, t_lik = 0, t_vi = 0, t_boot = 0;
+  b200::ViReport report;
+
+  auto worker = [&](int gpu) {
+    try {
+      failed_stage[gpu] = 1;
+      b200::Context ctx(gpu, bootstrap ? 0 : gpu, world, world > 1 ? nccl_id.data() : nullptr);
+      Timer tm;
+      if (gpu == 0) log("Building equivalence classes");
+      b200::Alignment aln(ctx, reads);
+      if (gpu == 0) { n_ecs = aln.n_ecs(); n_aligned = aln.n_aligned(); n_reads = aln.n_reads(); t_ec = tm.lap();
+                      log("  found " + std::to_string(n_ecs) + " unique alignments"); log("Computing the likelihood matrix"); }
+      b200::Likelihood ll(ctx, aln, grouping.group_of_target, grouping.sizes, q, e_disp, min_hits, zi, storage);
+      if (gpu == 0) { mask = ll.groups_considered(); t_lik = tm.lap(); }
+      if (args.has("no-fit-model")) { failed_stage[gpu] = 0; return; }
+
+      // prior counts (src/mSWEEP.cpp:391-398)
+      std::vector<double> prior(ll.get_rows(), 1.0);
+      if (args.has("alphas")) {
+        std::vector<double> a;
+        for (auto &x : split(args.str("alphas", ""), ',')) a.push_back(std::stod(x));
+        if (a.size() != ll.get_rows()) throw std::runtime_error("--alphas must have the same number of values as there are groups.");
+        prior = a;
+      }
+      failed_stage[gpu] = 2;
+      if (gpu == 0) log("Estimating relative abundances");
+      std::vector<std::vector<double>> res;
+      b200::ViReport rep;
+      res.push_back(b200::rcg_optl(ctx, ll, nullptr, prior, vi, (verbose && gpu == 0) ? &std::cerr : nullptr, &rep));
+      if (gpu == 0) { report = rep; t_vi = tm.lap(); }
+      if (bootstrap) {
+        failed_stage[gpu] = 3;
+        if (gpu == 0) log("Running estimation with " + std::to_string(iters) + " bootstrap iterations");
+        auto reps = ll.bootstrap(prior, vi, iters, bootstrap_count, seed, gpu, n_gpus, rng_mode);
+        for (auto &r : reps) res.push_back(std::move(r));
+        if (gpu == 0) t_boot = tm.lap();
+      }
+      results_by_gpu[gpu] = std::move(res);
+      failed_stage[gpu] = 0;
+    } catch (const std::exception &e) {
+      errors[gpu] = e.what();
+    }
+  };
+  {
+    std::vector<std::thread> threads;
+    for (int g = 1; g < n_gpus; ++g) threads.emplace_back(worker, g);
+    worker(0);
+    for (auto &t : threads) t.join();
+  }
+  for (int g = 0; g < n_gpus; ++g) {
+    if (!failed_stage[g]) continue;
+    const char *what = failed_stage[g] == 1 ? "Building the log-likelihood array failed:\n  "
+                     : failed_stage[g] == 2 ? "Estimating relative abundances failed:\n  " : "Bootstrap iteration failed:\n  ";
+    std::cerr << what << errors[g] << "\nexiting\n";
+    return 1;
+  }
+  if (args.has("no-fit-model")) { log("Skipping relative abundance estimation (--no-fit-model toggled)"); return 0; }
+  if (min_hits > 0)
+    std::cerr << "WARNING: --min-hits > 0 is an experimental option that has not been thoroughly tested and is subject to change.\n" << std::endl;
+
+  // merge the replicates computed on the different GPUs
+  std::vector<std::vector<double>> results = results_by_gpu[0];
+  for (uint64_t r = 0; r < iters; ++r) results[r + 1] = results_by_gpu[r % n_gpus][r + 1];
+
+  // names of estimated vs pruned groups (src/mSWEEP.cpp:425-435)
+  std::vector<std::string> estimated, zero;
+  for (size_t g = 0; g < grouping.names.size(); ++g) (mask[g] ? estimated : zero).push_back(grouping.names[g]);
+
+  try {
+    const std::string o = args.str("o", "");
+    if (o.empty()) {
+      write_abundances(std::cout, n_reads, n_aligned, estimated, zero, results, iters);
+    } else {
+      std::ofstream of(o + "_abundances.txt");                        // src/OutfileDesignator.cpp:104-114
+      write_abundances(of, n_reads, n_aligned, estimated, zero, results, iters);
+    }
+  } catch (std::exception &e) {
+    std::cerr << "Writing the relative abundances failed:\n  " << e.what() << "\nexiting\n";
+    return 1;
+  }
+  if (timings)
+    std::cerr << "{\"grouping_s\": " << t_grouping << ", \"parse_s\": " << t_parse << ", \"ec_build_s\": " << t_ec
+              << ", \"likelihood_s\": " << t_lik << ", \"optimiser_s\": " << t_vi << ", \"bootstrap_s\": " << t_boot
+              << ", \"write_s\": " << timer.lap() << ", \"n_ecs\": " << n_ecs << ", \"iters\": " << report.iters
+              << ", \"bound\": " << report.bound << ", \"converged\": " << (report.converged ? "true" : "false") << "}" << std::endl;
+  return 0;
+}

@@ -1,0 +1,77 @@
+// oracle/oracle_main.cpp — command-line front end of the CPU oracle with the reference's flags for the
+// abundance-estimation path (src/mSWEEP.cpp:68-160).  TEST INFRASTRUCTURE ONLY: lets the tests compare the
+// product's mSWEEP_b200 binary against the restated reference end to end, file against file.
+#include "oracle.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace oracle;
+
+int main(int argc, char **argv) {
+  std::map<std::string, std::string> kv;
+  for (int i = 1; i < argc; ++i) {
+    std::string k = argv[i];
+    k = k.substr(k[1] == '-' ? 2 : 1);
+    if (k == "verbose") continue;
+    if (i + 1 >= argc) { std::cerr << "missing value for " << k << "\n"; return 1; }
+    kv[k] = argv[++i];
+  }
+  auto get = [&](const std::string &k, const std::string &d) { return kv.count(k) ? kv[k] : d; };
+  try {
+#ifdef _OPENMP
+    omp_set_num_threads(std::stoi(get("t", "1")));
+#endif
+    std::ifstream gi(get("i", ""));
+    Grouping grouping = read_grouping(gi);
+    std::vector<std::string> paths;
+    if (kv.count("themisto")) { std::stringstream ss(kv["themisto"]); std::string p; while (std::getline(ss, p, ',')) paths.push_back(p); }
+    else paths = {get("themisto-1", ""), get("themisto-2", "")};
+    std::vector<std::ifstream> files;
+    for (auto &p : paths) { files.emplace_back(p); if (!files.back().good()) throw std::runtime_error("cannot open " + p); }
+    std::vector<std::istream*> strands;
+    for (auto &f : files) strands.push_back(&f);
+    ReadTable reads = read_themisto(strands, grouping.group_of_target.size(), get("themisto-mode", "intersection"));
+    EcTable ec = collapse(reads);
+    const uint64_t min_hits = std::stoull(get("min-hits", "0"));
+    Likelihood lik = build_likelihood(ec, grouping, std::stod(get("q", "0.65")), std::stod(get("e", "0.01")),
+                                      std::stod(get("zero-inflation", "0.01")), min_hits, false);
+    const uint32_t K = lik.n_groups;
+    std::vector<double> prior(K, 1.0);
+    if (kv.count("alphas")) { prior.clear(); std::stringstream ss(kv["alphas"]); std::string p; while (std::getline(ss, p, ',')) prior.push_back(std::stod(p)); }
+    const double tol = std::stod(get("tol", "0.000001"));
+    const uint64_t max_iters = std::stoull(get("max-iters", "5000"));
+    const std::string algo = get("algorithm", "rcgcpu");
+    const bool rcg = algo.rfind("rcg", 0) == 0;
+    auto estimate = [&](const std::vector<double> &lc) {
+      ViResult r = rcg ? rcg_optl(lik.logl.data(), K, ec.n_ecs(), lc.data(), prior.data(), tol, max_iters)
+                       : em_optl(lik.logl.data(), K, ec.n_ecs(), lc.data(), prior.data(), tol, max_iters);
+      return mixture_components(r.gamma.data(), K, ec.n_ecs(), lc.data());
+    };
+    std::vector<std::vector<double>> results;
+    results.push_back(estimate(lik.log_counts));
+    const uint64_t iters = std::stoull(get("iters", "0"));
+    if (iters) {
+      Bootstrapper bs(ec.count, (int32_t)std::stoull(get("seed", "26012023")), std::stoull(get("bootstrap-count", "0")));
+      for (uint64_t r = 0; r < iters; ++r) results.push_back(estimate(bs.resample_counts()));
+    }
+    std::vector<std::string> est, zero;
+    for (size_t g = 0; g < grouping.names.size(); ++g) (lik.groups_mask[g] ? est : zero).push_back(grouping.names[g]);
+    uint64_t n_aligned = 0;
+    for (auto c : ec.count) n_aligned += c;
+    std::ofstream of(get("o", "oracle") + "_abundances.txt");
+    write_abundances(of, get("version-string", "oracle"), reads.n_reads, n_aligned, est, zero, results, iters);
+  } catch (const std::exception &e) {
+    std::cerr << "oracle failed:\n  " << e.what() << "\nexiting\n";
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,109 @@
+"""GPU: the mSWEEP_b200 binary end to end (files in, <prefix>_abundances.txt out) against the oracle's
+command-line front end on the same files: the reference's output format byte for byte (modulo the
+version line), abundances within the printed precision."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from msweep_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "msweep_b200", "bin", "mSWEEP_b200")
+ORACLE = os.path.join(ROOT, "oracle", "msweep_oracle")
+
+
+@pytest.fixture(scope="module")
+def data(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli")
+    wl = synth.generate(20000, 600, 30, n_present=4, n_templates=200, p_noise=0.02, seed=31)
+    paths = synth.write_themisto(str(d / "aln"), wl, paired=True, shuffle_frac=0.05)
+    g = str(d / "grouping.txt")
+    synth.write_grouping(g, wl)
+    return d, wl, paths, g
+
+
+def parse_abundances(path):
+    head, rows = [], []
+    for line in open(path).read().splitlines():
+        (head if line.startswith("#") else rows).append(line)
+    names = [r.split("\t")[0] for r in rows]
+    vals = np.array([[float(x) for x in r.split("\t")[1:]] for r in rows])
+    return head, names, vals
+
+
+def run_both(d, paths, g, extra, tag, oracle_algo="rcgcpu"):
+    ours, ref = str(d / f"ours_{tag}"), str(d / f"ref_{tag}")
+    r = subprocess.run([CLI, "--themisto-1", paths[0], "--themisto-2", paths[1], "-i", g, "-o", ours, "-t", "4", *extra],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ex = [x for x in extra if x not in ("rcgb200", "emb200")]
+    if "--algorithm" in ex:
+        ex.remove("--algorithm")
+    r2 = subprocess.run([ORACLE, "--themisto-1", paths[0], "--themisto-2", paths[1], "-i", g, "-o", ref, "-t", "4",
+                         "--algorithm", oracle_algo, *ex], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    return parse_abundances(ours + "_abundances.txt"), parse_abundances(ref + "_abundances.txt"), r.stderr
+
+
+def test_plain_estimate(data):
+    d, wl, paths, g = data
+    (h, names, vals), (h2, names2, vals2), _ = run_both(d, paths, g, [], "plain")
+    assert h[0].startswith("#mSWEEP_version:\t")
+    assert h[1:] == h2[1:]                                  # num_reads, num_aligned, column header: identical bytes
+    assert h[1] == f"#num_reads:\t{wl.n_reads}" and h[-1] == "#c_id\tmean_theta"
+    assert names == names2 == wl.group_names
+    assert np.max(np.abs(vals - vals2)) < 2e-6              # 6 significant digits are printed
+    assert abs(vals.sum() - 1.0) < 1e-5
+
+
+def test_em_and_float_precision(data):
+    d, wl, paths, g = data
+    (h, names, vals), (h2, _, vals2), _ = run_both(d, paths, g, ["--algorithm", "emb200"], "em", oracle_algo="emgpu")
+    assert h[1:] == h2[1:] and np.max(np.abs(vals - vals2)) < 2e-6
+    (h, names, vals3), _, _ = run_both(d, paths, g, ["--algorithm", "emb200", "--emprecision", "float", "--tol", "1e-5"], "emf",
+                                       oracle_algo="emgpu")
+    assert np.max(np.abs(vals3 - vals2)) < 1e-3             # float EM stops elsewhere on the plateau (docs/gpubenchmarks.md:27)
+
+
+def test_min_hits_orders_pruned_groups_last(data):
+    d, wl, paths, g = data
+    (h, names, vals), (h2, names2, vals2), err = run_both(d, paths, g, ["--min-hits", "200"], "mh")
+    assert "WARNING: --min-hits > 0 is an experimental option" in err
+    assert names == names2 and sorted(names) == sorted(wl.group_names)
+    assert np.max(np.abs(vals - vals2)) < 2e-6
+    n_zero = int((vals[:, 0] == 0).sum())
+    assert n_zero > 0 and np.all(vals[-n_zero:, 0] == 0) and np.all(vals[:-n_zero, 0] > 0)   # src/PlainSample.cpp:56-66
+
+
+def test_bootstrap_output(data):
+    d, wl, paths, g = data
+    (h, names, vals), (h2, names2, vals2), _ = run_both(d, paths, g, ["--iters", "3", "--seed", "11"], "boot")
+    assert h[1:] == h2[1:]
+    assert h[3] == "#bootstrap_iters:\t3" and h[4] == "#c_id\tmean_theta\tbootstrap_mean_thetas"
+    assert vals.shape == (len(wl.group_names), 4)
+    assert np.max(np.abs(vals - vals2)) < 2e-6              # same mt19937_64 stream -> same resampled counts -> same estimates
+
+
+def test_options_reach_the_model(data):
+    d, wl, paths, g = data
+    extra = ["-q", "0.5", "-e", "0.02", "--zero-inflation", "0.02", "--alphas", ",".join(["0.7"] * wl.n_groups), "--tol", "1e-8",
+             "--themisto-mode", "union"]
+    (h, names, vals), (h2, names2, vals2), _ = run_both(d, paths, g, extra, "opts")
+    assert h[1:] == h2[1:] and np.max(np.abs(vals - vals2)) < 2e-6
+
+
+def test_stdout_when_no_prefix_and_timings(data):
+    d, wl, paths, g = data
+    r = subprocess.run([CLI, "--themisto", ",".join(paths), "-i", g, "--print-timings"], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert r.stdout.startswith("#mSWEEP_version:\t") and r.stdout.count("\n") == 4 + wl.n_groups
+    assert '"optimiser_s"' in r.stderr
+
+
+def test_alphas_length_is_checked(data):
+    d, wl, paths, g = data
+    r = subprocess.run([CLI, "--themisto", ",".join(paths), "-i", g, "--alphas", "1,1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "--alphas must have the same number of values as there are groups." in r.stderr

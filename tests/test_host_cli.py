@@ -1,0 +1,137 @@
+"""CPU: the C++17 host driver (msweep_b200/bin/mSWEEP_b200) up to the point where it needs the GPU:
+argument handling with the reference's messages and exit codes, the -i reader, and the multi-threaded
+Themisto parser against the oracle's line-by-line restatement of include/mSWEEP_alignment.hpp:54-135."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from msweep_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "msweep_b200", "bin", "mSWEEP_b200")
+
+
+def run(*args):
+    return subprocess.run([CLI, *args], capture_output=True, text=True)
+
+
+def dump(tmp_path, paths, grouping, mode="intersection", threads=4):
+    out = str(tmp_path / "aln.bin")
+    r = run("--themisto", ",".join(paths), "-i", grouping, "--themisto-mode", mode, "-t", str(threads), "--dump-alignment", out)
+    assert r.returncode == 0, r.stderr
+    raw = open(out, "rb").read()
+    R, T = np.frombuffer(raw[:16], np.uint64)
+    rp = np.frombuffer(raw[16:16 + 8 * (int(R) + 1)], np.uint64)
+    tg = np.frombuffer(raw[16 + 8 * (int(R) + 1):], np.uint32)
+    return int(R), int(T), rp, tg
+
+
+def test_binary_exists():
+    assert os.path.exists(CLI), "build with python -m msweep_b200._build"
+
+
+def test_version_help_cite():
+    assert run("--version").returncode == 0 and "mSWEEP-" in run("--version").stderr
+    assert "Usage: mSWEEP_b200" in run("--help").stderr
+    assert "Wellcome Open Res" in run("--cite").stderr
+
+
+@pytest.mark.parametrize("argv,msg", [
+    (["--themisto", "x"], "Required argument -i"),
+    (["-i", "g"], "No pseudoalignment files"),
+    (["-i", "g", "--themisto-1", "a"], "must be given together"),
+    (["-i", "g", "--themisto", "a", "--bogus", "1"], "Unknown argument"),
+    (["-i", "g", "--themisto", "a", "--bin-reads"], "outside the scope"),
+    (["-i", "g", "--themisto", "a", "-o", "/nonexistent_dir_xyz/out"], "does not seem to exist"),
+])
+def test_argument_errors(argv, msg):
+    r = run(*argv)
+    assert r.returncode == 1
+    assert r.stderr.startswith("Error in parsing arguments:\n  ") and r.stderr.endswith("\nexiting\n")   # src/mSWEEP.cpp:240-245
+    assert msg in r.stderr
+
+
+def test_algorithm_is_validated(tmp_path):
+    g = tmp_path / "g.txt"
+    g.write_text("a\nb\n")
+    for algo, msg in (("rcgcpu", "no CPU path"), ("foo", "Unknown --algorithm")):
+        r = run("-i", str(g), "--themisto", "x", "--algorithm", algo)
+        assert r.returncode == 1 and msg in r.stderr
+
+
+def test_grouping_errors(tmp_path):
+    r = run("-i", str(tmp_path / "missing.txt"), "--themisto", "x")
+    assert r.returncode == 1 and r.stderr == "Reading group indicators failed:\n  Could not read cluster indicators.\nexiting\n"
+    empty = tmp_path / "empty.txt"
+    empty.write_text("")
+    r = run("-i", str(empty), "--themisto", "x")
+    assert r.returncode == 1 and "The grouping contains 0 reference sequences" in r.stderr
+
+
+@pytest.mark.parametrize("mode", ["intersection", "union"])
+@pytest.mark.parametrize("threads", [1, 5])
+def test_parser_matches_oracle(oracle, tmp_path, mode, threads):
+    wl = synth.generate(3000, 90, 6, n_present=3, n_templates=40, p_noise=0.05, seed=21)
+    paths = synth.write_themisto(str(tmp_path / "aln"), wl, paired=True, shuffle_frac=0.2)
+    gpath = str(tmp_path / "g.txt")
+    synth.write_grouping(gpath, wl)
+    R, T, rp, tg = dump(tmp_path, paths, gpath, mode, threads)
+    n, rp_o, tg_o = oracle.read_themisto(paths, wl.n_targets, mode)
+    assert (R, T) == (n, wl.n_targets)
+    assert np.array_equal(rp, rp_o) and np.array_equal(tg, tg_o)
+    if mode == "intersection":
+        assert np.array_equal(rp, wl.row_ptr) and np.array_equal(tg, wl.targets)
+
+
+def test_parser_quirks_match_reference_semantics(oracle, tmp_path):
+    """Duplicate ids accumulate, unsorted and repeated targets collapse to a bit set, a target id >= T
+    lands in a later read's row (flat bit index, mSWEEP_alignment.hpp:64), rows past the line count are
+    ignored, a trailing space and CRLF are tolerated."""
+    g = tmp_path / "g.txt"
+    g.write_text("".join(f"g{i % 3}\n" for i in range(10)))
+    a = tmp_path / "a.aln"
+    a.write_text("0 5 3 3 1\n2 7 \n1\n0 9\n3 12\r\n7 1\n")
+    R, T, rp, tg = dump(tmp_path, [str(a)], str(g))
+    n, rp_o, tg_o = oracle.read_themisto([str(a)], 10, "intersection")
+    assert R == n == 6
+    assert np.array_equal(rp, rp_o) and np.array_equal(tg, tg_o)
+    rows = [list(tg[int(rp[i]):int(rp[i + 1])]) for i in range(R)]
+    assert rows[0] == [1, 3, 5, 9] and rows[2] == [7] and rows[1] == [] and rows[4] == [2] and rows[3] == []
+
+
+@pytest.mark.parametrize("content,line", [("0 1\nx 2\n", 2), ("0 1\n1  2\n", 2), ("0 1\n\n", 2), ("0 a\n", 1)])
+def test_parser_errors_name_the_line(tmp_path, content, line):
+    g = tmp_path / "g.txt"
+    g.write_text("a\nb\nc\n")
+    a = tmp_path / "a.aln"
+    a.write_text(content)
+    r = run("--themisto", str(a), "-i", str(g), "-t", "3", "--dump-alignment", str(tmp_path / "o.bin"))
+    assert r.returncode == 1
+    assert r.stderr.startswith("Reading the pseudoalignments failed:\n  File format not supported on line %d with content: " % line)
+
+
+def test_bad_merge_mode_and_compact_format(tmp_path):
+    g = tmp_path / "g.txt"
+    g.write_text("a\nb\nc\n")
+    a = tmp_path / "a.aln"
+    a.write_text("0 1\n1 2\n")
+    r = run("--themisto", f"{a},{a}", "-i", str(g), "--themisto-mode", "unpaired", "--dump-alignment", str(tmp_path / "o.bin"))
+    assert r.returncode == 1 and "Unrecognized option `unpaired` for --themisto-mode" in r.stderr
+    c = tmp_path / "c.aln"
+    c.write_text("n_reads:2,n_refs:3\n")
+    r = run("--themisto", str(c), "-i", str(g), "--dump-alignment", str(tmp_path / "o.bin"))
+    assert r.returncode == 1 and "compact" in r.stderr
+
+
+def test_no_gpu_fails_loudly(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    g = tmp_path / "g.txt"
+    g.write_text("a\nb\nc\n")
+    a = tmp_path / "a.aln"
+    a.write_text("0 1\n1 2\n")
+    r = run("--themisto", str(a), "-i", str(g))
+    assert r.returncode == 1 and "no CUDA device available" in r.stderr and r.stdout == ""
