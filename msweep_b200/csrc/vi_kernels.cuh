@@ -236,11 +236,16 @@ template <int R> __device__ __forceinline__ double warp_rows_sum(const double (&
 // lane that canonically holds row r after warp_rows_sum<R>
 template <int R> __device__ __forceinline__ int holder_lane(int r) { return R == 4 ? 16 * (r >> 1) + 8 * (r & 1) : (R == 2 ? 16 * r : 0); }
 
-// Two CTAs per SM when the two register buffers are small enough to leave room (<= 128 registers each).
-template <class TL> constexpr int em_min_blocks() { return TL::R * TL::KITER <= 8 && TL::NT <= 256 ? 2 : 1; }
+// Two CTAs per SM when the two register buffers, the accumulators and the weights leave room within 128
+// registers per thread (estimate in 32-bit registers: 2 buffers x R x KITER x 4, KITER x VEC doubles, KITER x VEC weights).
+template <typename ST, class TL> constexpr int em_min_blocks() {
+  constexpr int VEC = 16 / (int)sizeof(ST);
+  constexpr int est = 8 * TL::R * TL::KITER + 2 * TL::KITER * VEC + TL::KITER * VEC * ((int)sizeof(ST) / 4);
+  return est <= 100 && TL::NT <= 256 ? 2 : 1;
+}
 
 template <typename ST, class TL, bool PIPE>
-__global__ void __launch_bounds__(TL::NT, em_min_blocks<TL>())
+__global__ void __launch_bounds__(TL::NT, em_min_blocks<ST, TL>())
 em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ rowmax, const double *__restrict__ counts,
                    const double *__restrict__ w, const ViCtl *__restrict__ ctl, double *__restrict__ partials,
                    int pstride, unsigned long long N_pad, int K, PipeGeom geom) {
