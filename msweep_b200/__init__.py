@@ -15,7 +15,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmsweep_b200.so")
+LIB_PATH = os.environ.get("MSWB_LIB_PATH", os.path.join(_HERE, "lib", "libmsweep_b200.so"))   # override: A/B runs only
 HEADER_PATH = os.path.join(_HERE, "..", "include", "msweep_b200.h")
 
 ALGO_RCG, ALGO_EM = 0, 1

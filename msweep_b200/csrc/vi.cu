@@ -300,6 +300,22 @@ namespace {
     else throw Error("too many groups for the compiled tile shapes (max 16384 in fp64)");   \
   } while (0)
 
+// Log-domain sweeps: RA rows per batch for shapes with KITER <= 2, RB for KITER = 4, 1 row for KITER = 8.
+// Sweep A keeps two arrays live (R * KITER <= 8 for two CTAs per SM), sweep B four (R * KITER <= 4).
+#define MSWB_TILE_DISPATCH_RCG(slots, R1, R2, R4, ...)                                       \
+  do {                                                                                       \
+    if ((slots) <= 32) { using TL = Tile<32, 1, R1>; __VA_ARGS__; }                          \
+    else if ((slots) <= 64) { using TL = Tile<32, 2, R2>; __VA_ARGS__; }                     \
+    else if ((slots) <= 128) { using TL = Tile<32, 4, R4>; __VA_ARGS__; }                    \
+    else if ((slots) <= 256) { using TL = Tile<64, 4, R4>; __VA_ARGS__; }                    \
+    else if ((slots) <= 512) { using TL = Tile<128, 4, R4>; __VA_ARGS__; }                   \
+    else if ((slots) <= 1024) { using TL = Tile<256, 4, R4>; __VA_ARGS__; }                  \
+    else if ((slots) <= 2048) { using TL = Tile<256, 8, 1>; __VA_ARGS__; }                   \
+    else if ((slots) <= 4096) { using TL = Tile<512, 8, 1>; __VA_ARGS__; }                   \
+    else if ((slots) <= 8192) { using TL = Tile<1024, 8, 1>; __VA_ARGS__; }                  \
+    else throw Error("too many groups for the compiled tile shapes (max 16384 in fp64)");   \
+  } while (0)
+
 constexpr size_t SMEM_BUDGET = 200 * 1024;   // dynamic shared memory for the stage ring (of 227 KB per CTA)
 
 // Stage ring geometry for a sweep that streams `nsrc` arrays with rows of `row_bytes`, consumed in
@@ -378,6 +394,13 @@ bool want_rcg_pipe() { const char *e = getenv("MSWB_RCG_TMA"); return e && e[0] 
     MSWB_LAUNCHED();                                                                                           \
   } while (0)
 
+// Batch -> CTA mapping of the direct EM sweep (see the kernel): chunked once the matrix is large.
+static bool em_chunked(const mswb_lik *L) {
+  if (const char *e = getenv("MSWB_EM_CHUNKED")) return e[0] == '1';
+  const size_t el = L->storage == MSWB_STORE_F32 ? 4 : 8;
+  return (size_t)L->N_pad * L->K * el > ((size_t)16 << 30);   // measured: +1.2 % at 100 GB, neutral at 24 GB
+}
+
 // EM sweep launch: staged (TMA) when asked for and possible, else direct + register prefetch.
 #define MSWB_LAUNCH_EM(ST, PTR, LD)                                                                            \
   do {                                                                                                         \
@@ -419,7 +442,7 @@ void em_iteration(mswb_vi *vi) {
     else if (rsel == 4) MSWB_TILE_DISPATCH(L->Kp / 2, 4, 4, 2, MSWB_LAUNCH_EM(double, L->P64.p, L->Kp));
     else MSWB_TILE_DISPATCH_EM(L->Kp / 2, MSWB_LAUNCH_EM(double, L->P64.p, L->Kp));
   } else {
-    MSWB_TILE_DISPATCH(L->Kp / 2, 2, 1, 1,
+    MSWB_TILE_DISPATCH_RCG(L->Kp / 2, 4, 2, 1,
       MSWB_LAUNCH_SWEEP((rcg_sweep_b_kernel<TL, 1, false, true>), (rcg_sweep_b_kernel<TL, 1, false, false>), (size_t)L->Kp * 8, 3,
                         L->logl.p, (double *)nullptr, (double *)nullptr, (int)L->Kp, vi->dg.p, vi->counts, vi->ctl.p,
                         vi->partials.p, vi->pstride, L->N, K, 0));
@@ -442,7 +465,7 @@ void rcg_iteration(mswb_vi *vi) {
   // sweep A: gradient norm
   {
     PassTimer timer(vi);
-    MSWB_TILE_DISPATCH(slots, 2, 2, 1,
+    MSWB_TILE_DISPATCH_RCG(slots, 4, 4, 2,
       MSWB_LAUNCH_SWEEP((rcg_sweep_a_kernel<TL, true>), (rcg_sweep_a_kernel<TL, false>), row_bytes, 2,
                         L->logl.p, L->gamma.p, ld, vi->dg.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N, K));
     timer.stop();
@@ -459,7 +482,7 @@ void rcg_iteration(mswb_vi *vi) {
   // sweep B: step, renormalise, N_k, bound
   {
     PassTimer timer(vi);
-    MSWB_TILE_DISPATCH(slots, 2, 1, 1,
+    MSWB_TILE_DISPATCH_RCG(slots, 4, 2, 1,
       MSWB_LAUNCH_SWEEP((rcg_sweep_b_kernel<TL, 0, true, true>), (rcg_sweep_b_kernel<TL, 0, true, false>), row_bytes, 3,
                         L->logl.p, L->gamma.p, L->step.p, ld, vi->dg.p, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride,
                         L->N, K, 0));
@@ -470,7 +493,7 @@ void rcg_iteration(mswb_vi *vi) {
   rcg_ctl_b_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, 0);
   MSWB_LAUNCHED();
   // restart sweep: runs only when the control block says so (device-side decision, no host round trip)
-  MSWB_TILE_DISPATCH(slots, 2, 1, 1,
+  MSWB_TILE_DISPATCH_RCG(slots, 4, 2, 1,
     MSWB_LAUNCH_SWEEP((rcg_sweep_b_kernel<TL, 1, true, true>), (rcg_sweep_b_kernel<TL, 1, true, false>), row_bytes, 3,
                       L->logl.p, L->gamma.p, L->step.p, ld, vi->dg.p, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride,
                       L->N, K, 1));

@@ -19,6 +19,8 @@
 //   PIPE = false  direct 128-bit streaming loads into registers (fallback for rows too long to stage).
 #pragma once
 #include "common.cuh"
+#include "mathfn.cuh"
+#include <type_traits>
 
 namespace mswb {
 
@@ -371,16 +373,22 @@ em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ 
 #pragma unroll
       for (int i = 0; i < KITER; ++i) { bufA[r][i] = zero; bufB[r][i] = zero; }
     double cA = 0.0, cB = 0.0;
-    const unsigned long long stride = gridDim.x;
-    unsigned long long b = blockIdx.x;
-    if (b < n_batches) {
-      const unsigned long long last = n_batches - 1;
+    // Batch -> CTA mapping.  Interleaved (stride = grid): the whole GPU reads one contiguous window at a time.
+    // Chunked (geom.stage_rows == 1 in direct mode): every CTA walks its own contiguous range of batches, so an SM
+    // stays inside one 2 MB page for many batches — far fewer TLB fills once the matrix outgrows the TLB reach.
+    const bool chunked = geom.stage_rows == 1;
+    const unsigned long long per = (n_batches + gridDim.x - 1) / gridDim.x;
+    const unsigned long long stride = chunked ? 1 : gridDim.x;
+    unsigned long long b = chunked ? blockIdx.x * per : blockIdx.x;
+    const unsigned long long b_end = chunked ? min(n_batches, b + per) : n_batches;
+    if (b < b_end) {
+      const unsigned long long last = b_end - 1;
       fetch(bufA, cA, b);
-      for (; b < n_batches; b += 2 * stride) {
+      for (; b < b_end; b += 2 * stride) {
         const unsigned long long b1 = b + stride;
         fetch(bufB, cB, min(b1, last));                 // past the end: a harmless reload, never processed
         process(bufA, cA, b * RB + (unsigned long long)g * R);
-        if (b1 < n_batches) {
+        if (b1 < b_end) {
           fetch(bufA, cA, min(b1 + stride, last));
           process(bufB, cB, b1 * RB + (unsigned long long)g * R);
         }
@@ -421,11 +429,67 @@ em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ 
 // Log-domain sweeps (fp64): the RCG optimiser, the restart step, and the log-domain EM pass.
 // =====================================================================================================
 
+// Reduce R per-row values over the TPR threads of a row group (sum or max).  On return lanes 0..R-1 of every
+// warp of the group hold the group-wide result of row `lane`; other lanes hold unspecified values.
+// Transposing butterfly inside the warp (6 / 6 / 5 64-bit shuffles for R = 4 / 2 / 1), then one
+// shared-memory hop when the row spans several warps.  scratch: 2 * NW * R doubles.
+template <bool IS_MAX> __device__ __forceinline__ double red_op(double a, double b) { return IS_MAX ? fmax(a, b) : a + b; }
+
+template <class TL, bool IS_MAX>
+__device__ __forceinline__ double rows_reduce(const double (&v)[TL::R], double *scratch, int &phase, int lane, int warp) {
+  constexpr int R = TL::R;
+  static_assert(R == 1 || R == 2 || R == 4, "rows per batch must be 1, 2 or 4");
+  double k;
+  int rid;
+  if constexpr (R == 4) {
+    const bool hi = lane & 16, h8 = lane & 8;
+    double a0 = hi ? v[2] : v[0], a1 = hi ? v[3] : v[1];
+    const double b0 = hi ? v[0] : v[2], b1 = hi ? v[1] : v[3];
+    a0 = red_op<IS_MAX>(a0, __shfl_xor_sync(0xffffffffu, b0, 16));
+    a1 = red_op<IS_MAX>(a1, __shfl_xor_sync(0xffffffffu, b1, 16));
+    k = h8 ? a1 : a0;
+    const double snd = h8 ? a0 : a1;
+    k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, snd, 8));
+    rid = (hi ? 2 : 0) + (h8 ? 1 : 0);
+  } else if constexpr (R == 2) {
+    const bool hi = lane & 16;
+    k = hi ? v[1] : v[0];
+    const double snd = hi ? v[0] : v[1];
+    k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, snd, 16));
+    k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 8));
+    rid = hi ? 1 : 0;
+  } else {
+    k = v[0];
+    k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 16));
+    k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 8));
+    rid = 0;
+  }
+  k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 4));
+  k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 2));
+  k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 1));
+  if constexpr (TL::WPG > 1) {
+    double *buf = scratch + phase * (TL::NW * R);
+    phase ^= 1;
+    if ((lane & (R == 4 ? 7 : (R == 2 ? 15 : 31))) == 0) buf[warp * R + rid] = k;
+    __syncthreads();
+    double tot = IS_MAX ? -INFINITY : 0.0;
+    if (lane < R) {
+      const int w0 = (warp / TL::WPG) * TL::WPG;
+#pragma unroll
+      for (int ww = 0; ww < TL::WPG; ++ww) tot = red_op<IS_MAX>(tot, buf[(w0 + ww) * R + lane]);
+    }
+    return tot;
+  } else {
+    const int src = R == 4 ? 16 * ((lane >> 1) & 1) + 8 * (lane & 1) : (R == 2 ? 16 * (lane & 1) : 0);
+    return __shfl_sync(0xffffffffu, k, src);
+  }
+}
+
 // Sweep A of an RCG iteration ("mixt_negnatgrad"): d = logl + (digamma(N_k) - 1) - gamma,
 // newnorm = sum_jk q (d - <d>_j) d  with q = exp(gamma), <d>_j = sum_k q d.  Nothing is written: d is
 // recomputed by sweep B, which saves 16 B/element of traffic over storing it.
 template <class TL, bool PIPE>
-__global__ void __launch_bounds__(TL::NT)
+__global__ void __launch_bounds__(TL::NT, TL::R * TL::KITER <= 8 && TL::NT <= 256 ? 2 : 1)
 rcg_sweep_a_kernel(const double *__restrict__ logl, const double *__restrict__ gamma, int ld,
                    const double *__restrict__ dgm1, const ViCtl *__restrict__ ctl, double *__restrict__ partials,
                    int pstride, unsigned long long N, int K, PipeGeom geom) {
@@ -434,54 +498,80 @@ rcg_sweep_a_kernel(const double *__restrict__ logl, const double *__restrict__ g
   __shared__ double s_red[2 * TL::NW * R];
   __shared__ double s_blk[32];
   const int t = threadIdx.x % TPR, g = threadIdx.x / TPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = ld / 2;
   double dk[KITER][2];
   bool ok[KITER][2];
+  bool cols_ok = true;
 #pragma unroll
   for (int i = 0; i < KITER; ++i)
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       const int k = 2 * (t + TPR * i) + v;
       ok[i][v] = k < K;
+      cols_ok = cols_ok && ok[i][v];
       dk[i][v] = ok[i][v] ? dgm1[k] : 0.0;
     }
   double nn = 0.0;
   int phase = 0;
-  const int nvec = ld / 2;
+  const bool warp_cols_ok = __all_sync(0xffffffffu, cols_ok) != 0;
 
   auto body = [&](auto &&load, unsigned long long row0) {   // load(src, r, idx): src 0 = logl, 1 = gamma
     double d[R][KITER][2], q[R][KITER][2];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int i = 0; i < KITER; ++i) {
-        const int idx = t + TPR * i;
-        if (row0 + r < N && idx < nvec) { unpack(load(0, r, idx), d[r][i]); unpack(load(1, r, idx), q[r][i]); }
-        else { d[r][i][0] = d[r][i][1] = 0.0; q[r][i][0] = q[r][i][1] = 0.0; }
-      }
     double s[R];
+    if (warp_cols_ok && row0 + R <= N) {
+      // fast path (warp-uniform): every row and column this warp touches is real — no predicates
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int i = 0; i < KITER; ++i) { unpack(load(0, r, t + TPR * i), d[r][i]); unpack(load(1, r, t + TPR * i), q[r][i]); }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        s[r] = 0.0;
+#pragma unroll
+        for (int i = 0; i < KITER; ++i)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const double gam = q[r][i][v];
+            d[r][i][v] = d[r][i][v] + dk[i][v] - gam;
+            q[r][i][v] = exp_nonpos(gam);
+            s[r] = fma(d[r][i][v], q[r][i][v], s[r]);
+          }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int i = 0; i < KITER; ++i) {
+          const int idx = t + TPR * i;
+          if (row0 + r < N && idx < nvec) { unpack(load(0, r, idx), d[r][i]); unpack(load(1, r, idx), q[r][i]); }
+          else { d[r][i][0] = d[r][i][1] = 0.0; q[r][i][0] = q[r][i][1] = 0.0; }
+        }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool rv = row0 + r < N;
+        s[r] = 0.0;
+#pragma unroll
+        for (int i = 0; i < KITER; ++i)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const bool on = rv && ok[i][v];
+            const double gam = q[r][i][v];
+            d[r][i][v] = on ? d[r][i][v] + dk[i][v] - gam : 0.0;
+            q[r][i][v] = on ? exp_nonpos(fmin(gam, 0.0)) : 0.0;
+            s[r] = fma(d[r][i][v], q[r][i][v], s[r]);
+          }
+      }
+    }
+    const double tot = rows_reduce<TL, false>(s, s_red, phase, lane, warp);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const bool rv = row0 + r < N;
-      s[r] = 0.0;
+      const double sr = __shfl_sync(0xffffffffu, tot, r);
 #pragma unroll
       for (int i = 0; i < KITER; ++i)
 #pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          const bool on = rv && ok[i][v];
-          const double gam = q[r][i][v];
-          const double dd = on ? d[r][i][v] + dk[i][v] - gam : 0.0;
-          const double qq = on ? exp(gam) : 0.0;
-          d[r][i][v] = dd; q[r][i][v] = qq;
-          s[r] = fma(dd, qq, s[r]);
-        }
+        for (int v = 0; v < 2; ++v) nn = fma(q[r][i][v] * (d[r][i][v] - sr), d[r][i][v], nn);
     }
-    group_reduce<TL, false>(s, s_red, phase);
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int i = 0; i < KITER; ++i)
-#pragma unroll
-        for (int v = 0; v < 2; ++v) nn = fma(q[r][i][v] * (d[r][i][v] - s[r]), d[r][i][v], nn);
   };
 
   if constexpr (!PIPE) {
@@ -489,9 +579,9 @@ rcg_sweep_a_kernel(const double *__restrict__ logl, const double *__restrict__ g
     const unsigned long long n_batches = (N + rows_per_batch - 1) / rows_per_batch;
     for (unsigned long long b = blockIdx.x; b < n_batches; b += gridDim.x) {
       const unsigned long long row0 = b * rows_per_batch + (unsigned long long)g * R;
-      body([&](int s, int r, int idx) {
-        return ld_stream(reinterpret_cast<const double2 *>((s == 0 ? logl : gamma) + (row0 + r) * (unsigned long long)ld) + idx);
-      }, row0);
+      const double2 *lp = reinterpret_cast<const double2 *>(logl) + row0 * (unsigned long long)nvec;
+      const double2 *gp = reinterpret_cast<const double2 *>(gamma) + row0 * (unsigned long long)nvec;
+      body([&](int s, int r, int idx) { return ld_stream((s == 0 ? lp : gp) + (size_t)r * nvec + idx); }, row0);
     }
   } else {
     RowPipe<2> pipe;
@@ -522,7 +612,7 @@ rcg_sweep_a_kernel(const double *__restrict__ logl, const double *__restrict__ g
 // MODE 0: RCG step.  MODE 1: plain step from the current digamma vector, gamma = normalise(logl + dg)
 // (the RCG restart, and the log-domain EM pass); WRITE says whether gamma is stored.
 template <class TL, int MODE, bool WRITE, bool PIPE>
-__global__ void __launch_bounds__(TL::NT)
+__global__ void __launch_bounds__(TL::NT, TL::R * TL::KITER <= 4 && TL::NT <= 256 ? 2 : 1)
 rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, double *__restrict__ step, int ld,
                    const double *__restrict__ dgv, const double *__restrict__ counts, const ViCtl *__restrict__ ctl,
                    double *__restrict__ partials, int pstride, unsigned long long N, int K, int only_if_reset,
@@ -534,16 +624,21 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
   __shared__ double s_comb[TL::G > 1 ? TL::G * TPR * KITER * 2 : 1];
   __shared__ double s_blk[32];
   const int t = threadIdx.x % TPR, g = threadIdx.x / TPR;
-  const double beta = ctl->beta;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool use_old = MODE == 0 && ctl->use_old != 0;
+  const double beta_eff = use_old ? ctl->beta : 0.0;   // step = d + beta * oldstep; no direction memory -> beta 0
+  const int nvec = ld / 2;
+  const double NEG_INF = -INFINITY;
   double dk[KITER][2];
   bool ok[KITER][2];
+  bool cols_ok = true;
 #pragma unroll
   for (int i = 0; i < KITER; ++i)
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       const int k = 2 * (t + TPR * i) + v;
       ok[i][v] = k < K;
+      cols_ok = cols_ok && ok[i][v];
       dk[i][v] = ok[i][v] ? dgv[k] : 0.0;
     }
   double acc[KITER][2];
@@ -551,100 +646,125 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
   for (int i = 0; i < KITER; ++i) acc[i][0] = acc[i][1] = 0.0;
   double bound = 0.0;
   int phase = 0;
-  const int nvec = ld / 2;
-  const double NEG_INF = -INFINITY;
 
+  // One batch = three element-wise phases separated by two row reductions.  The phases exist in two
+  // compile-time flavours: FULL (every row and column this WARP touches is real: no predicates, the loads of a
+  // batch issue back to back) and the predicated one for ragged edges.  The choice is warp-uniform and the
+  // reductions (shuffles with a full mask, __syncthreads) sit outside the flavoured code, in common control flow.
+  const bool warp_cols_ok = __all_sync(0xffffffffu, cols_ok) != 0;
   auto body = [&](auto &&load, unsigned long long row0) {   // load(src, r, idx): 0 = logl, 1 = gamma, 2 = old step
-    double l[R][KITER][2], gn[R][KITER][2];
-    {
+    const bool full = warp_cols_ok && row0 + R <= N;        // uniform over the warp (a warp never spans two row groups)
+    double l[R][KITER][2], gn[R][KITER][2], m[R];
+    double e[R][KITER][2], sum[R], lsum[R], cinv[R];
+
+    // FULL is a literal at both call sites; the lambda is inlined and specialised for it
+    auto phase1 = [&](const bool FULL) {
       double st[R][KITER][2];
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int i = 0; i < KITER; ++i) {
           const int idx = t + TPR * i;
-          const bool in = row0 + r < N && idx < nvec;
+          const bool in = FULL || (row0 + r < N && idx < nvec);
           if (in) unpack(load(0, r, idx), l[r][i]); else l[r][i][0] = l[r][i][1] = 0.0;
-          if (MODE == 0) {
-            if (in) unpack(load(1, r, idx), gn[r][i]); else gn[r][i][0] = gn[r][i][1] = 0.0;
-            if (in && use_old) unpack(load(2, r, idx), st[r][i]); else st[r][i][0] = st[r][i][1] = 0.0;
-          }
+          if (MODE == 0) { if (in) unpack(load(1, r, idx), gn[r][i]); else gn[r][i][0] = gn[r][i][1] = 0.0; }
         }
+      if (MODE == 0 && use_old) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int i = 0; i < KITER; ++i) {
+            const int idx = t + TPR * i;
+            const bool in = FULL || (row0 + r < N && idx < nvec);
+            if (in) unpack(load(2, r, idx), st[r][i]); else st[r][i][0] = st[r][i][1] = 0.0;
+          }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int i = 0; i < KITER; ++i) st[r][i][0] = st[r][i][1] = 0.0;
+      }
       // the new direction leaves for HBM straight away so that its registers die before the reductions
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const unsigned long long row = row0 + r;
-        double2 *sp = reinterpret_cast<double2 *>(step + row * (unsigned long long)ld);
+        double2 *sp = reinterpret_cast<double2 *>(step) + row * (unsigned long long)nvec;
+        m[r] = NEG_INF;
 #pragma unroll
         for (int i = 0; i < KITER; ++i) {
           const int idx = t + TPR * i;
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
-            const bool on = row < N && ok[i][v];
+            const bool on = FULL || (row < N && ok[i][v]);
             double g2;
             if (MODE == 0) {
               const double d = l[r][i][v] + dk[i][v] - gn[r][i][v];
-              const double s = use_old ? fma(beta, st[r][i][v], d) : d;
+              const double s = fma(beta_eff, st[r][i][v], d);
               st[r][i][v] = on ? s : 0.0;
               g2 = gn[r][i][v] + s;
             } else {
               g2 = l[r][i][v] + dk[i][v];
             }
             gn[r][i][v] = on ? g2 : NEG_INF;
+            m[r] = fmax(m[r], gn[r][i][v]);
           }
-          if (MODE == 0 && row < N && idx < nvec) st_stream(sp + idx, make_double2(st[r][i][0], st[r][i][1]));
+          if (MODE == 0 && (FULL || (row < N && idx < nvec))) st_stream(sp + idx, make_double2(st[r][i][0], st[r][i][1]));
         }
       }
-    }
-    double m[R];
+    };
+    auto phase3 = [&](const bool FULL) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const unsigned long long row = row0 + r;
+        if (!FULL && row >= N) continue;
+        double2 *gp = reinterpret_cast<double2 *>(gamma) + row * (unsigned long long)nvec;
+#pragma unroll
+        for (int i = 0; i < KITER; ++i) {
+          const int idx = t + TPR * i;
+          if (!FULL && idx >= nvec) continue;
+          double gout[2];
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const double g2 = gn[r][i][v] - lsum[r];     // normalised log-responsibility
+            gout[v] = (FULL || ok[i][v]) ? g2 : 0.0;
+            const double cq = cinv[r] * e[r][i][v];      // c_j q(j,k); 0 for unobserved classes and padding
+            acc[i][v] += cq;
+            if (cq > 0.0) bound = fma(cq, l[r][i][v] - g2, bound);
+          }
+          if (WRITE) st_stream(gp + idx, make_double2(gout[0], gout[1]));
+        }
+      }
+    };
+
+    if (full) phase1(true); else phase1(false);
+    const double mt = rows_reduce<TL, true>(m, s_red, phase, lane, warp);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      m[r] = NEG_INF;
-#pragma unroll
-      for (int i = 0; i < KITER; ++i) m[r] = fmax(m[r], fmax(gn[r][i][0], gn[r][i][1]));
-    }
-    group_reduce<TL, true>(m, s_red, phase);
-    double e[R][KITER][2], sum[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double mm = m[r] == NEG_INF ? 0.0 : m[r];   // a row past the end: keep the arithmetic finite
+      double mm = __shfl_sync(0xffffffffu, mt, r);
+      mm = mm == NEG_INF ? 0.0 : mm;                     // a row past the end: keep the arithmetic finite
       sum[r] = 0.0;
 #pragma unroll
       for (int i = 0; i < KITER; ++i)
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           gn[r][i][v] -= mm;
-          e[r][i][v] = exp(gn[r][i][v]);                 // exp(-inf) = 0 on padding columns
+          e[r][i][v] = exp_nonpos(gn[r][i][v]);          // 0 on padding columns (-inf)
           sum[r] += e[r][i][v];
         }
     }
-    group_reduce<TL, false>(sum, s_red, phase);
+    const double tot = rows_reduce<TL, false>(sum, s_red, phase, lane, warp);
+    // lanes 0..R-1: one log, one division and one count load per warp serve the whole batch
+    double lsum_l = 0.0, cinv_l = 0.0;
+    if (lane < R && row0 + lane < N) {
+      lsum_l = log(tot);
+      cinv_l = counts[row0 + lane] / tot;
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const unsigned long long row = row0 + r;
-      if (row >= N) continue;
-      const double lsum = log(sum[r]);
-      const double inv = 1.0 / sum[r];
-      const double c = counts[row];
-      double2 *gp = reinterpret_cast<double2 *>(gamma + row * (unsigned long long)ld);
-#pragma unroll
-      for (int i = 0; i < KITER; ++i) {
-        const int idx = t + TPR * i;
-        if (idx >= nvec) continue;
-        double gout[2];
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          const double g2 = gn[r][i][v] - lsum;          // normalised log-responsibility
-          gout[v] = ok[i][v] ? g2 : 0.0;
-          if (ok[i][v] && c > 0.0) {
-            const double cq = c * (e[r][i][v] * inv);
-            acc[i][v] += cq;
-            if (cq > 0.0) bound = fma(cq, l[r][i][v] - g2, bound);
-          }
-        }
-        if (WRITE) st_stream(gp + idx, make_double2(gout[0], gout[1]));
-      }
+      lsum[r] = __shfl_sync(0xffffffffu, lsum_l, r);
+      cinv[r] = __shfl_sync(0xffffffffu, cinv_l, r);
     }
+    if (full) phase3(true); else phase3(false);
   };
 
   if constexpr (!PIPE) {
@@ -652,10 +772,11 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
     const unsigned long long n_batches = (N + rows_per_batch - 1) / rows_per_batch;
     for (unsigned long long b = blockIdx.x; b < n_batches; b += gridDim.x) {
       const unsigned long long row0 = b * rows_per_batch + (unsigned long long)g * R;
-      body([&](int s, int r, int idx) {
-        const double *base = s == 0 ? logl : (s == 1 ? gamma : step);
-        return ld_stream(reinterpret_cast<const double2 *>(base + (row0 + r) * (unsigned long long)ld) + idx);
-      }, row0);
+      const unsigned long long off = row0 * (unsigned long long)nvec;
+      const double2 *lp = reinterpret_cast<const double2 *>(logl) + off;
+      const double2 *gp = reinterpret_cast<const double2 *>(gamma) + off;
+      const double2 *sp = reinterpret_cast<const double2 *>(step) + off;
+      body([&](int s, int r, int idx) { return ld_stream((s == 0 ? lp : (s == 1 ? gp : sp)) + (size_t)r * nvec + idx); }, row0);
     }
   } else {
     RowPipe<3> pipe;
