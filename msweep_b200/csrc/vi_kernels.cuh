@@ -148,12 +148,11 @@ template <class TL, bool IS_MAX> __device__ __forceinline__ void group_reduce(do
   }
 }
 
-// ---- per-CTA partial vector: combine the G row groups, then one coalesced store ---------------------
-// acc[i][v] belongs to column VEC*(t + TPR*i) + v.  comb: G * TPR*KITER*VEC doubles when G > 1.
+// ---- per-CTA partial vector: fold the G row groups in group order, then one coalesced store ---------
+// acc[i][v] belongs to column VEC*(t + TPR*i) + v.  comb: TPR*KITER*VEC doubles when G > 1.
 template <class TL, int VEC>
 __device__ __forceinline__ void store_partials(const double (&acc)[TL::KITER][VEC], double *comb, double *out, int K) {
   const int t = threadIdx.x % TL::TPR, g = threadIdx.x / TL::TPR;
-  constexpr int KCAP = TL::TPR * TL::KITER * VEC;
   if constexpr (TL::G == 1) {
 #pragma unroll
     for (int i = 0; i < TL::KITER; ++i)
@@ -163,18 +162,20 @@ __device__ __forceinline__ void store_partials(const double (&acc)[TL::KITER][VE
         if (k < K) out[k] = acc[i][v];
       }
   } else {
-    __syncthreads();
+    for (int gg = 0; gg < TL::G; ++gg) {      // fixed order: bit-reproducible
+      __syncthreads();
+      if (g == gg) {
 #pragma unroll
-    for (int i = 0; i < TL::KITER; ++i)
+        for (int i = 0; i < TL::KITER; ++i)
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) comb[g * KCAP + VEC * (t + TL::TPR * i) + v] = acc[i][v];
-    __syncthreads();
-    for (int k = threadIdx.x; k < K; k += TL::NT) {
-      double a = 0.0;
-#pragma unroll
-      for (int gg = 0; gg < TL::G; ++gg) a += comb[gg * KCAP + k];
-      out[k] = a;
+          for (int v = 0; v < VEC; ++v) {
+            const int c = VEC * (t + TL::TPR * i) + v;
+            comb[c] = gg == 0 ? acc[i][v] : comb[c] + acc[i][v];
+          }
+      }
     }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += TL::NT) out[k] = comb[k];
   }
 }
 
@@ -257,7 +258,7 @@ em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ 
   constexpr int RB = TL::G * R;                       // rows per CTA batch
   if (ctl->done) return;
   __shared__ double s_red[2 * TL::NW * R];
-  __shared__ double s_comb[TL::G > 1 ? TL::G * TPR * KITER * VEC : 1];
+  __shared__ double s_comb[TL::G > 1 ? TPR * KITER * VEC : 1];
   __shared__ double s_blk[32];
   const int t = threadIdx.x % TPR, g = threadIdx.x / TPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -621,7 +622,7 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
   if (ctl->done) return;
   if (only_if_reset && !ctl->didreset) return;
   __shared__ double s_red[2 * TL::NW * R];
-  __shared__ double s_comb[TL::G > 1 ? TL::G * TPR * KITER * 2 : 1];
+  __shared__ double s_comb[TL::G > 1 ? TPR * KITER * 2 : 1];
   __shared__ double s_blk[32];
   const int t = threadIdx.x % TPR, g = threadIdx.x / TPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
