@@ -189,6 +189,9 @@ def main():
     t_gen = time.time()
     wl = synth.generate_ec_patterns(n_local, N_GROUPS, GROUP_SIZE, seed=20231019 + rank)
     t_gen = time.time() - t_gen
+    # the e2e leg copies its inputs from PINNED host memory (page-locked in place)
+    for arr in (wl.row_ptr, wl.targets, wl.group_of_target, wl.group_sizes):
+        torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
 
     # ---- resident leg: likelihood in HBM, W warm-up + K timed iterations ----------------------------
     with torch.cuda.stream(stream):

@@ -44,6 +44,7 @@ struct mswb_lik {
   mswb::DevBuf<uint32_t> pat_targets;
   mswb::DevBuf<uint32_t> group_of_target;  // [T]
   mswb::DevBuf<uint32_t> kept_dev;         // [K]
+  mswb::DevBuf<int> pos_dev;               // [K_all] row position of group g among the kept groups, -1 if pruned
   mswb::DevBuf<uint64_t> lut_off;          // [K+1] ragged LUT offsets
   mswb::DevBuf<double> lut;                // LUT[g'][c], c = 0..size(g')
   uint64_t n_targets = 0;

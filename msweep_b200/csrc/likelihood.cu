@@ -50,52 +50,67 @@ group_hits_kernel(const uint64_t *__restrict__ pat_ptr, const uint32_t *__restri
   }
 }
 
-// Dense rows.  MODE 0: logl (fp64).  MODE 1: P = exp(logl - rowmax) fp64 + rowmax.  MODE 2: same in fp32.
-// MODE 3: raw hit counts as uint32 (parity export; row stride K_all, all groups).
+// Dense rows.  MODE 0: logl (fp64).  MODE 1: P = exp(logl - M) fp64 + M.  MODE 2: same in fp32.
+// MODE 3: raw hit counts as uint32 (parity export; row stride K_all, all groups, pos = identity).
+//
+// LUT[g][0] = log(zero_inflation) = l0 for every group and almost every (class, group) pair has no hit, so a
+// row is written as a constant with 16-byte stores and the few groups the class does hit are patched in by
+// walking its pattern again: O(K / lanes) wide stores + O(pattern length) table lookups per class.  atomicExch
+// hands each distinct group to one lane and leaves the counter row clean for the next class.
+// M only has to be a shift that keeps P in range: max(l0, values of the hit groups) >= the true row maximum.
+template <typename OT> struct Vec16;
+template <> struct Vec16<double> { using type = double2; static constexpr int N = 2; static __device__ double2 splat(double v) { return make_double2(v, v); } };
+template <> struct Vec16<float> { using type = float4; static constexpr int N = 4; static __device__ float4 splat(float v) { return make_float4(v, v, v, v); } };
+template <> struct Vec16<uint32_t> { using type = uint4; static constexpr int N = 4; static __device__ uint4 splat(uint32_t v) { return make_uint4(v, v, v, v); } };
+
 template <int MODE, typename OT>
 __global__ void __launch_bounds__(LIK_NT)
 lik_fill_kernel(const uint64_t *__restrict__ pat_ptr, const uint32_t *__restrict__ pat_targets,
-                const uint32_t *__restrict__ group_of_target, const uint32_t *__restrict__ kept,
+                const uint32_t *__restrict__ group_of_target, const int *__restrict__ pos_of_group,
                 const uint64_t *__restrict__ lut_off, const double *__restrict__ lut, unsigned long long N,
                 int K_all, int K, int ld, int active_warps, double l0, OT *__restrict__ out, double *__restrict__ rowmax) {
+  using V = Vec16<OT>;
   extern __shared__ unsigned s_rows[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp >= active_warps) return;
+  if (warp >= active_warps) return;   // (no block-wide barrier below: warps are independent)
   unsigned *row = s_rows + (size_t)warp * K_all;
   for (int k = lane; k < K_all; k += 32) row[k] = 0;
   __syncwarp();
+  const int nvec = ld / V::N;         // ld is a multiple of the vector width (16-byte aligned rows)
   const unsigned long long n_warps = (unsigned long long)gridDim.x * active_warps;
   for (unsigned long long j = (unsigned long long)blockIdx.x * active_warps + warp; j < N; j += n_warps) {
     const unsigned long long a = pat_ptr[j], b = pat_ptr[j + 1];
     count_pattern(row, pat_targets, a, b, group_of_target, lane);
     OT *orow = out + j * (unsigned long long)ld;
-    if (MODE == 3) {
-      for (int k = lane; k < K_all; k += 32) orow[k] = (OT)row[k];
-    } else {
-      // LUT[g][0] = log(zero_inflation) = l0 for every group, and almost every (class, group) pair has
-      // no hit: only the few non-zero counters go to the table (and, in the linear modes, through exp).
-      double m = -INFINITY, e0 = 0.0;
-      if (MODE != 0) {
-        for (int k = lane; k < K; k += 32) {
-          const unsigned c = row[kept[k]];
-          m = fmax(m, c == 0 ? l0 : lut[lut_off[k] + c]);
-        }
-        m = warp_max(m);
-        if (lane == 0) rowmax[j] = m;
-        e0 = exp(l0 - m);
+    double m = l0;
+    if (MODE == 1 || MODE == 2) {
+      for (unsigned long long p = a + lane; p < b; p += 32) {
+        const uint32_t g = group_of_target[pat_targets[p]];
+        const int pos = pos_of_group[g];
+        if (pos >= 0) m = fmax(m, lut[lut_off[pos] + row[g]]);
       }
-      for (int k = lane; k < ld; k += 32) {
-        double v = 0.0;
-        if (k < K) {
-          const unsigned c = row[kept[k]];
-          if (MODE == 0) v = c == 0 ? l0 : lut[lut_off[k] + c];
-          else v = c == 0 ? e0 : exp(lut[lut_off[k] + c] - m);
-        }
-        orow[k] = (OT)v;
-      }
+      m = warp_max(m);
+      if (lane == 0) rowmax[j] = m;
     }
-    __syncwarp();
-    for (unsigned long long p = a + lane; p < b; p += 32) row[group_of_target[pat_targets[p]]] = 0;
+    const OT fillv = MODE == 3 ? (OT)0 : (MODE == 0 ? (OT)l0 : (OT)exp(l0 - m));
+    typename V::type *vrow = reinterpret_cast<typename V::type *>(orow);
+    const typename V::type fv = V::splat(fillv);
+    for (int i = lane; i < nvec; i += 32) vrow[i] = fv;
+    if (MODE != 3 && ld > K) {          // padding columns hold 0
+      __syncwarp();
+      for (int k = K + lane; k < ld; k += 32) orow[k] = (OT)0;
+    }
+    __syncwarp();                       // the constant fill is ordered before the patches below
+    for (unsigned long long p = a + lane; p < b; p += 32) {
+      const uint32_t g = group_of_target[pat_targets[p]];
+      const unsigned c = atomicExch(&row[g], 0u);
+      if (c == 0) continue;             // another lane owns this group
+      if (MODE == 3) { orow[g] = (OT)c; continue; }
+      const int pos = pos_of_group[g];
+      if (pos < 0) continue;            // pruned by --min-hits
+      const double v = lut[lut_off[pos] + c];
+      orow[pos] = (OT)(MODE == 0 ? v : exp(v - m));
+    }
     __syncwarp();
   }
 }
@@ -205,7 +220,7 @@ void lik_ensure_logl(mswb_lik *L) {
   auto kern = lik_fill_kernel<0, double>;
   const size_t smem = lik_smem_bytes(L->K_all);
   prepare_fill_kernel(kern, smem);
-  kern<<<fill_grid(ctx, L->N, L->K_all), LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->kept_dev.p,
+  kern<<<fill_grid(ctx, L->N, L->K_all), LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->pos_dev.p,
                                                             L->lut_off.p, L->lut.p, L->N, (int)L->K_all, (int)L->K, (int)L->Kp,
                                                             lik_active_warps(L->K_all), L->l0, L->logl.p, nullptr);
   MSWB_LAUNCHED();
@@ -221,7 +236,7 @@ template <typename ST> static void fill_linear(mswb_lik *L, DevBuf<ST> &P, uint3
   auto kern = lik_fill_kernel<sizeof(ST) == 8 ? 1 : 2, ST>;
   const size_t smem = lik_smem_bytes(L->K_all);
   prepare_fill_kernel(kern, smem);
-  kern<<<fill_grid(ctx, L->N, L->K_all), LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->kept_dev.p,
+  kern<<<fill_grid(ctx, L->N, L->K_all), LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->pos_dev.p,
                                                             L->lut_off.p, L->lut.p, L->N, (int)L->K_all, (int)L->K, (int)ld,
                                                             lik_active_warps(L->K_all), L->l0, P.p, L->rowmax.p);
   MSWB_LAUNCHED();
@@ -370,6 +385,10 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
     L->Kp = (uint32_t)round_up(L->K, 2);
     L->kept_dev.alloc(L->K);
     h2d(L->kept_dev.p, L->kept.data(), L->K, s);
+    std::vector<int> pos(n_groups, -1);
+    for (uint32_t k = 0; k < L->K; ++k) pos[L->kept[k]] = (int)k;
+    L->pos_dev.alloc(n_groups);
+    h2d(L->pos_dev.p, pos.data(), n_groups, s);
 
     // ---- lookup table (include/Likelihood.hpp:92-107) --------------------------------------------
     std::vector<uint64_t> off;
@@ -481,17 +500,18 @@ int mswb_lik_export_hit_counts(const mswb_lik *lik, uint32_t *out) {
     cudaStream_t s = ctx->stream;
     const size_t n_el = (size_t)lik->N * lik->K_all;
     if (n_el == 0) return;
+    const size_t ld = round_up(lik->K_all, 4);          // 16-byte aligned rows for the vector fill
     DevBuf<uint32_t> ecmajor, gmajor;
-    ecmajor.alloc(n_el);
+    ecmajor.alloc((size_t)lik->N * ld);
     gmajor.alloc(n_el);
     auto kern = lik_fill_kernel<3, uint32_t>;
     const size_t smem = lik_smem_bytes(lik->K_all);
     prepare_fill_kernel(kern, smem);
     kern<<<fill_grid(ctx, lik->N, lik->K_all), LIK_NT, smem, s>>>(lik->pat_ptr.p, lik->pat_targets.p, lik->group_of_target.p, nullptr,
-                                                                  nullptr, nullptr, lik->N, (int)lik->K_all, (int)lik->K_all, (int)lik->K_all,
+                                                                  nullptr, nullptr, lik->N, (int)lik->K_all, (int)lik->K_all, (int)ld,
                                                                   lik_active_warps(lik->K_all), 0.0, ecmajor.p, nullptr);
     MSWB_LAUNCHED();
-    transpose<uint32_t, uint32_t>(ecmajor.p, lik->N, lik->K_all, lik->K_all, gmajor.p, lik->N, s);
+    transpose<uint32_t, uint32_t>(ecmajor.p, lik->N, lik->K_all, ld, gmajor.p, lik->N, s);
     d2h(out, gmajor.p, n_el, s);
     MSWB_CUDA(cudaStreamSynchronize(s));
   });
