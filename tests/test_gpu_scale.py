@@ -1,0 +1,85 @@
+"""GPU: size-independent properties at sizes where the oracle would take minutes (BASELINE configs 2-4 shapes):
+sortedness / conservation / idempotence of the EC build, conservation of the likelihood build, and
+model invariants of the optimiser on a multi-GB matrix."""
+import numpy as np
+import pytest
+
+from msweep_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big(mswb, ctx):
+    wl = synth.generate_ec_patterns(1_500_000, 1000, 24, n_present=40, seed=77, dup_factor=1.5)
+    aln = mswb.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    return wl, aln
+
+
+def test_ec_build_properties_at_scale(big, mswb, ctx):
+    wl, aln = big
+    e = aln.export()
+    lens = np.diff(wl.row_ptr.astype(np.int64))
+    assert np.all(np.diff(e.hash.astype(np.uint64)) > 0)                     # strictly ascending: std::map order, no duplicate keys
+    assert int(e.count.sum()) == int((lens > 0).sum()) == aln.n_aligned        # every aligned read in exactly one class
+    assert np.array_equal(np.diff(e.read_ptr.astype(np.int64)), e.count.astype(np.int64))
+    assert np.array_equal(np.sort(e.read_ids), np.nonzero(lens > 0)[0].astype(np.uint32))   # a permutation of the aligned reads
+    first = e.read_ids[e.read_ptr[:-1].astype(np.int64)]
+    assert np.array_equal(first, e.rep_read)                                  # representative = first (smallest) member
+    seg_min = np.minimum.reduceat(e.read_ids, e.read_ptr[:-1].astype(np.int64))
+    assert np.array_equal(seg_min, e.rep_read)
+    assert np.array_equal(np.diff(e.pat_ptr.astype(np.int64)), lens[e.rep_read])
+    # idempotence: collapsing the class patterns again gives the same classes, each seen once
+    again = mswb.Alignment(ctx, aln.n_ecs, wl.n_targets, e.pat_ptr, e.pat_targets).export()
+    assert np.array_equal(again.hash, e.hash) and np.all(again.count == 1)
+    assert np.array_equal(again.pat_targets, e.pat_targets)
+    # spot-check hashes against the host fold (mswb_pattern_hash)
+    pp = e.pat_ptr.astype(np.int64)
+    for i in np.linspace(0, aln.n_ecs - 1, 50).astype(int):
+        assert mswb.pattern_hash(e.pat_targets[pp[i]:pp[i + 1]]) == int(e.hash[i])
+
+
+def test_likelihood_and_optimiser_invariants_at_scale(big, mswb, ctx):
+    wl, aln = big
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)             # ~1e6 x 1000 fp64 = 8 GB
+    # every lineage gets a few stray hits in this workload: prune the half of the lineages with the fewest
+    _, hits0 = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, min_hits=1).mask(want_hits=True)
+    thr = int(np.sort(hits0)[wl.n_groups // 2])
+    lik1 = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, min_hits=thr)
+    mask, hits = lik1.mask(want_hits=True)
+    # tallies by hand from the exported class table
+    e = aln.export()
+    grp = wl.group_of_target[e.pat_targets]
+    cls = np.repeat(np.arange(aln.n_ecs), np.diff(e.pat_ptr.astype(np.int64)))
+    pairs = np.unique(np.stack([cls, grp.astype(np.int64)]), axis=1)
+    want = np.bincount(pairs[1], weights=e.count[pairs[0]].astype(np.float64), minlength=wl.n_groups).astype(np.uint64)
+    assert np.array_equal(hits, want) and np.array_equal(mask, (want >= thr).astype(np.uint8))
+    assert lik1.n_groups == int(mask.sum()) < wl.n_groups
+
+    em = lik.vi_begin(mswb.ALGO_EM, tol=0.0, max_iters=40)
+    em.step(40)
+    tb, _, _ = em.trace()
+    r = em.finish()
+    assert np.all(np.diff(tb) >= -1e-9 * np.abs(tb[:-1]))                     # EM never decreases the bound
+    assert abs(r.theta.sum() - 1.0) < 1e-12
+    total = float(aln.n_aligned)
+    assert np.max(np.abs((r.N_k - 1.0) / total - r.theta)) < 1e-15            # theta = (N_k - alpha0) / sum c
+
+    rcg = lik.vi_run(mswb.ALGO_RCG, tol=1e-6, max_iters=400)
+    assert rcg.converged and abs(rcg.theta.sum() - 1.0) < 1e-12
+    em_long = lik.vi_run(mswb.ALGO_EM, tol=1e-7, max_iters=3000)
+    assert np.max(np.abs(em_long.theta - rcg.theta)) < 2e-4                   # same optimum, different paths
+    assert abs(em_long.bound - rcg.bound) < 1e-6 * abs(rcg.bound)
+    # pruning lineages with few hits moves the estimates of the others by about the pruned mass (README.md:136-140)
+    r1 = lik1.vi_run(mswb.ALGO_RCG, tol=1e-6, max_iters=400)
+    pruned_mass = float(rcg.theta[~mask.astype(bool)].sum())
+    assert pruned_mass < 0.05
+    assert np.max(np.abs(r1.theta - rcg.theta[mask.astype(bool)])) < max(5e-4, 2 * pruned_mass)
+    # fp32 storage against fp64 at a fixed iteration count
+    lik32 = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=mswb.STORE_F32)
+    a = lik32.vi_run(mswb.ALGO_EM, tol=0.0, max_iters=30)
+    b = lik.vi_run(mswb.ALGO_EM, tol=0.0, max_iters=30)
+    assert np.max(np.abs(a.theta - b.theta)) < 2e-6 and abs(a.bound - b.bound) < 1e-6 * abs(b.bound)
+    # run-to-run bit reproducibility (no atomics on the path)
+    c = lik.vi_run(mswb.ALGO_RCG, tol=1e-6, max_iters=400)
+    assert np.array_equal(c.theta, rcg.theta) and c.bound == rcg.bound and c.iters == rcg.iters
