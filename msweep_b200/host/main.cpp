@@ -4,7 +4,7 @@
 // Kept from the reference: the flags of the hot path with their defaults and meaning, the order of the
 // stages, the messages and exit codes of the failure sites, and the <prefix>_abundances.txt format
 // (src/PlainSample.cpp:32-71, src/BootstrapSample.cpp:75-130).  Not here (out of scope):
-// read binning, probability / likelihood dumps, RATE, output compression, the compact alignment format.
+// read binning, likelihood dumps, RATE, output compression, the compact alignment format.
 // New: --algorithm takes the B200 backends (rcgb200 | emb200; the reference's rcggpu / emgpu are accepted
 // as aliases and rcgcpu is refused: there is no CPU path in this binary), and --gpus N.
 #include "input.hpp"
@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -47,11 +48,11 @@ struct Args {
   }
 };
 
-const std::set<std::string> kBool = {"verbose", "version", "cite", "help", "no-fit-model", "print-timings"};
+const std::set<std::string> kBool = {"verbose", "version", "cite", "help", "no-fit-model", "print-timings", "write-probs", "print-probs"};
 const std::set<std::string> kValued = {"themisto-1", "themisto-2", "themisto", "i", "o", "themisto-mode", "t", "max-iters", "tol",
                                        "algorithm", "emprecision", "iters", "seed", "bootstrap-count", "q", "e", "alphas",
                                        "zero-inflation", "min-hits", "gpus", "rng", "dump-alignment"};
-const std::set<std::string> kUnsupported = {"bin-reads", "target-groups", "min-abundance", "write-probs", "print-probs",
+const std::set<std::string> kUnsupported = {"bin-reads", "target-groups", "min-abundance",
                                             "write-likelihood", "write-likelihood-bitseq", "compress", "compression-level",
                                             "read-likelihood", "run-rate"};
 
@@ -105,6 +106,7 @@ const char *kHelp =
     "  --alphas                     comma separated prior counts (default: all 1.0)\n"
     "  --zero-inflation             likelihood of zero hits against a group (default: 0.01)\n"
     "  --min-hits                   only consider groups with at least this many aligned reads (default: 0)\n"
+    "  --write-probs, --print-probs write / print the read-class to group probabilities (<prefix>_probs.tsv)\n"
     "  --no-fit-model, --verbose, --version, --cite, --help, --print-timings\n";
 
 void cite() {
@@ -255,6 +257,8 @@ int main(int argc, char *argv[]) {
   if (world > 1 && mswb_nccl_unique_id(nccl_id.data())) { std::cerr << "Initialising the GPUs failed:\n  " << mswb_last_error() << "\nexiting\n"; return 1; }
 
   std::vector<std::vector<std::vector<double>>> results_by_gpu(n_gpus);   // [gpu][0 = plain, 1.. = replicates][group]
+  const bool want_probs = args.has("write-probs") || args.has("print-probs");
+  std::vector<std::string> probs_rows(n_gpus);   // formatted rows of each GPU's class shard, in class order
   std::vector<std::string> errors(n_gpus);
   std::vector<int> failed_stage(n_gpus, 0);   // 1 = EC/likelihood, 2 = estimation, 3 = bootstrap
   std::vector<bool> mask;
@@ -272,7 +276,8 @@ int main(int argc, char *argv[]) {
       if (gpu == 0) { n_ecs = aln.n_ecs(); n_aligned = aln.n_aligned(); n_reads = aln.n_reads(); t_ec = tm.lap();
                       log("  found " + std::to_string(n_ecs) + " unique alignments"); log("Computing the likelihood matrix"); }
       b200::Likelihood ll(ctx, aln, grouping.group_of_target, grouping.sizes, q, e_disp, min_hits, zi, storage);
-      if (gpu == 0) { mask = ll.groups_considered(); t_lik = tm.lap(); }
+      const std::vector<bool> my_mask = ll.groups_considered();
+      if (gpu == 0) { mask = my_mask; t_lik = tm.lap(); }
       if (args.has("no-fit-model")) { failed_stage[gpu] = 0; return; }
 
       // prior counts (src/mSWEEP.cpp:391-398)
@@ -289,6 +294,23 @@ int main(int argc, char *argv[]) {
       b200::ViReport rep;
       res.push_back(b200::rcg_optl(ctx, ll, nullptr, prior, vi, (verbose && gpu == 0) ? &std::cerr : nullptr, &rep));
       if (gpu == 0) { report = rep; t_vi = tm.lap(); }
+      if (want_probs && (!bootstrap || gpu == 0)) {
+        // src/Sample.cpp:63-85 / 154-186: one row per class, exp(log-posterior) per group, pruned groups as 0 at the
+        // end.  The K x N matrix never sits on the host: tiles of classes are pulled and formatted as they come.
+        const size_t n_zero = (size_t)std::count(my_mask.begin(), my_mask.end(), false);
+        std::ostringstream os;
+        const uint64_t tile = 4096, N = ll.get_cols(), K = ll.get_rows();
+        for (uint64_t b = 0; b < N; b += tile) {
+          const uint64_t e = std::min(N, b + tile), n = e - b;
+          const std::vector<double> g = ll.posteriors(b, e);
+          for (uint64_t j = 0; j < n; ++j) {
+            os << (ll.ec_begin() + b + j) << '\t';
+            for (uint64_t k = 0; k < K; ++k) os << std::exp(g[k * n + j]) << (k + 1 < K + n_zero ? '\t' : '\n');
+            for (size_t z = 0; z < n_zero; ++z) os << (double)0.0 << (z + 1 < n_zero ? '\t' : '\n');
+          }
+        }
+        probs_rows[gpu] = os.str();
+      }
       if (bootstrap) {
         failed_stage[gpu] = 3;
         if (gpu == 0) log("Running estimation with " + std::to_string(iters) + " bootstrap iterations");
@@ -326,6 +348,25 @@ int main(int argc, char *argv[]) {
   // names of estimated vs pruned groups (src/mSWEEP.cpp:425-435)
   std::vector<std::string> estimated, zero;
   for (size_t g = 0; g < grouping.names.size(); ++g) (mask[g] ? estimated : zero).push_back(grouping.names[g]);
+
+  if (want_probs) {
+    try {
+      auto write_probs = [&](std::ostream &of) {
+        if (!of.good()) throw std::runtime_error("Can't write to probs file.");
+        of << "ec_id" << '\t';
+        const size_t n_rows = estimated.size() + zero.size();
+        for (size_t i = 0; i < n_rows; ++i)
+          of << (i < estimated.size() ? estimated[i] : zero[i - estimated.size()]) << (i + 1 < n_rows ? '\t' : '\n');
+        for (int g = 0; g < (bootstrap ? 1 : n_gpus); ++g) of << probs_rows[g];
+        of << std::endl;
+      };
+      if (args.has("print-probs")) write_probs(std::cout);
+      if (args.has("write-probs")) { std::ofstream of(args.str("o", "") + "_probs.tsv"); write_probs(of); }   // src/OutfileDesignator.cpp:96-102
+    } catch (std::exception &e) {
+      std::cerr << "Writing the probabilities failed:\n  " << e.what() << "\nexiting\n";
+      return 1;
+    }
+  }
 
   try {
     const std::string o = args.str("o", "");

@@ -99,6 +99,7 @@ public:
   size_t get_rows() const { return n_groups_; }                 // log_mat().get_rows()
   size_t get_cols() const { return n_ecs_; }
   size_t n_groups_all() const { return n_groups_all_; }
+  uint64_t ec_begin() const { return ec_begin_; }               // first global class index of this rank's shard
   std::vector<bool> groups_considered() const {                 // include/Likelihood.hpp:79, 330
     std::vector<uint8_t> m(n_groups_all_);
     check(mswb_lik_mask(h_, m.data(), nullptr));
@@ -126,11 +127,11 @@ public:
     return out;
   }
 private:
-  void refresh() { check(mswb_lik_info(h_, &n_groups_all_, &n_groups_, &n_ecs_, nullptr, nullptr)); }
+  void refresh() { check(mswb_lik_info(h_, &n_groups_all_, &n_groups_, &n_ecs_, &ec_begin_, nullptr)); }
   const Context *ctx_;
   mswb_lik *h_ = nullptr;
   uint32_t n_groups_all_ = 0, n_groups_ = 0;
-  uint64_t n_ecs_ = 0;
+  uint64_t n_ecs_ = 0, ec_begin_ = 0;
 };
 
 // Drop-in for `rcg_optl(args, ll_mat, log_ec_counts, prior_counts, log)` + `rcgpar::mixture_components`

@@ -22,6 +22,7 @@ int main(int argc, char **argv) {
     std::string k = argv[i];
     k = k.substr(k[1] == '-' ? 2 : 1);
     if (k == "verbose") continue;
+    if (k == "write-probs") { kv[k] = "1"; continue; }
     if (i + 1 >= argc) { std::cerr << "missing value for " << k << "\n"; return 1; }
     kv[k] = argv[++i];
   }
@@ -51,9 +52,11 @@ int main(int argc, char **argv) {
     const uint64_t max_iters = std::stoull(get("max-iters", "5000"));
     const std::string algo = get("algorithm", "rcgcpu");
     const bool rcg = algo.rfind("rcg", 0) == 0;
+    std::vector<double> first_gamma;
     auto estimate = [&](const std::vector<double> &lc) {
       ViResult r = rcg ? rcg_optl(lik.logl.data(), K, ec.n_ecs(), lc.data(), prior.data(), tol, max_iters)
                        : em_optl(lik.logl.data(), K, ec.n_ecs(), lc.data(), prior.data(), tol, max_iters);
+      if (first_gamma.empty()) first_gamma = r.gamma;
       return mixture_components(r.gamma.data(), K, ec.n_ecs(), lc.data());
     };
     std::vector<std::vector<double>> results;
@@ -67,6 +70,18 @@ int main(int argc, char **argv) {
     for (size_t g = 0; g < grouping.names.size(); ++g) (lik.groups_mask[g] ? est : zero).push_back(grouping.names[g]);
     uint64_t n_aligned = 0;
     for (auto c : ec.count) n_aligned += c;
+    if (kv.count("write-probs")) {   // src/Sample.cpp:63-85, 154-186
+      std::ofstream pf(get("o", "oracle") + "_probs.tsv");
+      pf << "ec_id" << '\t';
+      const size_t n_rows = est.size() + zero.size();
+      for (size_t i = 0; i < n_rows; ++i) pf << (i < est.size() ? est[i] : zero[i - est.size()]) << (i + 1 < n_rows ? '\t' : '\n');
+      for (uint64_t j = 0; j < ec.n_ecs(); ++j) {
+        pf << j << '\t';
+        for (size_t i = 0; i < n_rows; ++i)
+          pf << (i < est.size() ? std::exp(first_gamma[i * ec.n_ecs() + j]) : 0.0) << (i + 1 < n_rows ? '\t' : '\n');
+      }
+      pf << std::endl;
+    }
     std::ofstream of(get("o", "oracle") + "_abundances.txt");
     write_abundances(of, get("version-string", "oracle"), reads.n_reads, n_aligned, est, zero, results, iters);
   } catch (const std::exception &e) {

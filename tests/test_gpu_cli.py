@@ -107,3 +107,19 @@ def test_alphas_length_is_checked(data):
     d, wl, paths, g = data
     r = subprocess.run([CLI, "--themisto", ",".join(paths), "-i", g, "--alphas", "1,1"], capture_output=True, text=True)
     assert r.returncode == 1 and "--alphas must have the same number of values as there are groups." in r.stderr
+
+
+def test_write_probs(data):
+    """src/Sample.cpp:63-85, 154-186: <prefix>_probs.tsv, one row per class, pruned groups as trailing zeros."""
+    d, wl, paths, g = data
+    for extra, tag in (([], "p0"), (["--min-hits", "200"], "p1")):
+        run_both(d, paths, g, ["--write-probs", *extra], tag)
+        ours = open(d / f"ours_{tag}_probs.tsv").read().split("\n")
+        ref = open(d / f"ref_{tag}_probs.tsv").read().split("\n")
+        assert ours[0] == ref[0] and ours[0].startswith("ec_id\t")
+        assert len(ours) == len(ref) and ours[-1] == "" and ours[-2] == ""          # trailing std::endl
+        a = np.array([[float(x) for x in l.split("\t")] for l in ours[1:-2]])
+        b = np.array([[float(x) for x in l.split("\t")] for l in ref[1:-2]])
+        assert a.shape == b.shape and np.array_equal(a[:, 0], np.arange(len(a)))
+        assert np.max(np.abs(a - b)) < 2e-6
+        assert np.max(np.abs(a[:, 1:].sum(axis=1) - 1.0)) < 1e-4
