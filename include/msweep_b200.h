@@ -64,6 +64,9 @@ MSWB_API int  mswb_nccl_unique_id(void *out_id /* MSWB_NCCL_ID_BYTES */);
 MSWB_API int  mswb_ctx_create(int device, int rank, int world_size, const void *nccl_id, void *cuda_stream,
                      mswb_ctx **out);
 MSWB_API void mswb_ctx_destroy(mswb_ctx *ctx);
+/* Creates the CUDA primary context of `device` (seconds on a cold process); call it from a side thread while
+ * the host is still parsing its inputs so that mswb_ctx_create returns immediately afterwards. */
+MSWB_API int  mswb_device_warmup(int device);
 MSWB_API int  mswb_ctx_sync(mswb_ctx *ctx);
 /* Contiguous EC range [*begin, *end) owned by this rank when n_ecs classes are sharded. */
 MSWB_API int  mswb_shard_range(const mswb_ctx *ctx, uint64_t n_ecs, uint64_t *begin, uint64_t *end);

@@ -115,6 +115,16 @@ void mswb_ctx_destroy(mswb_ctx *ctx) {
   delete ctx;
 }
 
+int mswb_device_warmup(int device) {
+  return mswb::guarded([&] {
+    int n_dev = 0;
+    MSWB_REQUIRE(cudaGetDeviceCount(&n_dev) == cudaSuccess && n_dev > 0, "no CUDA device available: msweep_b200 has no CPU fallback");
+    MSWB_REQUIRE(device >= 0 && device < n_dev, "device index out of range");
+    MSWB_CUDA(cudaSetDevice(device));
+    MSWB_CUDA(cudaFree(nullptr));
+  });
+}
+
 int mswb_ctx_sync(mswb_ctx *ctx) {
   return mswb::guarded([&] {
     MSWB_REQUIRE(ctx, "ctx is NULL");

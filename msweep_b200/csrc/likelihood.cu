@@ -300,6 +300,7 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
     MSWB_REQUIRE(aln->ctx == ctx, "alignment belongs to another context");
     MSWB_REQUIRE(storage == MSWB_STORE_F64 || storage == MSWB_STORE_F32, "unknown storage");
     MSWB_REQUIRE(n_groups >= 1, "the grouping has no groups");
+    MSWB_REQUIRE(aln->partitioned || aln->n_ecs > 0, "the alignment holds no equivalence class: no read aligned to any reference sequence");
     MSWB_REQUIRE(zero_inflation > 0.0 && zero_inflation < 1.0, "zero inflation must lie in (0, 1)");
     MSWB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;

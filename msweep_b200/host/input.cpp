@@ -133,11 +133,18 @@ Strand parse_strand(const std::string &buf, uint64_t T, int n_threads) {
   // bucket by row (= flat / T); rows at or beyond the line count are never visited by collapse()
   const uint64_t R = s.n_lines;
   s.row_ptr.assign(R + 1, 0);
-  for (auto &v : keys) for (uint64_t k : v) { const uint64_t r = k / T; if (r < R) ++s.row_ptr[r + 1]; }
+  // counting sort by row, all threads at once (relaxed atomics; the order inside a row is fixed by the sort below)
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
+  for (int t = 0; t < n_threads; ++t)
+    for (uint64_t k : keys[t]) { const uint64_t r = k / T; if (r < R) __atomic_fetch_add(&s.row_ptr[r + 1], 1, __ATOMIC_RELAXED); }
   for (uint64_t r = 0; r < R; ++r) s.row_ptr[r + 1] += s.row_ptr[r];
   s.cols.resize(s.row_ptr[R]);
   std::vector<uint64_t> fill(s.row_ptr.begin(), s.row_ptr.end() - 1);
-  for (auto &v : keys) { for (uint64_t k : v) { const uint64_t r = k / T; if (r < R) s.cols[fill[r]++] = (uint32_t)(k % T); } std::vector<uint64_t>().swap(v); }
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
+  for (int t = 0; t < n_threads; ++t) {
+    for (uint64_t k : keys[t]) { const uint64_t r = k / T; if (r < R) s.cols[__atomic_fetch_add(&fill[r], 1, __ATOMIC_RELAXED)] = (uint32_t)(k % T); }
+    std::vector<uint64_t>().swap(keys[t]);
+  }
   // ascending + unique inside each row (a bit can only be set once)
   std::vector<uint64_t> len(R);
 #pragma omp parallel for schedule(static) num_threads(n_threads)
@@ -164,9 +171,18 @@ ReadTable read_themisto(const std::vector<std::string> &paths, uint64_t n_target
   if (n_threads < 1) n_threads = 1;
   ReadTable out;
   out.n_targets = n_targets;
+  // the files are read from disk concurrently (one reader thread each); tokenising uses all threads per strand
+  std::vector<std::string> bufs(paths.size());
+  std::vector<std::string> read_err(paths.size());
+#pragma omp parallel for schedule(static, 1) num_threads((int)std::min<size_t>(paths.size(), (size_t)n_threads))
+  for (size_t i = 0; i < paths.size(); ++i) {
+    try { bufs[i] = slurp(paths[i]); } catch (const std::exception &e) { read_err[i] = e.what(); }
+  }
+  for (auto &e : read_err) if (!e.empty()) throw std::runtime_error(e);
   Strand acc;
   for (size_t i = 0; i < paths.size(); ++i) {
-    Strand s = parse_strand(slurp(paths[i]), n_targets, n_threads);
+    Strand s = parse_strand(bufs[i], n_targets, n_threads);
+    std::string().swap(bufs[i]);
     if (i == 0) { acc = std::move(s); continue; }
     const bool isect = merge_mode == "intersection";
     if (!isect && merge_mode != "union")

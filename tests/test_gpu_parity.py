@@ -168,6 +168,8 @@ def test_empty_and_degenerate_inputs(oracle, mswb, ctx):
     # all reads unaligned
     aln = mswb.Alignment(ctx, 5, 9, np.zeros(6, np.uint64), np.zeros(0, np.uint32))
     assert (aln.n_ecs, aln.n_aligned, aln.n_reads) == (0, 0, 5)
+    with pytest.raises(mswb.MswbError, match="no read aligned"):
+        mswb.Likelihood.build(ctx, aln, np.zeros(9, np.uint32), np.array([9], np.uint64))
     # zero reads
     aln = mswb.Alignment(ctx, 0, 9, np.zeros(1, np.uint64), np.zeros(0, np.uint32))
     assert aln.n_ecs == 0
