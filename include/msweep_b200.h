@@ -63,6 +63,9 @@ MSWB_API int  mswb_nccl_unique_id(void *out_id /* MSWB_NCCL_ID_BYTES */);
  * or NULL for a private non-blocking stream.  nccl_id may be NULL iff world_size == 1. */
 MSWB_API int  mswb_ctx_create(int device, int rank, int world_size, const void *nccl_id, void *cuda_stream,
                      mswb_ctx **out);
+/* Single-process form: one context per listed device, rank i on devices[i], joined by one NCCL clique
+ * (ncclCommInitAll — no bootstrap network, so it is much quicker than n calls of mswb_ctx_create).  out[n]. */
+MSWB_API int  mswb_ctx_create_group(int n, const int *devices, mswb_ctx **out);
 MSWB_API void mswb_ctx_destroy(mswb_ctx *ctx);
 /* Creates the CUDA primary context of `device` (seconds on a cold process); call it from a side thread while
  * the host is still parsing its inputs so that mswb_ctx_create returns immediately afterwards. */

@@ -19,6 +19,7 @@ struct NcclApi {
   void *handle = nullptr;
   int (*GetUniqueId)(NcclUniqueId *) = nullptr;
   int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+  int (*CommInitAll)(void **, int, const int *) = nullptr;
   int (*CommDestroy)(void *) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
@@ -36,6 +37,7 @@ static NcclApi &nccl() {
     if (!api.handle) return;
     api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
     api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+    api.CommInitAll = (decltype(api.CommInitAll))dlsym(api.handle, "ncclCommInitAll");
     api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
     api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
@@ -103,6 +105,24 @@ int mswb_ctx_create(int device, int rank, int world_size, const void *nccl_id, v
       MSWB_NCCL(nccl().CommInitRank(&ctx->nccl_comm, world_size, id, rank));
     }
     *out = ctx.release();
+  });
+}
+
+int mswb_ctx_create_group(int n, const int *devices, mswb_ctx **out) {
+  return mswb::guarded([&] {
+    MSWB_REQUIRE(n >= 1 && devices && out, "bad arguments");
+    std::vector<void *> comms(n, nullptr);
+    if (n > 1) {
+      MSWB_REQUIRE(nccl().CommInitAll, "ncclCommInitAll is not available in the loaded NCCL");
+      MSWB_NCCL(nccl().CommInitAll(comms.data(), n, devices));
+    }
+    for (int i = 0; i < n; ++i) {
+      out[i] = nullptr;
+      if (mswb_ctx_create(devices[i], 0, 1, nullptr, nullptr, &out[i])) throw mswb::Error(mswb_last_error());
+      out[i]->rank = i;
+      out[i]->world = n;
+      out[i]->nccl_comm = comms[i];
+    }
   });
 }
 

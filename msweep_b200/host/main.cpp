@@ -258,8 +258,16 @@ int main(int argc, char *argv[]) {
   // One host thread per GPU.  Plain estimate: classes sharded over the GPUs (world = n_gpus, one NCCL
   // all-reduce per pass).  Bootstrap: every GPU holds the whole likelihood and takes replicates r % n_gpus.
   const int world = bootstrap ? 1 : n_gpus;
-  std::vector<unsigned char> nccl_id(MSWB_NCCL_ID_BYTES, 0);
-  if (world > 1 && mswb_nccl_unique_id(nccl_id.data())) { std::cerr << "Initialising the GPUs failed:\n  " << mswb_last_error() << "\nexiting\n"; return 1; }
+  std::vector<mswb_ctx *> group(n_gpus, nullptr);   // sharded mode: one NCCL clique created in one call
+  if (world > 1) {
+    for (auto &x : warmups) if (x.joinable()) x.join();
+    std::vector<int> devs(n_gpus);
+    for (int g = 0; g < n_gpus; ++g) devs[g] = g;
+    if (mswb_ctx_create_group(n_gpus, devs.data(), group.data())) {
+      std::cerr << "Initialising the GPUs failed:\n  " << mswb_last_error() << "\nexiting\n";
+      return 1;
+    }
+  }
 
   std::vector<std::vector<std::vector<double>>> results_by_gpu(n_gpus);   // [gpu][0 = plain, 1.. = replicates][group]
   const bool want_probs = args.has("write-probs") || args.has("print-probs");
@@ -274,7 +282,8 @@ int main(int argc, char *argv[]) {
   auto worker = [&](int gpu) {
     try {
       failed_stage[gpu] = 1;
-      b200::Context ctx(gpu, bootstrap ? 0 : gpu, world, world > 1 ? nccl_id.data() : nullptr);
+      std::unique_ptr<b200::Context> ctx_holder(world > 1 ? new b200::Context(group[gpu], gpu, world) : new b200::Context(gpu));
+      b200::Context &ctx = *ctx_holder;
       Timer tm;
       if (gpu == 0) log("Building equivalence classes");
       b200::Alignment aln(ctx, reads);

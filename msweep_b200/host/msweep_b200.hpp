@@ -29,6 +29,8 @@ public:
     check(mswb_ctx_create(device, rank, world, nccl_id, nullptr, &h_));
     rank_ = rank; world_ = world;
   }
+  // adopt a context created elsewhere (mswb_ctx_create_group)
+  Context(mswb_ctx *adopted, int rank, int world) : h_(adopted), rank_(rank), world_(world) {}
   ~Context() { mswb_ctx_destroy(h_); }
   Context(const Context &) = delete;
   Context &operator=(const Context &) = delete;
