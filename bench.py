@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ecs-per-gpu", type=int, default=12_500_000)
-    ap.add_argument("--storage", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--storage", default="f32", choices=["f32", "f64", "sparse"])
     ap.add_argument("--algo", default="em", choices=["em", "rcg"])
     ap.add_argument("--cpu-sample-ecs", type=int, default=40_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -61,7 +61,8 @@ def peak_gbs():
 
 
 def workload_name(a, n_local):
-    st = "fp32-stored linear likelihood, fp64 accumulation" if a.storage == "f32" else "fp64 likelihood"
+    st = {"f32": "fp32-stored linear likelihood, fp64 accumulation", "f64": "fp64 likelihood",
+          "sparse": "lossless sparse fp64 likelihood (log(zero_inflation) once per class + its group hits)"}[a.storage]
     al = "EM/VB one-pass sweep" if a.algo == "em" else "RCG two-sweep iteration"
     return (f"config 3 shard: {n_local:.3g} ECs x {N_GROUPS} lineages per GPU ({n_local * a.gpus:.3g} ECs in the job), "
             f"{al}, {st}")
@@ -184,7 +185,7 @@ def main():
     ctx = M.Context(local, rank, world, nccl_id, cuda_stream=stream.cuda_stream)
 
     n_local = a.ecs_per_gpu
-    storage = M.STORE_F32 if a.storage == "f32" else M.STORE_F64
+    storage = {"f32": M.STORE_F32, "f64": M.STORE_F64, "sparse": M.STORE_SPARSE}[a.storage]
     algo = M.ALGO_EM if a.algo == "em" else M.ALGO_RCG
     t_gen = time.time()
     wl = synth.generate_ec_patterns(n_local, N_GROUPS, GROUP_SIZE, seed=20231019 + rank)
@@ -270,7 +271,7 @@ def main():
                        "generator_s": round(t_gen, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_of_nominal_8TBs": achieved / 8000.0, "peak_source": peak_src, "traffic": traffic,
-                         "kernel": "em_lin_pass_kernel" if a.algo == "em" else "rcg_sweep_a_kernel + rcg_sweep_b_kernel",
+                         "kernel": ("em_sparse_pass_kernel" if a.storage == "sparse" else "em_lin_pass_kernel") if a.algo == "em" else "rcg_sweep_a_kernel + rcg_sweep_b_kernel",
                          "bytes_per_launch": bytes_per_launch, "kernel_ms": pass_ms,
                          "kernel_share_of_step": pass_ms * passes_per_iter / ms_per_step},
             "cpu_baseline": cb,

@@ -97,7 +97,11 @@ MSWB_API int  mswb_ec_export(const mswb_aln *aln, uint64_t *hash, uint64_t *coun
 MSWB_API void mswb_aln_destroy(mswb_aln *aln);
 
 /* ---- (1b) likelihood ----------------------------------------------------------------------- */
-enum { MSWB_STORE_F64 = 0, MSWB_STORE_F32 = 1 };
+/* F64 / F32: the dense K x N matrix the reference builds (fp32 = --emprecision float, EM only).
+ * SPARSE (EM only, from class patterns only): LL_WOR21 gives every group a class does NOT hit the same value
+ * log(zero_inflation), so a class is stored as that constant plus its few (group, value) hits in fp64 — the same
+ * numbers as F64, O(hits) instead of O(K) bytes per class; config 3 (1e8 x 2000) then fits one GPU. */
+enum { MSWB_STORE_F64 = 0, MSWB_STORE_F32 = 1, MSWB_STORE_SPARSE = 2 };
 /* group_of_target[n_targets], group_sizes[n_groups] as read from the -i file (ids in order of first
  * appearance).  q, e, zero_inflation, min_hits are the reference's -q, -e, --zero-inflation,
  * --min-hits.  The rank keeps the rows of its own EC shard. */

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("MSWB_LIB_PATH", os.path.join(_HERE, "lib", "libmsweep
 HEADER_PATH = os.path.join(_HERE, "..", "include", "msweep_b200.h")
 
 ALGO_RCG, ALGO_EM = 0, 1
-STORE_F64, STORE_F32 = 0, 1
+STORE_F64, STORE_F32, STORE_SPARSE = 0, 1, 2
 RNG_EXACT, RNG_PHILOX = 0, 1
 NCCL_ID_BYTES = 128
 

@@ -57,6 +57,12 @@ struct mswb_lik {
   mswb::DevBuf<double> P64;      // [N x Kp] exp(logl - M_j)                 (EM, F64 storage)
   mswb::DevBuf<float> P32;       // [N x Kp4] same in fp32                   (EM, F32 storage)
   uint32_t Kp32 = 0;             // row stride of P32 (K rounded up to 4)
+  // sparse storage: P(j,k) = P0[j] for the groups class j does not hit, P0[j] + dP for its hits (sorted by group)
+  mswb::DevBuf<uint64_t> nz_ptr;   // [N+1]
+  mswb::DevBuf<uint32_t> nz_grp;   // [nnz] row position (kept-group index) of the hit
+  mswb::DevBuf<double> nz_dP;      // [nnz] exp(logl - M_j) - P0[j]
+  mswb::DevBuf<double> P0;         // [N_pad] exp(log(zero_inflation) - M_j)
+  uint64_t nnz = 0;
 
   // optimiser state that outlives a run (posterior export)
   mswb::DevBuf<double> gamma;    // [N x Kp] RCG log-responsibilities
@@ -71,4 +77,5 @@ namespace mswb {
 // same way when something asks for it again.
 void lik_ensure_logl(mswb_lik *L);     // fp64 log-likelihood (RCG, exports)
 void lik_ensure_linear(mswb_lik *L);   // P = exp(logl - rowmax) in the storage precision (EM)
+void lik_ensure_sparse(mswb_lik *L);   // hit lists (MSWB_STORE_SPARSE)
 } // namespace mswb

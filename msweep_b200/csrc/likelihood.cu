@@ -3,6 +3,7 @@
 // lookup table and the dense gather, written EC-major straight into the layout the VI sweeps read.
 #include "handles.cuh"
 
+#include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -115,6 +116,105 @@ lik_fill_kernel(const uint64_t *__restrict__ pat_ptr, const uint32_t *__restrict
   }
 }
 
+// ---- sparse storage -------------------------------------------------------------------------------------
+// Pass 1: number of distinct kept groups each class hits.  Pass 2: the hits themselves, sorted by group inside a
+// class so that every run produces the same arrays bit for bit.
+__global__ void __launch_bounds__(LIK_NT)
+sparse_count_kernel(const uint64_t *__restrict__ pat_ptr, const uint32_t *__restrict__ pat_targets,
+                    const uint32_t *__restrict__ group_of_target, const int *__restrict__ pos_of_group,
+                    unsigned long long N, int K_all, int active_warps, uint64_t *__restrict__ nz_count) {
+  extern __shared__ unsigned s_rows[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= active_warps) return;
+  unsigned *row = s_rows + (size_t)warp * K_all;
+  for (int k = lane; k < K_all; k += 32) row[k] = 0;
+  __syncwarp();
+  const unsigned long long n_warps = (unsigned long long)gridDim.x * active_warps;
+  for (unsigned long long j = (unsigned long long)blockIdx.x * active_warps + warp; j < N; j += n_warps) {
+    const unsigned long long a = pat_ptr[j], b = pat_ptr[j + 1];
+    count_pattern(row, pat_targets, a, b, group_of_target, lane);
+    unsigned n = 0;
+    for (unsigned long long p = a + lane; p < b; p += 32) {
+      const uint32_t g = group_of_target[pat_targets[p]];
+      if (atomicExch(&row[g], 0u) > 0u && pos_of_group[g] >= 0) ++n;
+    }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) nz_count[j] = n;
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(LIK_NT)
+sparse_fill_kernel(const uint64_t *__restrict__ pat_ptr, const uint32_t *__restrict__ pat_targets,
+                   const uint32_t *__restrict__ group_of_target, const int *__restrict__ pos_of_group,
+                   const uint64_t *__restrict__ lut_off, const double *__restrict__ lut, unsigned long long N,
+                   int K_all, int active_warps, double l0, const uint64_t *__restrict__ nz_ptr,
+                   uint32_t *__restrict__ nz_grp, double *__restrict__ nz_dP, double *__restrict__ P0,
+                   double *__restrict__ rowmax) {
+  extern __shared__ unsigned s_rows[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= active_warps) return;
+  unsigned *row = s_rows + (size_t)warp * K_all;
+  for (int k = lane; k < K_all; k += 32) row[k] = 0;
+  __syncwarp();
+  const unsigned long long n_warps = (unsigned long long)gridDim.x * active_warps;
+  for (unsigned long long j = (unsigned long long)blockIdx.x * active_warps + warp; j < N; j += n_warps) {
+    const unsigned long long a = pat_ptr[j], b = pat_ptr[j + 1];
+    count_pattern(row, pat_targets, a, b, group_of_target, lane);
+    double m = l0;
+    for (unsigned long long p = a + lane; p < b; p += 32) {
+      const uint32_t g = group_of_target[pat_targets[p]];
+      const int pos = pos_of_group[g];
+      if (pos >= 0) m = fmax(m, lut[lut_off[pos] + row[g]]);
+    }
+    m = warp_max(m);
+    const double p0 = exp(l0 - m);
+    if (lane == 0) { rowmax[j] = m; P0[j] = p0; }
+    // emit the hits in arrival order ...
+    const unsigned long long base = nz_ptr[j];
+    const unsigned n_row = (unsigned)(nz_ptr[j + 1] - base);
+    unsigned emitted = 0;
+    for (unsigned long long p0i = a; p0i < b; p0i += 32) {
+      const unsigned long long p = p0i + lane;
+      bool mine = false;
+      uint32_t pos_u = 0;
+      double v = 0.0;
+      if (p < b) {
+        const uint32_t g = group_of_target[pat_targets[p]];
+        const unsigned c = atomicExch(&row[g], 0u);
+        const int pos = pos_of_group[g];
+        if (c > 0u && pos >= 0) { mine = true; pos_u = (uint32_t)pos; v = exp(lut[lut_off[pos] + c] - m) - p0; }
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, mine);
+      if (mine) {
+        const unsigned slot = emitted + __popc(ballot & ((1u << lane) - 1u));
+        nz_grp[base + slot] = pos_u;
+        nz_dP[base + slot] = v;
+      }
+      emitted += __popc(ballot);
+    }
+    __syncwarp();
+    // ... then order them by group (distinct within a row): every entry finds its rank and moves there
+    if (n_row <= 32) {
+      uint32_t gi = 0; double vi = 0.0; unsigned rank = 0;
+      if ((unsigned)lane < n_row) {
+        gi = nz_grp[base + lane]; vi = nz_dP[base + lane];
+        for (unsigned q = 0; q < n_row; ++q) rank += nz_grp[base + q] < gi ? 1u : 0u;
+      }
+      __syncwarp();                                        // everything is read before anything is overwritten
+      if ((unsigned)lane < n_row) { nz_grp[base + rank] = gi; nz_dP[base + rank] = vi; }
+    } else if (lane == 0) {                                // a class hitting more than 32 groups: insertion sort, rare
+      for (unsigned x = 1; x < n_row; ++x) {
+        const uint32_t g = nz_grp[base + x]; const double v = nz_dP[base + x];
+        unsigned y = x;
+        while (y > 0 && nz_grp[base + y - 1] > g) { nz_grp[base + y] = nz_grp[base + y - 1]; nz_dP[base + y] = nz_dP[base + y - 1]; --y; }
+        nz_grp[base + y] = g; nz_dP[base + y] = v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void u64_to_double_kernel(const uint64_t *in, double *out, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
 }
@@ -180,6 +280,15 @@ void build_lut(const std::vector<uint64_t> &sizes, double q, double e, double zi
     row[0] = l0;
     for (uint64_t c = 1; c <= sizes[g]; ++c) row[c] = ldbb_scaled_h(c, sizes[g], alpha, beta) + l1;
   }
+}
+
+void device_exclusive_sum_u64(mswb_ctx *ctx, const uint64_t *in, uint64_t *out, size_t n) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int64_t)n, ctx->stream);
+  mswb::DevBuf<unsigned char> tmp;
+  tmp.alloc(bytes);
+  MSWB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int64_t)n, ctx->stream));
+  MSWB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 // Warps of a CTA that get a counter row: as many as fit in ~200 KB of shared memory.
@@ -272,6 +381,39 @@ template <typename ST> static void dense_to_linear(mswb_lik *L, DevBuf<ST> &P, u
   MSWB_LAUNCHED();
 }
 
+void lik_ensure_sparse(mswb_lik *L) {
+  if (L->nz_ptr.p) return;
+  MSWB_REQUIRE(L->from_patterns, "sparse storage needs a likelihood built from class patterns");
+  mswb_ctx *ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  const size_t smem = lik_smem_bytes(L->K_all);
+  const int grid = fill_grid(ctx, L->N, L->K_all), aw = lik_active_warps(L->K_all);
+  DevBuf<uint64_t> cnt;
+  cnt.alloc(L->N + 1);
+  MSWB_CUDA(cudaMemsetAsync(cnt.p, 0, (L->N + 1) * sizeof(uint64_t), s));
+  prepare_fill_kernel(sparse_count_kernel, smem);
+  sparse_count_kernel<<<grid, LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->pos_dev.p, L->N,
+                                                 (int)L->K_all, aw, cnt.p);
+  MSWB_LAUNCHED();
+  L->nz_ptr.alloc(L->N + 1);
+  device_exclusive_sum_u64(ctx, cnt.p, L->nz_ptr.p, L->N + 1);
+  uint64_t nnz = 0;
+  d2h(&nnz, L->nz_ptr.p + L->N, 1, s);
+  MSWB_CUDA(cudaStreamSynchronize(s));
+  L->nnz = nnz;
+  L->nz_grp.alloc(nnz);
+  L->nz_dP.alloc(nnz);
+  L->P0.alloc(L->N_pad);
+  L->rowmax.alloc(L->N_pad);
+  MSWB_CUDA(cudaMemsetAsync(L->P0.p, 0, L->P0.bytes(), s));
+  MSWB_CUDA(cudaMemsetAsync(L->rowmax.p, 0, L->rowmax.bytes(), s));
+  prepare_fill_kernel(sparse_fill_kernel, smem);
+  sparse_fill_kernel<<<grid, LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->pos_dev.p, L->lut_off.p,
+                                                L->lut.p, L->N, (int)L->K_all, aw, L->l0, L->nz_ptr.p, L->nz_grp.p, L->nz_dP.p,
+                                                L->P0.p, L->rowmax.p);
+  MSWB_LAUNCHED();
+}
+
 void lik_ensure_linear(mswb_lik *L) {
   if (L->storage == MSWB_STORE_F32) {
     if (L->P32.p) return;
@@ -298,7 +440,7 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
   return guarded([&] {
     MSWB_REQUIRE(ctx && aln && group_of_target && group_sizes && out, "NULL argument");
     MSWB_REQUIRE(aln->ctx == ctx, "alignment belongs to another context");
-    MSWB_REQUIRE(storage == MSWB_STORE_F64 || storage == MSWB_STORE_F32, "unknown storage");
+    MSWB_REQUIRE(storage == MSWB_STORE_F64 || storage == MSWB_STORE_F32 || storage == MSWB_STORE_SPARSE, "unknown storage");
     MSWB_REQUIRE(n_groups >= 1, "the grouping has no groups");
     MSWB_REQUIRE(aln->partitioned || aln->n_ecs > 0, "the alignment holds no equivalence class: no read aligned to any reference sequence");
     MSWB_REQUIRE(zero_inflation > 0.0 && zero_inflation < 1.0, "zero inflation must lie in (0, 1)");
@@ -402,7 +544,9 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
 
     // ---- dense gather (include/Likelihood.hpp:176-185), EC-major ---------------------------------
     // fp32 storage exists for matrices that do not fit as fp64: it goes straight to the linear form.
-    if (storage == MSWB_STORE_F64) lik_ensure_logl(L.get()); else lik_ensure_linear(L.get());
+    if (storage == MSWB_STORE_F64) lik_ensure_logl(L.get());
+    else if (storage == MSWB_STORE_F32) lik_ensure_linear(L.get());
+    else lik_ensure_sparse(L.get());
     MSWB_CUDA(cudaStreamSynchronize(s));   // host vectors above go out of scope
     *out = L.release();
   });

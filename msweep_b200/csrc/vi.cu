@@ -67,7 +67,7 @@ __global__ void em_ctl_kernel(ViArrays a, ViCtl *ctl, int K, int linear) {
   __shared__ double scratch[32];
   double lg = 0.0, dga = 0.0;
   for (int k = threadIdx.x; k < K; k += CTL_NT) {
-    const double A = linear ? a.w[k] * a.red[k] : a.red[k];
+    const double A = linear ? a.w[k] * (a.red[k] + a.red[K + 1]) : a.red[k];   // red[K+1]: the share every group gets (sparse pass), else 0
     const double nk = a.alpha0[k] + A;
     a.N_k[k] = nk;
     lg += lgamma(nk);
@@ -431,7 +431,17 @@ void em_iteration(mswb_vi *vi) {
   bool want_pipe = false;
   if (const char *e = getenv("MSWB_EM_R")) rsel = atoi(e);
   if (const char *e = getenv("MSWB_EM_TMA")) want_pipe = e[0] == '1';
-  if (vi->linear && L->storage == MSWB_STORE_F32) {
+  if (vi->linear && L->storage == MSWB_STORE_SPARSE) {
+    const size_t smem = (size_t)2 * K * sizeof(double);
+    MSWB_REQUIRE(smem <= 200 * 1024, "too many groups for the sparse EM pass (weights and accumulators live in shared memory)");
+    if (smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(em_sparse_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    MSWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_sparse_pass_kernel, 256, smem));
+    vi->grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)vi->ctx->n_sms * std::max(1, per_sm), std::min<uint64_t>(ceil_div(L->N, 256), (uint64_t)vi->max_grid)));
+    em_sparse_pass_kernel<<<vi->grid, 256, smem, s>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_dP.p, L->P0.p, L->rowmax.p, vi->counts, vi->w.p,
+                                                     vi->ctl.p, vi->partials.p, vi->pstride, L->N, K);
+    MSWB_LAUNCHED();
+  } else if (vi->linear && L->storage == MSWB_STORE_F32) {
     if (rsel == 1) MSWB_TILE_DISPATCH(L->Kp32 / 4, 1, 1, 1, MSWB_LAUNCH_EM(float, L->P32.p, L->Kp32));
     else if (rsel == 2) MSWB_TILE_DISPATCH(L->Kp32 / 4, 2, 2, 1, MSWB_LAUNCH_EM(float, L->P32.p, L->Kp32));
     else if (rsel == 4) MSWB_TILE_DISPATCH(L->Kp32 / 4, 4, 4, 2, MSWB_LAUNCH_EM(float, L->P32.p, L->Kp32));
@@ -448,8 +458,8 @@ void em_iteration(mswb_vi *vi) {
                         vi->partials.p, vi->pstride, L->N, K, 0));
   }
   timer.stop();
-  launch_finalize(vi, K + 1, 0);
-  vi->ctx->allreduce_sum(vi->red.p, K + 1);
+  launch_finalize(vi, vi->linear ? K + 2 : K + 1, 0);
+  vi->ctx->allreduce_sum(vi->red.p, vi->linear ? K + 2 : K + 1);
   em_ctl_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, vi->linear ? 1 : 0);
   MSWB_LAUNCHED();
 }
@@ -573,9 +583,14 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
       vi->pass_bytes = (uint64_t)lik->N * K * 56 + (uint64_t)lik->N * 8;   // sweep A 16 B + sweep B 40 B per element
     } else {
       vi->linear = true;
-      lik_ensure_linear(lik);
-      const uint64_t bl = lik->storage == MSWB_STORE_F32 ? 4 : 8;
-      vi->pass_bytes = (uint64_t)lik->N * K * bl + (uint64_t)lik->N * 16;    // P once, c_j and M_j once
+      if (lik->storage == MSWB_STORE_SPARSE) {
+        lik_ensure_sparse(lik);
+        vi->pass_bytes = lik->nnz * 12 + (uint64_t)lik->N * 40;              // hits (group + value), ptr, P0, M_j, c_j
+      } else {
+        lik_ensure_linear(lik);
+        const uint64_t bl = lik->storage == MSWB_STORE_F32 ? 4 : 8;
+        vi->pass_bytes = (uint64_t)lik->N * K * bl + (uint64_t)lik->N * 16;  // P once, c_j and M_j once
+      }
     }
 
     // per-group vectors
@@ -737,6 +752,7 @@ int mswb_vi_posteriors(mswb_ctx *ctx, mswb_lik *lik, uint64_t ec_begin, uint64_t
     tile.alloc((size_t)n * lik->K);
     const int K = (int)lik->K;
     const int blocks = (int)std::min<uint64_t>(ceil_div(n, 8), (uint64_t)ctx->n_sms * 8);
+    MSWB_REQUIRE(lik->storage != MSWB_STORE_SPARSE, "posterior export is not available in sparse storage (build the likelihood dense)");
     if (lik->last_algo == MSWB_ALGO_RCG) {
       posterior_tile_kernel<double><<<blocks, 256, 0, ctx->stream>>>(0, lik->gamma.p, nullptr, (int)lik->Kp, nullptr, 0, nullptr, ec_begin, n, K, tile.p);
     } else if (lik->logl.p) {

@@ -808,6 +808,50 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
   if (threadIdx.x == 0) out[K] = bound;
 }
 
+// =====================================================================================================
+// EM / VB pass over the SPARSE storage: class j is P0_j on every group except its hits, where it is P0_j + dP.
+//   S_j = P0_j W + sum_hits dP w_g          (W = sum_k w_k)
+//   A_k = Z + sum_{hits of k} dP c_j / S_j  (Z = sum_j P0_j c_j / S_j, the part every group receives)
+// One thread per class, the weight vector and the per-group accumulators in shared memory (fp64 atomics: the
+// only place on the path where the summation order, hence the last bits, can vary from run to run).
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+em_sparse_pass_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_dP,
+                      const double *__restrict__ P0, const double *__restrict__ rowmax, const double *__restrict__ counts,
+                      const double *__restrict__ w, const ViCtl *__restrict__ ctl, double *__restrict__ partials, int pstride,
+                      unsigned long long N, int K) {
+  if (ctl->done) return;
+  extern __shared__ double s_dyn[];
+  double *s_w = s_dyn, *s_acc = s_dyn + K;
+  __shared__ double s_blk[32];
+  double wsum = 0.0;
+  for (int k = threadIdx.x; k < K; k += 256) { const double x = w[k]; s_w[k] = x; s_acc[k] = 0.0; wsum += x; }
+  wsum = block_sum<256>(wsum, s_blk);        // same order in every CTA and on every rank
+  __syncthreads();
+  double z = 0.0, elbo = 0.0;
+  int fault = 0;
+  for (unsigned long long j = blockIdx.x * 256ull + threadIdx.x; j < N; j += (unsigned long long)gridDim.x * 256ull) {
+    const double c = counts[j];
+    if (!(c > 0.0)) continue;
+    const unsigned long long a = nz_ptr[j], b = nz_ptr[j + 1];
+    const double p0 = P0[j];
+    double s = p0 * wsum;
+    for (unsigned long long e = a; e < b; ++e) s = fma(nz_dP[e], s_w[nz_grp[e]], s);
+    if (!(s > 0.0) || isinf(s)) { fault = 1; continue; }
+    const double r = c / s;
+    z = fma(r, p0, z);
+    elbo = fma(c, log(s) + rowmax[j], elbo);
+    for (unsigned long long e = a; e < b; ++e) atomicAdd(&s_acc[nz_grp[e]], r * nz_dP[e]);
+  }
+  __syncthreads();
+  double *out = partials + (unsigned long long)blockIdx.x * pstride;
+  for (int k = threadIdx.x; k < K; k += 256) out[k] = s_acc[k];
+  z = block_sum<256>(z, s_blk);
+  elbo = block_sum<256>(elbo, s_blk);
+  if (threadIdx.x == 0) { out[K] = elbo; out[K + 1] = z; }
+  if (fault) atomicExch(const_cast<int *>(&ctl->fault), 1);
+}
+
 // ---- small kernels --------------------------------------------------------------------------------
 // red[v] = sum over CTAs of partials[cta][v], fixed order.  v < nvals.
 __global__ void finalize_partials_kernel(const double *__restrict__ partials, int pstride, int n_ctas, int nvals,

@@ -139,6 +139,35 @@ def test_fp32_storage_tolerance(case, oracle, mswb, ctx):
         lik.vi_run(mswb.ALGO_RCG)
 
 
+@pytest.mark.parametrize("min_hits", [0, 3])
+def test_sparse_storage_is_lossless(case, oracle, mswb, ctx, min_hits):
+    """MSWB_STORE_SPARSE keeps, per class, log(zero_inflation) once plus its (group, value) hits in fp64: the same
+    numbers as the dense fp64 matrix, so EM must follow the oracle's fp64 trajectory (fp64 tolerances apply)."""
+    name, wl, ec, aln = case
+    ref_l = oracle.lik_build(ec, wl.group_of_target, wl.group_sizes, min_hits=min_hits)
+    if ref_l.n_groups == 0:
+        pytest.skip("all groups pruned")
+    ref = oracle.vi_run("em", ref_l.logl, ref_l.log_counts, tol=1e-6, max_iters=5000)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, min_hits=min_hits, storage=mswb.STORE_SPARSE)
+    assert lik.n_groups == ref_l.n_groups
+    got = lik.vi_run(mswb.ALGO_EM, tol=1e-6, max_iters=5000)
+    assert got.iters == ref.iters and got.converged == ref.converged
+    assert np.max(np.abs(got.theta - ref.theta)) < THETA_TOL
+    assert abs(got.bound - ref.bound) <= ELBO_RTOL * abs(ref.bound)
+    dense = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, min_hits=min_hits).vi_run(mswb.ALGO_EM, tol=0.0, max_iters=25)
+    sparse = lik.vi_run(mswb.ALGO_EM, tol=0.0, max_iters=25)
+    assert np.max(np.abs(dense.theta - sparse.theta)) < 1e-12
+    with pytest.raises(mswb.MswbError, match="RCG needs"):
+        lik.vi_run(mswb.ALGO_RCG)
+    # bootstrap replicates run on the sparse form too
+    thetas, _ = lik.bootstrap_run(2, seed=5, algo=mswb.ALGO_EM, max_iters=30, tol=0.0)
+    counts = oracle.bootstrap_resample(ec.count, 5, 2)
+    for r in range(2):
+        with np.errstate(divide="ignore"):
+            want = oracle.vi_run("em", ref_l.logl, np.log(counts[r].astype(np.float64)), tol=0.0, max_iters=30)
+        assert np.max(np.abs(thetas[r] - want.theta)) < THETA_TOL
+
+
 def test_golden_fixture(mswb, ctx):
     """The frozen numbers (no oracle at run time)."""
     g = np.load(os.path.join(GOLD, "small_case.npz"))
