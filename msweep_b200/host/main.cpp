@@ -51,7 +51,7 @@ struct Args {
 const std::set<std::string> kBool = {"verbose", "version", "cite", "help", "no-fit-model", "print-timings", "write-probs", "print-probs"};
 const std::set<std::string> kValued = {"themisto-1", "themisto-2", "themisto", "i", "o", "themisto-mode", "t", "max-iters", "tol",
                                        "algorithm", "emprecision", "iters", "seed", "bootstrap-count", "q", "e", "alphas",
-                                       "zero-inflation", "min-hits", "gpus", "rng", "dump-alignment"};
+                                       "zero-inflation", "min-hits", "gpus", "rng", "dump-alignment", "storage"};
 const std::set<std::string> kUnsupported = {"bin-reads", "target-groups", "min-abundance",
                                             "write-likelihood", "write-likelihood-bitseq", "compress", "compression-level",
                                             "read-likelihood", "run-rate"};
@@ -96,6 +96,7 @@ const char *kHelp =
     "  --gpus                       number of B200s to use (default: 1)\n"
     "  --algorithm                  rcgb200 | emb200 (aliases: rcggpu, emgpu; default: rcgb200)\n"
     "  --emprecision                float | double, for emb200 (default: double)\n"
+    "  --storage                    dense | sparse likelihood on the device, sparse for emb200 only (default: dense)\n"
     "  --max-iters                  optimiser iteration cap (default: 5000)\n"
     "  --tol                        stop when the bound changes by less than this (default: 0.000001)\n"
     "  --iters                      bootstrap replicates (default: 0)\n"
@@ -216,6 +217,12 @@ int main(int argc, char *argv[]) {
     const std::string prec = args.str("emprecision", "double");
     if (prec == "float") { if (vi.algo == MSWB_ALGO_EM) storage = MSWB_STORE_F32; }
     else if (prec != "double") throw std::runtime_error("Unknown --emprecision `" + prec + "` (one of float, double)");
+    const std::string store = args.str("storage", "dense");
+    if (store == "sparse") {
+      if (vi.algo != MSWB_ALGO_EM) throw std::runtime_error("--storage sparse needs --algorithm emb200 (RCG keeps dense per-class state)");
+      if (args.has("write-probs") || args.has("print-probs")) throw std::runtime_error("--storage sparse cannot export the probability matrix; use --storage dense");
+      storage = MSWB_STORE_SPARSE;
+    } else if (store != "dense") throw std::runtime_error("Unknown --storage `" + store + "` (one of dense, sparse)");
     vi.tol = args.num<double>("tol", 1e-6);
     vi.max_iters = args.num<uint64_t>("max-iters", 5000);
   } catch (std::exception &e) {

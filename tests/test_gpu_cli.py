@@ -39,9 +39,10 @@ def run_both(d, paths, g, extra, tag, oracle_algo="rcgcpu"):
     r = subprocess.run([CLI, "--themisto-1", paths[0], "--themisto-2", paths[1], "-i", g, "-o", ours, "-t", "4", *extra],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    ex = [x for x in extra if x not in ("rcgb200", "emb200")]
-    if "--algorithm" in ex:
-        ex.remove("--algorithm")
+    ex = [x for x in extra if x not in ("rcgb200", "emb200", "sparse", "dense")]
+    for flag in ("--algorithm", "--storage"):
+        if flag in ex:
+            ex.remove(flag)
     r2 = subprocess.run([ORACLE, "--themisto-1", paths[0], "--themisto-2", paths[1], "-i", g, "-o", ref, "-t", "4",
                          "--algorithm", oracle_algo, *ex], capture_output=True, text=True)
     assert r2.returncode == 0, r2.stderr
@@ -66,6 +67,14 @@ def test_em_and_float_precision(data):
     (h, names, vals3), _, _ = run_both(d, paths, g, ["--algorithm", "emb200", "--emprecision", "float", "--tol", "1e-5"], "emf",
                                        oracle_algo="emgpu")
     assert np.max(np.abs(vals3 - vals2)) < 1e-3             # float EM stops elsewhere on the plateau (docs/gpubenchmarks.md:27)
+
+
+def test_sparse_storage_flag(data):
+    d, wl, paths, g = data
+    (h, names, vals), (h2, _, vals2), _ = run_both(d, paths, g, ["--algorithm", "emb200", "--storage", "sparse"], "sp", oracle_algo="emgpu")
+    assert h[1:] == h2[1:] and np.max(np.abs(vals - vals2)) < 2e-6
+    r = subprocess.run([CLI, "--themisto", ",".join(paths), "-i", g, "--storage", "sparse"], capture_output=True, text=True)
+    assert r.returncode == 1 and "needs --algorithm emb200" in r.stderr
 
 
 def test_min_hits_orders_pruned_groups_last(data):
