@@ -267,52 +267,60 @@ struct mswb_vi {
 namespace {
 
 // ---- tile dispatch ---------------------------------------------------------------------------------
-// slots = 16-byte vectors per row.  (TPR, KITER) is the smallest shape that covers the row; R (rows per
-// thread group and batch) trades registers and stage size for fewer row reductions: RS for narrow rows
-// (several row groups per CTA), RM for the 256x4 shape, RL for KITER = 8.
-#define MSWB_TILE_DISPATCH(slots, RS, RM, RL, ...)                                            \
+// slots = 16-byte pieces per row.  A row is covered by TPR threads x KITER pieces with TPR a multiple of 32 —
+// the smallest TPR for the KITER class, so at most one warp's worth of lanes idles whatever K is.  KITER grows with
+// the row (1, 2 up to 512 pieces, 4 up to 1024, 8 beyond) and the rows per batch shrink with it:
+// R = RMAX / KITER (at most 4), RMAX = 8 for the sweeps that keep two arrays live (EM with its prefetch buffer,
+// RCG sweep A), 4 for RCG sweep B (four arrays), so that two CTAs fit an SM (<= 128 registers) up to KITER = 4.
+template <int RMAX, int KITER> constexpr int rows_for() { return RMAX / KITER >= 4 ? 4 : (RMAX / KITER >= 2 ? 2 : 1); }
+
+#define MSWB_SHAPE_CASE(TPRV, KITERV, RMAX, ...) { using TL = Tile<TPRV, KITERV, rows_for<RMAX, KITERV>()>; __VA_ARGS__; }
+#define MSWB_SHAPE_BY_TPR(tpr, KITERV, RMAX, ...)                                            \
+  switch (tpr) {                                                                             \
+    case 32: MSWB_SHAPE_CASE(32, KITERV, RMAX, __VA_ARGS__) break;                           \
+    case 64: MSWB_SHAPE_CASE(64, KITERV, RMAX, __VA_ARGS__) break;                           \
+    case 96: MSWB_SHAPE_CASE(96, KITERV, RMAX, __VA_ARGS__) break;                           \
+    case 128: MSWB_SHAPE_CASE(128, KITERV, RMAX, __VA_ARGS__) break;                         \
+    case 160: MSWB_SHAPE_CASE(160, KITERV, RMAX, __VA_ARGS__) break;                         \
+    case 192: MSWB_SHAPE_CASE(192, KITERV, RMAX, __VA_ARGS__) break;                         \
+    case 224: MSWB_SHAPE_CASE(224, KITERV, RMAX, __VA_ARGS__) break;                         \
+    default: MSWB_SHAPE_CASE(256, KITERV, RMAX, __VA_ARGS__) break;                          \
+  }
+// rows of more than 512 pieces need at least 160 threads per row in the KITER = 4 / 8 classes
+#define MSWB_SHAPE_BY_TPR_WIDE(tpr, KITERV, RMAX, ...)                                       \
+  switch (tpr) {                                                                             \
+    case 160: MSWB_SHAPE_CASE(160, KITERV, RMAX, __VA_ARGS__) break;                         \
+    case 192: MSWB_SHAPE_CASE(192, KITERV, RMAX, __VA_ARGS__) break;                         \
+    case 224: MSWB_SHAPE_CASE(224, KITERV, RMAX, __VA_ARGS__) break;                         \
+    default: MSWB_SHAPE_CASE(256, KITERV, RMAX, __VA_ARGS__) break;                          \
+  }
+#define MSWB_TILE_DISPATCH(slots, RMAX, ...)                                                 \
   do {                                                                                       \
-    if ((slots) <= 32) { using TL = Tile<32, 1, RS>; __VA_ARGS__; }                          \
-    else if ((slots) <= 64) { using TL = Tile<32, 2, RS>; __VA_ARGS__; }                     \
-    else if ((slots) <= 128) { using TL = Tile<32, 4, RS>; __VA_ARGS__; }                    \
-    else if ((slots) <= 256) { using TL = Tile<64, 4, RS>; __VA_ARGS__; }                    \
-    else if ((slots) <= 512) { using TL = Tile<128, 4, RS>; __VA_ARGS__; }                   \
-    else if ((slots) <= 1024) { using TL = Tile<256, 4, RM>; __VA_ARGS__; }                  \
-    else if ((slots) <= 2048) { using TL = Tile<256, 8, RL>; __VA_ARGS__; }                  \
-    else if ((slots) <= 4096) { using TL = Tile<512, 8, 1>; __VA_ARGS__; }                   \
-    else if ((slots) <= 8192) { using TL = Tile<1024, 8, 1>; __VA_ARGS__; }                  \
+    const int _s = (int)(slots);                                                             \
+    if (_s <= 32) MSWB_SHAPE_CASE(32, 1, RMAX, __VA_ARGS__)                                  \
+    else if (_s <= 512) { const int _t = (int)round_up(ceil_div(_s, 2), 32); MSWB_SHAPE_BY_TPR(_t, 2, RMAX, __VA_ARGS__) }   \
+    else if (_s <= 1024) { const int _t = (int)round_up(ceil_div(_s, 4), 32); MSWB_SHAPE_BY_TPR_WIDE(_t, 4, RMAX, __VA_ARGS__) }  \
+    else if (_s <= 2048) { const int _t = (int)round_up(ceil_div(_s, 8), 32); MSWB_SHAPE_BY_TPR_WIDE(_t, 8, RMAX, __VA_ARGS__) }  \
+    else if (_s <= 4096) MSWB_SHAPE_CASE(512, 8, RMAX, __VA_ARGS__)                          \
+    else if (_s <= 8192) MSWB_SHAPE_CASE(1024, 8, RMAX, __VA_ARGS__)                         \
     else throw Error("too many groups for the compiled tile shapes (max 16384 in fp64)");   \
   } while (0)
 
-// EM sweep: shapes chosen so that R * KITER <= 8 pieces per thread and buffer — two register buffers
-// (prefetch) then fit in <= 128 registers and two CTAs share an SM (measured: +8..15 % over one CTA).
-#define MSWB_TILE_DISPATCH_EM(slots, ...)                                                    \
+// Log-domain (RCG) sweeps: measured best with 256-thread CTAs throughout (16 warps per SM hide the longer
+// dependency chains of these sweeps better than the tighter 160/192/224-thread rows do: K = 1500 runs at 4.3 TB/s on
+// Tile<192,4,.> and K = 300 at 2.9 on Tile<96,2,.> against 5.3-5.5 on the power-of-two shapes), KITER = 4 from 65 pieces.
+#define MSWB_TILE_DISPATCH_RCG(slots, RMAX, ...)                                             \
   do {                                                                                       \
-    if ((slots) <= 32) { using TL = Tile<32, 1, 4>; __VA_ARGS__; }                           \
-    else if ((slots) <= 64) { using TL = Tile<32, 2, 4>; __VA_ARGS__; }                      \
-    else if ((slots) <= 128) { using TL = Tile<64, 2, 4>; __VA_ARGS__; }                     \
-    else if ((slots) <= 256) { using TL = Tile<128, 2, 4>; __VA_ARGS__; }                    \
-    else if ((slots) <= 512) { using TL = Tile<256, 2, 4>; __VA_ARGS__; }                    \
-    else if ((slots) <= 1024) { using TL = Tile<256, 4, 2>; __VA_ARGS__; }                   \
-    else if ((slots) <= 2048) { using TL = Tile<256, 8, 1>; __VA_ARGS__; }                   \
-    else if ((slots) <= 4096) { using TL = Tile<512, 8, 1>; __VA_ARGS__; }                   \
-    else if ((slots) <= 8192) { using TL = Tile<1024, 8, 1>; __VA_ARGS__; }                  \
-    else throw Error("too many groups for the compiled tile shapes (max 16384 in fp64)");   \
-  } while (0)
-
-// Log-domain sweeps: RA rows per batch for shapes with KITER <= 2, RB for KITER = 4, 1 row for KITER = 8.
-// Sweep A keeps two arrays live (R * KITER <= 8 for two CTAs per SM), sweep B four (R * KITER <= 4).
-#define MSWB_TILE_DISPATCH_RCG(slots, R1, R2, R4, ...)                                       \
-  do {                                                                                       \
-    if ((slots) <= 32) { using TL = Tile<32, 1, R1>; __VA_ARGS__; }                          \
-    else if ((slots) <= 64) { using TL = Tile<32, 2, R2>; __VA_ARGS__; }                     \
-    else if ((slots) <= 128) { using TL = Tile<32, 4, R4>; __VA_ARGS__; }                    \
-    else if ((slots) <= 256) { using TL = Tile<64, 4, R4>; __VA_ARGS__; }                    \
-    else if ((slots) <= 512) { using TL = Tile<128, 4, R4>; __VA_ARGS__; }                   \
-    else if ((slots) <= 1024) { using TL = Tile<256, 4, R4>; __VA_ARGS__; }                  \
-    else if ((slots) <= 2048) { using TL = Tile<256, 8, 1>; __VA_ARGS__; }                   \
-    else if ((slots) <= 4096) { using TL = Tile<512, 8, 1>; __VA_ARGS__; }                   \
-    else if ((slots) <= 8192) { using TL = Tile<1024, 8, 1>; __VA_ARGS__; }                  \
+    const int _s = (int)(slots);                                                             \
+    if (_s <= 32) MSWB_SHAPE_CASE(32, 1, RMAX, __VA_ARGS__)                                  \
+    else if (_s <= 64) MSWB_SHAPE_CASE(32, 2, RMAX, __VA_ARGS__)                             \
+    else if (_s <= 128) MSWB_SHAPE_CASE(32, 4, RMAX, __VA_ARGS__)                            \
+    else if (_s <= 256) MSWB_SHAPE_CASE(64, 4, RMAX, __VA_ARGS__)                            \
+    else if (_s <= 512) MSWB_SHAPE_CASE(128, 4, RMAX, __VA_ARGS__)                           \
+    else if (_s <= 1024) MSWB_SHAPE_CASE(256, 4, RMAX, __VA_ARGS__)                          \
+    else if (_s <= 2048) MSWB_SHAPE_CASE(256, 8, RMAX, __VA_ARGS__)                          \
+    else if (_s <= 4096) MSWB_SHAPE_CASE(512, 8, RMAX, __VA_ARGS__)                          \
+    else if (_s <= 8192) MSWB_SHAPE_CASE(1024, 8, RMAX, __VA_ARGS__)                         \
     else throw Error("too many groups for the compiled tile shapes (max 16384 in fp64)");   \
   } while (0)
 
@@ -373,26 +381,10 @@ void launch_finalize(mswb_vi *vi, int nvals, int only_if_reset) {
 }
 
 // Measured on B200 (1e6 x 2000 fp64): the log-domain sweeps run at 5.5 TB/s with direct streaming loads and
-// two CTAs per SM, 4.0 TB/s through the TMA stage ring; the ring stays available behind MSWB_RCG_TMA=1.
+// two CTAs per SM, 4.0 TB/s through the TMA stage ring; the EM sweep 6.5-6.7 vs 5.2 TB/s.  The ring is therefore
+// opt-in (MSWB_RCG_TMA=1 / MSWB_EM_TMA=1) and compiled for the full-width (TPR = 256) shapes only.
 bool want_rcg_pipe() { const char *e = getenv("MSWB_RCG_TMA"); return e && e[0] == '1'; }
-
-// Launch one sweep: the staged (TMA) instantiation when asked for and the geometry allows, else the direct one.
-// KERN(PIPE) names the kernel template instantiation; ARGS are its arguments before the PipeGeom.
-#define MSWB_LAUNCH_SWEEP(KERN_PIPE, KERN_DIRECT, ROW_BYTES, NSRC, ...)                                        \
-  do {                                                                                                         \
-    const PipeGeom geom = want_rcg_pipe() ? pipe_geometry((ROW_BYTES), TL::G * TL::R, (NSRC), TL::TPR) : PipeGeom{0, 0, 0}; \
-    if (geom.stages) {                                                                                         \
-      auto kern = KERN_PIPE;                                                                                   \
-      const size_t smem = pipe_smem_bytes(geom, (NSRC));                                                       \
-      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N, (uint64_t)geom.stage_rows), vi->max_grid); \
-      kern<<<vi->grid, TL::NT, smem, s>>>(__VA_ARGS__, geom);                                                  \
-    } else {                                                                                                   \
-      auto kern = KERN_DIRECT;                                                                                 \
-      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, ceil_div(L->N, (uint64_t)TL::G * TL::R), vi->max_grid); \
-      kern<<<vi->grid, TL::NT, 0, s>>>(__VA_ARGS__, geom);                                                     \
-    }                                                                                                          \
-    MSWB_LAUNCHED();                                                                                           \
-  } while (0)
+bool want_em_pipe() { const char *e = getenv("MSWB_EM_TMA"); return e && e[0] == '1'; }
 
 // Batch -> CTA mapping of the direct EM sweep (see the kernel): chunked once the matrix is large.
 static bool em_chunked(const mswb_lik *L) {
@@ -401,36 +393,81 @@ static bool em_chunked(const mswb_lik *L) {
   return (size_t)L->N_pad * L->K * el > ((size_t)16 << 30);   // measured: +1.2 % at 100 GB, neutral at 24 GB
 }
 
-// EM sweep launch: staged (TMA) when asked for and possible, else direct + register prefetch.
-#define MSWB_LAUNCH_EM(ST, PTR, LD)                                                                            \
-  do {                                                                                                         \
-    PipeGeom geom = want_pipe ? pipe_geometry((size_t)(LD) * sizeof(ST), TL::G * TL::R, 1, TL::TPR) : PipeGeom{0, 0, 0}; \
-    if (geom.stages) {                                                                                         \
-      auto kern = em_lin_pass_kernel<ST, TL, true>;                                                      \
-      const size_t smem = pipe_smem_bytes(geom, 1);                                                            \
-      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N_pad, (uint64_t)geom.stage_rows), vi->max_grid); \
-      kern<<<vi->grid, TL::NT, smem, s>>>(PTR, (int)(LD), L->rowmax.p, vi->counts, vi->w.p, vi->ctl.p, vi->partials.p, \
-                                          vi->pstride, L->N_pad, K, geom);                                      \
-    } else {                                                                                                   \
-      auto kern = em_lin_pass_kernel<ST, TL, false>;                                                     \
-      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, L->N_pad / (TL::G * TL::R), vi->max_grid);            \
-      kern<<<vi->grid, TL::NT, 0, s>>>(PTR, (int)(LD), L->rowmax.p, vi->counts, vi->w.p, vi->ctl.p, vi->partials.p, \
-                                       vi->pstride, L->N_pad, K, geom);                                         \
-    }                                                                                                          \
-    MSWB_LAUNCHED();                                                                                           \
-  } while (0)
+template <typename ST, class TL> void launch_em(mswb_vi *vi, const ST *P, int ld) {
+  mswb_lik *L = vi->lik;
+  cudaStream_t s = vi->ctx->stream;
+  PipeGeom geom{0, 0, 0};
+  if constexpr (TL::TPR == 256) {
+    if (want_em_pipe()) geom = pipe_geometry((size_t)ld * sizeof(ST), TL::G * TL::R, 1, TL::TPR);
+    if (geom.stages) {
+      auto kern = em_lin_pass_kernel<ST, TL, true>;
+      const size_t smem = pipe_smem_bytes(geom, 1);
+      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N_pad, (uint64_t)geom.stage_rows), vi->max_grid);
+      kern<<<vi->grid, TL::NT, smem, s>>>(P, ld, L->rowmax.p, vi->counts, vi->w.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N_pad,
+                                          vi->K, geom);
+      MSWB_LAUNCHED();
+      return;
+    }
+  }
+  if (em_chunked(L)) geom.stage_rows = 1;
+  auto kern = em_lin_pass_kernel<ST, TL, false>;
+  vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, L->N_pad / (TL::G * TL::R), vi->max_grid);
+  kern<<<vi->grid, TL::NT, 0, s>>>(P, ld, L->rowmax.p, vi->counts, vi->w.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N_pad, vi->K, geom);
+  MSWB_LAUNCHED();
+}
+
+template <class TL> void launch_sweep_a(mswb_vi *vi) {
+  mswb_lik *L = vi->lik;
+  cudaStream_t s = vi->ctx->stream;
+  const int ld = (int)L->Kp;
+  PipeGeom geom{0, 0, 0};
+  if constexpr (TL::TPR == 256) {
+    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 2, TL::TPR);
+    if (geom.stages) {
+      auto kern = rcg_sweep_a_kernel<TL, true>;
+      const size_t smem = pipe_smem_bytes(geom, 2);
+      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N, (uint64_t)geom.stage_rows), vi->max_grid);
+      kern<<<vi->grid, TL::NT, smem, s>>>(L->logl.p, L->gamma.p, ld, vi->dg.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N, vi->K, geom);
+      MSWB_LAUNCHED();
+      return;
+    }
+  }
+  auto kern = rcg_sweep_a_kernel<TL, false>;
+  vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, ceil_div(L->N, (uint64_t)TL::G * TL::R), vi->max_grid);
+  kern<<<vi->grid, TL::NT, 0, s>>>(L->logl.p, L->gamma.p, ld, vi->dg.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N, vi->K, geom);
+  MSWB_LAUNCHED();
+}
+
+template <class TL, int MODE, bool WRITE> void launch_sweep_b(mswb_vi *vi, int only_if_reset) {
+  mswb_lik *L = vi->lik;
+  cudaStream_t s = vi->ctx->stream;
+  const int ld = (int)L->Kp;
+  double *gam = WRITE || MODE == 0 ? L->gamma.p : nullptr, *stp = MODE == 0 ? L->step.p : nullptr;
+  PipeGeom geom{0, 0, 0};
+  if constexpr (TL::TPR == 256) {
+    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 3, TL::TPR);
+    if (geom.stages) {
+      auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, true>;
+      const size_t smem = pipe_smem_bytes(geom, 3);
+      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N, (uint64_t)geom.stage_rows), vi->max_grid);
+      kern<<<vi->grid, TL::NT, smem, s>>>(L->logl.p, gam, stp, ld, vi->dg.p, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N,
+                                          vi->K, only_if_reset, geom);
+      MSWB_LAUNCHED();
+      return;
+    }
+  }
+  auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, false>;
+  vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, ceil_div(L->N, (uint64_t)TL::G * TL::R), vi->max_grid);
+  kern<<<vi->grid, TL::NT, 0, s>>>(L->logl.p, gam, stp, ld, vi->dg.p, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N, vi->K,
+                                   only_if_reset, geom);
+  MSWB_LAUNCHED();
+}
 
 void em_iteration(mswb_vi *vi) {
   mswb_lik *L = vi->lik;
   cudaStream_t s = vi->ctx->stream;
   const int K = vi->K;
   PassTimer timer(vi);
-  // Measured on B200 (1e6 x 2000, profiles/): direct loads + register prefetch beat the staged (TMA) form
-  // for this sweep (6.5-6.7 vs 5.2 TB/s); MSWB_EM_TMA=1 / MSWB_EM_R select the alternatives for experiments.
-  int rsel = 0;
-  bool want_pipe = false;
-  if (const char *e = getenv("MSWB_EM_R")) rsel = atoi(e);
-  if (const char *e = getenv("MSWB_EM_TMA")) want_pipe = e[0] == '1';
   if (vi->linear && L->storage == MSWB_STORE_SPARSE) {
     const size_t smem = (size_t)2 * K * sizeof(double);
     MSWB_REQUIRE(smem <= 200 * 1024, "too many groups for the sparse EM pass (weights and accumulators live in shared memory)");
@@ -442,20 +479,11 @@ void em_iteration(mswb_vi *vi) {
                                                      vi->ctl.p, vi->partials.p, vi->pstride, L->N, K);
     MSWB_LAUNCHED();
   } else if (vi->linear && L->storage == MSWB_STORE_F32) {
-    if (rsel == 1) MSWB_TILE_DISPATCH(L->Kp32 / 4, 1, 1, 1, MSWB_LAUNCH_EM(float, L->P32.p, L->Kp32));
-    else if (rsel == 2) MSWB_TILE_DISPATCH(L->Kp32 / 4, 2, 2, 1, MSWB_LAUNCH_EM(float, L->P32.p, L->Kp32));
-    else if (rsel == 4) MSWB_TILE_DISPATCH(L->Kp32 / 4, 4, 4, 2, MSWB_LAUNCH_EM(float, L->P32.p, L->Kp32));
-    else MSWB_TILE_DISPATCH_EM(L->Kp32 / 4, MSWB_LAUNCH_EM(float, L->P32.p, L->Kp32));
+    MSWB_TILE_DISPATCH(L->Kp32 / 4, 8, launch_em<float, TL>(vi, L->P32.p, (int)L->Kp32));
   } else if (vi->linear) {
-    if (rsel == 1) MSWB_TILE_DISPATCH(L->Kp / 2, 1, 1, 1, MSWB_LAUNCH_EM(double, L->P64.p, L->Kp));
-    else if (rsel == 2) MSWB_TILE_DISPATCH(L->Kp / 2, 4, 2, 2, MSWB_LAUNCH_EM(double, L->P64.p, L->Kp));
-    else if (rsel == 4) MSWB_TILE_DISPATCH(L->Kp / 2, 4, 4, 2, MSWB_LAUNCH_EM(double, L->P64.p, L->Kp));
-    else MSWB_TILE_DISPATCH_EM(L->Kp / 2, MSWB_LAUNCH_EM(double, L->P64.p, L->Kp));
+    MSWB_TILE_DISPATCH(L->Kp / 2, 8, launch_em<double, TL>(vi, L->P64.p, (int)L->Kp));
   } else {
-    MSWB_TILE_DISPATCH_RCG(L->Kp / 2, 4, 2, 1,
-      MSWB_LAUNCH_SWEEP((rcg_sweep_b_kernel<TL, 1, false, true>), (rcg_sweep_b_kernel<TL, 1, false, false>), (size_t)L->Kp * 8, 3,
-                        L->logl.p, (double *)nullptr, (double *)nullptr, (int)L->Kp, vi->dg.p, vi->counts, vi->ctl.p,
-                        vi->partials.p, vi->pstride, L->N, K, 0));
+    MSWB_TILE_DISPATCH_RCG(L->Kp / 2, 4, launch_sweep_b<TL, 1, false>(vi, 0));
   }
   timer.stop();
   launch_finalize(vi, vi->linear ? K + 2 : K + 1, 0);
@@ -470,14 +498,10 @@ void rcg_iteration(mswb_vi *vi) {
   cudaStream_t s = ctx->stream;
   const int K = vi->K;
   const int slots = L->Kp / 2;
-  const int ld = (int)L->Kp;
-  const size_t row_bytes = (size_t)L->Kp * 8;
   // sweep A: gradient norm
   {
     PassTimer timer(vi);
-    MSWB_TILE_DISPATCH_RCG(slots, 4, 4, 2,
-      MSWB_LAUNCH_SWEEP((rcg_sweep_a_kernel<TL, true>), (rcg_sweep_a_kernel<TL, false>), row_bytes, 2,
-                        L->logl.p, L->gamma.p, ld, vi->dg.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N, K));
+    MSWB_TILE_DISPATCH_RCG(slots, 8, launch_sweep_a<TL>(vi));
     timer.stop();
   }
   if (ctx->world > 1) {
@@ -492,10 +516,7 @@ void rcg_iteration(mswb_vi *vi) {
   // sweep B: step, renormalise, N_k, bound
   {
     PassTimer timer(vi);
-    MSWB_TILE_DISPATCH_RCG(slots, 4, 2, 1,
-      MSWB_LAUNCH_SWEEP((rcg_sweep_b_kernel<TL, 0, true, true>), (rcg_sweep_b_kernel<TL, 0, true, false>), row_bytes, 3,
-                        L->logl.p, L->gamma.p, L->step.p, ld, vi->dg.p, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride,
-                        L->N, K, 0));
+    MSWB_TILE_DISPATCH_RCG(slots, 4, launch_sweep_b<TL, 0, true>(vi, 0));
     timer.stop();
   }
   launch_finalize(vi, K + 1, 0);
@@ -503,10 +524,7 @@ void rcg_iteration(mswb_vi *vi) {
   rcg_ctl_b_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, 0);
   MSWB_LAUNCHED();
   // restart sweep: runs only when the control block says so (device-side decision, no host round trip)
-  MSWB_TILE_DISPATCH_RCG(slots, 4, 2, 1,
-    MSWB_LAUNCH_SWEEP((rcg_sweep_b_kernel<TL, 1, true, true>), (rcg_sweep_b_kernel<TL, 1, true, false>), row_bytes, 3,
-                      L->logl.p, L->gamma.p, L->step.p, ld, vi->dg.p, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride,
-                      L->N, K, 1));
+  MSWB_TILE_DISPATCH_RCG(slots, 4, launch_sweep_b<TL, 1, true>(vi, 1));
   launch_finalize(vi, K + 1, 1);
   ctx->allreduce_sum(vi->red.p, K + 1);
   rcg_ctl_b_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, 1);

@@ -35,7 +35,7 @@ struct ViCtl {
 
 template <int TPR_, int KITER_, int R_> struct Tile {
   static constexpr int TPR = TPR_, KITER = KITER_, R = R_;
-  static constexpr int NT = TPR < 256 ? 256 : TPR;
+  static constexpr int NT = TPR < 256 ? (256 / TPR) * TPR : TPR;   // as many whole row groups as fit in 256 threads
   static constexpr int G = NT / TPR;
   static constexpr int NW = NT / 32;
   static constexpr int WPG = TPR / 32;   // warps per row group
