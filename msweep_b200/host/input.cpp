@@ -6,7 +6,11 @@
 
 #include <algorithm>
 #include <cstring>
+#include <fcntl.h>
 #include <fstream>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <sstream>
 #include <unordered_map>
 
@@ -57,16 +61,46 @@ struct Strand {
   std::vector<uint32_t> cols;
 };
 
-std::string slurp(const std::string &path) {
-  std::ifstream in(path, std::ios::binary);
-  if (!in.good()) throw std::runtime_error("Could not open " + path);
-  in.seekg(0, std::ios::end);
-  const std::streamoff n = in.tellg();
-  in.seekg(0);
-  std::string buf((size_t)n, '\0');
-  in.read(&buf[0], n);
-  return buf;
-}
+// Read-only view of a whole file: mmap when possible (no copy, pages faulted in by the tokeniser threads), else a
+// plain read into memory (pipes, /dev/stdin).
+struct FileView {
+  const char *data = nullptr;
+  size_t size = 0;
+  void *map = nullptr;
+  std::string fallback;
+  FileView() = default;
+  FileView(const FileView &) = delete;
+  FileView &operator=(const FileView &) = delete;
+  FileView(FileView &&o) noexcept { *this = std::move(o); }
+  FileView &operator=(FileView &&o) noexcept {
+    release();
+    map = o.map; size = o.size; fallback = std::move(o.fallback);
+    data = map ? (const char *)map : fallback.data();
+    o.map = nullptr; o.data = nullptr; o.size = 0;
+    return *this;
+  }
+  ~FileView() { release(); }
+  void release() { if (map) munmap(map, size); map = nullptr; data = nullptr; size = 0; std::string().swap(fallback); }
+  void open(const std::string &path) {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw std::runtime_error("Could not open " + path);
+    struct stat st;
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+      void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m != MAP_FAILED) {
+        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL | MADV_WILLNEED);
+        map = m; size = (size_t)st.st_size; data = (const char *)m;
+        ::close(fd);
+        return;
+      }
+    }
+    ::close(fd);
+    std::ifstream in(path, std::ios::binary);
+    if (!in.good()) throw std::runtime_error("Could not open " + path);
+    fallback.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+    data = fallback.data(); size = fallback.size();
+  }
+};
 
 // std::stoul semantics on a space-delimited token: optional leading whitespace, then digits; junk after
 // the digits is ignored; no digits at all is an error.
@@ -81,12 +115,14 @@ inline bool parse_token(const char *&p, const char *end, uint64_t &out) {
   return true;
 }
 
-Strand parse_strand(const std::string &buf, uint64_t T, int n_threads) {
-  if (buf.find(',') != std::string::npos && buf.find(',') < buf.find('\n'))
+Strand parse_strand(const FileView &buf, uint64_t T, int n_threads) {
+  const char *first_nl = (const char *)memchr(buf.data, '\n', buf.size);
+  const size_t first_len = first_nl ? (size_t)(first_nl - buf.data) : buf.size;
+  if (buf.size && memchr(buf.data, ',', first_len))
     throw std::runtime_error("compact (alignment-writer) pseudoalignments are not supported by this backend; "
                              "convert to Themisto plaintext");
-  const char *base = buf.data();
-  const size_t n = buf.size();
+  const char *base = buf.data;
+  const size_t n = buf.size;
   std::vector<size_t> cut(n_threads + 1, n);
   cut[0] = 0;
   for (int t = 1; t < n_threads; ++t) {
@@ -172,17 +208,12 @@ ReadTable read_themisto(const std::vector<std::string> &paths, uint64_t n_target
   ReadTable out;
   out.n_targets = n_targets;
   // the files are read from disk concurrently (one reader thread each); tokenising uses all threads per strand
-  std::vector<std::string> bufs(paths.size());
-  std::vector<std::string> read_err(paths.size());
-#pragma omp parallel for schedule(static, 1) num_threads((int)std::min<size_t>(paths.size(), (size_t)n_threads))
-  for (size_t i = 0; i < paths.size(); ++i) {
-    try { bufs[i] = slurp(paths[i]); } catch (const std::exception &e) { read_err[i] = e.what(); }
-  }
-  for (auto &e : read_err) if (!e.empty()) throw std::runtime_error(e);
+  std::vector<FileView> bufs(paths.size());
+  for (size_t i = 0; i < paths.size(); ++i) bufs[i].open(paths[i]);
   Strand acc;
   for (size_t i = 0; i < paths.size(); ++i) {
     Strand s = parse_strand(bufs[i], n_targets, n_threads);
-    std::string().swap(bufs[i]);
+    bufs[i].release();
     if (i == 0) { acc = std::move(s); continue; }
     const bool isect = merge_mode == "intersection";
     if (!isect && merge_mode != "union")
