@@ -501,7 +501,7 @@ void rcg_iteration(mswb_vi *vi) {
   // sweep A: gradient norm
   {
     PassTimer timer(vi);
-    MSWB_TILE_DISPATCH_RCG(slots, 8, launch_sweep_a<TL>(vi));
+    MSWB_TILE_DISPATCH_RCG(slots, 8, launch_sweep_a<TL>(vi));   // (one row per batch / three CTAs per SM measured the same: 5456 vs 5445 GB/s)
     timer.stop();
   }
   if (ctx->world > 1) {
@@ -529,20 +529,6 @@ void rcg_iteration(mswb_vi *vi) {
   ctx->allreduce_sum(vi->red.p, K + 1);
   rcg_ctl_b_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, 1);
   MSWB_LAUNCHED();
-}
-
-double device_sum(mswb_vi *vi, const double *c, size_t n) {
-  const int nb = 296;
-  vi->block_sums.ensure(nb + 1);
-  sum_kernel<<<nb, 256, 0, vi->ctx->stream>>>(c, n, vi->block_sums.p);
-  MSWB_LAUNCHED();
-  sum_blocks_kernel<<<1, 256, 0, vi->ctx->stream>>>(vi->block_sums.p, nb, vi->block_sums.p + nb);
-  MSWB_LAUNCHED();
-  vi->ctx->allreduce_sum(vi->block_sums.p + nb, 1);
-  double out = 0.0;
-  d2h(&out, vi->block_sums.p + nb, 1, vi->ctx->stream);
-  MSWB_CUDA(cudaStreamSynchronize(vi->ctx->stream));
-  return out;
 }
 
 void fill_stat(mswb_vi *vi, const ViCtl &c, mswb_vi_stat *stat) {

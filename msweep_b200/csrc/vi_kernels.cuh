@@ -490,7 +490,7 @@ __device__ __forceinline__ double rows_reduce(const double (&v)[TL::R], double *
 // newnorm = sum_jk q (d - <d>_j) d  with q = exp(gamma), <d>_j = sum_k q d.  Nothing is written: d is
 // recomputed by sweep B, which saves 16 B/element of traffic over storing it.
 template <class TL, bool PIPE>
-__global__ void __launch_bounds__(TL::NT, TL::R * TL::KITER <= 8 && TL::NT <= 256 ? 2 : 1)
+__global__ void __launch_bounds__(TL::NT, TL::NT > 256 ? 1 : (TL::R * TL::KITER <= 4 ? 3 : (TL::R * TL::KITER <= 8 ? 2 : 1)))
 rcg_sweep_a_kernel(const double *__restrict__ logl, const double *__restrict__ gamma, int ld,
                    const double *__restrict__ dgm1, const ViCtl *__restrict__ ctl, double *__restrict__ partials,
                    int pstride, unsigned long long N, int K, PipeGeom geom) {

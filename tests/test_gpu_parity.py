@@ -260,6 +260,25 @@ def test_bootstrap_counts_bit_exact(oracle, mswb, ctx):
     assert list(ph.sum(axis=1)) == [int(ec.count.sum())] * 2 and not np.array_equal(ph[0], ph[1])
 
 
+def test_philox_bootstrap_is_a_fair_multinomial(mswb, ctx):
+    """MSWB_RNG_PHILOX has no reference stream to match: check it statistically (counts within 6 sigma of n p, replicates
+    and seeds independent, totals exact)."""
+    wl = synth.generate(30000, 200, 10, n_present=3, n_templates=40, seed=18)
+    aln = mswb.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+    c = aln.export().count.astype(np.float64)
+    n, p = c.sum(), c / c.sum()
+    reps = lik.bootstrap_resample(123, 6, rng_mode=mswb.RNG_PHILOX).astype(np.float64)
+    assert np.all(reps.sum(axis=1) == n)
+    sigma = np.sqrt(n * p * (1 - p)) + 1e-9
+    assert np.max(np.abs(reps - n * p) / np.maximum(sigma, 1.0)) < 6.0
+    assert np.max(np.abs(reps.mean(axis=0) - n * p) / np.maximum(sigma / np.sqrt(6), 1.0)) < 6.0
+    other = lik.bootstrap_resample(124, 1, rng_mode=mswb.RNG_PHILOX)[0]
+    assert not np.array_equal(other, reps[0]) and not np.array_equal(reps[0], reps[1])
+    again = lik.bootstrap_resample(123, 6, rng_mode=mswb.RNG_PHILOX)
+    assert np.array_equal(again, reps.astype(np.uint32))               # counter-based: reproducible for a seed
+
+
 def test_bootstrap_run_matches_reference_loop(oracle, mswb, ctx):
     """src/mSWEEP.cpp:496-518: resample, re-estimate from a cold start, once per replicate."""
     wl = synth.generate(8000, 120, 6, n_present=3, n_templates=80, seed=12)
