@@ -248,6 +248,29 @@ def test_dense_entry_all_tile_shapes(oracle, mswb, ctx, K, N):
         assert abs(got.bound - ref.bound) <= ELBO_RTOL * abs(ref.bound)
 
 
+@pytest.mark.parametrize("algo,K,env", [("em", 1000, "MSWB_EM_TMA"), ("rcg", 1100, "MSWB_RCG_TMA"), ("rcg", 2000, "MSWB_RCG_TMA")])
+def test_tma_stage_ring_variant(oracle, mswb, ctx, algo, K, env):
+    """The cp.async.bulk + mbarrier stage ring is opt-in (it measured slower than direct loads) but it
+    is shipped: it has to give the same answers as the direct path and the oracle."""
+    rng = np.random.default_rng(K)
+    N = 700
+    logl = rng.normal(-6.0, 2.0, size=(K, N))
+    logl[rng.integers(0, K, size=N), np.arange(N)] = -0.3
+    lc = np.log(rng.integers(1, 30, size=N).astype(np.float64))
+    ref = oracle.vi_run(algo, logl, lc, tol=1e-7, max_iters=12)
+    lik = mswb.Likelihood.from_dense(ctx, logl, lc)
+    code = mswb.ALGO_RCG if algo == "rcg" else mswb.ALGO_EM
+    direct = lik.vi_run(code, tol=1e-7, max_iters=12)
+    os.environ[env] = "1"
+    try:
+        ring = lik.vi_run(code, tol=1e-7, max_iters=12)
+    finally:
+        del os.environ[env]
+    assert ring.iters == ref.iters == direct.iters
+    assert np.max(np.abs(ring.theta - ref.theta)) < THETA_TOL and abs(ring.bound - ref.bound) <= ELBO_RTOL * abs(ref.bound)
+    assert np.max(np.abs(ring.theta - direct.theta)) < 1e-13
+
+
 def test_bootstrap_counts_bit_exact(oracle, mswb, ctx):
     wl = synth.generate(20000, 200, 10, n_present=3, n_templates=300, seed=8)
     ec = oracle.ec_build_csr(wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
