@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-ecs", type=int, default=40_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp64 EM and RCG side series (N = 1 only)")
     return ap.parse_args()
 
 
@@ -246,6 +247,36 @@ def main():
                "what": "mswb_ec_build + mswb_lik_build + mswb_vi_run(K iterations) from host CSR buffers, theta back on the host"}
         lik.close(); aln.close()
 
+    # ---- side series on the same inputs (N = 1 only): the fp64 forms of the sweep, which cannot hold the full shard ----
+    extras = None
+    if world == 1 and not a.no_extras and a.storage == "f32" and a.algo == "em":
+        extras = {}
+        peak, _ = peak_gbs()
+        for name, st, al, n_sub, steps in (("em_f64", M.STORE_F64, M.ALGO_EM, min(n_local, 6_000_000), 20),
+                                           ("rcg_f64", M.STORE_F64, M.ALGO_RCG, min(n_local, 1_000_000), 10)):
+            rp = wl.row_ptr[:n_sub + 1]
+            with torch.cuda.stream(stream):
+                aln = M.Alignment(ctx, n_sub, wl.n_targets, rp, wl.targets[:int(rp[-1])])
+                lik = M.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=st)
+                sess = lik.vi_begin(al, tol=0.0 if al == M.ALGO_EM else -1e300, max_iters=10 ** 9, time_kernels=True)
+                sess.step(a.warmup)
+                s0 = sess.poll()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                sess.step(steps)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                s1 = sess.poll()
+                sess.finish()
+            ms = e0.elapsed_time(e1) / steps
+            kms = (s1.pass_ms_sum - s0.pass_ms_sum) / steps
+            gbs = s1.pass_bytes / (kms * 1e-3) / 1e9
+            extras[name] = {"ecs": lik.n_ecs, "n_groups": N_GROUPS, "steps": steps, "ms_per_step": ms, "vi_iters_per_s": 1e3 / ms,
+                            "pass_kernels_ms_per_step": kms, "achieved_gbs": gbs, "frac_of_measured_peak": gbs / peak,
+                            "frac_of_nominal_8TBs": gbs / 8000.0, "bytes_per_step": s1.pass_bytes}
+            lik.close(); aln.close()
+
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cb = cpu_baseline(wl, a, n_local, steps=3, warmup=1)
@@ -278,6 +309,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks,
+            "extras": extras,
             "check": {"theta_sum": theta_sum, "bound": res.bound},
         }
         print(json.dumps(line), flush=True)
