@@ -74,7 +74,7 @@ def build_host(force: bool = False) -> str | None:
     deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")] + [LIB]
     if force or _stale(CLI, deps):
         _run([HOST_CXX, "-std=c++17", "-O2", "-fopenmp", "-Wall", "-I", os.path.join(HERE, "..", "include"), "-o", CLI] + srcs +
-             ["-L", LIBDIR, "-lmsweep_b200", "-Wl,-rpath,$ORIGIN/../lib", "-lpthread", "-ldl"])
+             ["-L", LIBDIR, "-lmsweep_b200", "-Wl,-rpath,$ORIGIN/../lib", "-lpthread", "-ldl", "-lz"])
     return CLI
 
 

@@ -11,6 +11,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 #include <sstream>
 #include <unordered_map>
 
@@ -84,6 +85,24 @@ struct FileView {
   void open(const std::string &path) {
     const int fd = ::open(path.c_str(), O_RDONLY);
     if (fd < 0) throw std::runtime_error("Could not open " + path);
+    unsigned char magic[2] = {0, 0};
+    const bool gz = ::pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (gz) {   // gzip (the reference reads compressed alignments transparently through cxxio/bxzstr): inflate into memory
+      ::close(fd);
+      gzFile f = gzopen(path.c_str(), "rb");
+      if (!f) throw std::runtime_error("Could not open " + path);
+      gzbuffer(f, 1 << 20);
+      std::vector<char> chunk(1 << 22);
+      for (;;) {
+        const int got = gzread(f, chunk.data(), (unsigned)chunk.size());
+        if (got < 0) { gzclose(f); throw std::runtime_error("Could not decompress " + path); }
+        if (got == 0) break;
+        fallback.append(chunk.data(), (size_t)got);
+      }
+      gzclose(f);
+      data = fallback.data(); size = fallback.size();
+      return;
+    }
     struct stat st;
     if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
       void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);

@@ -4,7 +4,7 @@
 // Kept from the reference: the flags of the hot path with their defaults and meaning, the order of the
 // stages, the messages and exit codes of the failure sites, and the <prefix>_abundances.txt format
 // (src/PlainSample.cpp:32-71, src/BootstrapSample.cpp:75-130).  Not here (out of scope):
-// read binning, likelihood dumps, RATE, output compression, the compact alignment format.
+// read binning, likelihood dumps, RATE, output compression, the compact alignment format (gzip input is read).
 // New: --algorithm takes the B200 backends (rcgb200 | emb200; the reference's rcggpu / emgpu are accepted
 // as aliases and rcgcpu is refused: there is no CPU path in this binary), and --gpus N.
 #include "input.hpp"

@@ -135,3 +135,20 @@ def test_no_gpu_fails_loudly(tmp_path):
     a.write_text("0 1\n1 2\n")
     r = run("--themisto", str(a), "-i", str(g))
     assert r.returncode == 1 and "no CUDA device available" in r.stderr and r.stdout == ""
+
+
+def test_gzip_input_is_read_transparently(oracle, tmp_path):
+    """The reference opens its inputs through cxxio (bxzstr): a gzipped Themisto file works unchanged."""
+    import gzip
+    import shutil
+    wl = synth.generate(800, 60, 5, n_present=2, n_templates=20, seed=4)
+    paths = synth.write_themisto(str(tmp_path / "aln"), wl, paired=True)
+    gpath = str(tmp_path / "g.txt")
+    synth.write_grouping(gpath, wl)
+    gz = []
+    for p in paths:
+        with open(p, "rb") as fi, gzip.open(p + ".gz", "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+        gz.append(p + ".gz")
+    R, T, rp, tg = dump(tmp_path, gz, gpath)
+    assert np.array_equal(rp, wl.row_ptr) and np.array_equal(tg, wl.targets)
