@@ -7,7 +7,10 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <memory>
+#include <mutex>
+#include <tuple>
 
 using namespace mswb;
 
@@ -345,12 +348,25 @@ PipeGeom pipe_geometry(size_t row_bytes, int unit_rows, int nsrc, int tpr) {
 }
 size_t pipe_smem_bytes(const PipeGeom &g, int nsrc) { return (size_t)g.stages * nsrc * g.stage_pitch + (size_t)g.stages * 8; }
 
-// Persistent grid: as many CTAs as are resident at once (one per SM for the staged kernels).
+// Persistent grid: as many CTAs as are resident at once (one per SM for the staged kernels).  The occupancy query
+// is cached per (kernel, block size, shared memory): small problems run thousands of launches per second.
 template <class Kern> int persistent_grid(mswb_ctx *ctx, Kern kern, int nt, size_t smem, uint64_t n_batches, int max_grid) {
-  if (smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 1;
-  MSWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
-  if (per_sm < 1) per_sm = 1;
+  struct Key { const void *k; int nt; size_t smem; bool operator<(const Key &o) const { return std::tie(k, nt, smem) < std::tie(o.k, o.nt, o.smem); } };
+  static std::map<Key, int> cache;
+  static std::mutex mu;
+  int per_sm;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    const Key key{(const void *)kern, nt, smem};
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      if (smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int v = 1;
+      MSWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, nt, smem));
+      it = cache.emplace(key, v < 1 ? 1 : v).first;
+    }
+    per_sm = it->second;
+  }
   uint64_t g = (uint64_t)ctx->n_sms * per_sm;
   if (g > n_batches) g = n_batches;
   if (g > (uint64_t)max_grid) g = max_grid;
