@@ -54,3 +54,37 @@ def test_struct_layouts_match_header(mswb):
         subprocess.check_call(["/usr/bin/gcc", "-I", inc, src, "-o", exe])
         a, b = map(int, subprocess.check_output([exe]).split())
     assert C.sizeof(mswb.ViOpts) == a and C.sizeof(mswb.ViStat) == b
+
+
+def test_null_arguments_are_errors_not_crashes(mswb):
+    """Every entry validates its pointers before touching the device: a NULL handle is an error code + message."""
+    L = mswb.lib()
+    out = C.c_void_p()
+    a, b = C.c_uint64(), C.c_uint64()
+    calls = [
+        lambda: L.mswb_shard_range(None, C.c_uint64(10), C.byref(a), C.byref(b)),
+        lambda: L.mswb_ec_build(None, C.c_uint64(0), C.c_uint64(1), None, None, C.byref(out)),
+        lambda: L.mswb_ec_info(None, None, None, None, None),
+        lambda: L.mswb_lik_build(None, None, None, C.c_uint32(1), None, C.c_double(0.65), C.c_double(0.01), C.c_double(0.01), C.c_uint64(0), C.c_int(0), C.byref(out)),
+        lambda: L.mswb_lik_info(None, None, None, None, None, None),
+        lambda: L.mswb_lik_mask(None, None, None),
+        lambda: L.mswb_vi_begin(None, None, None, None, None, C.byref(out)),
+        lambda: L.mswb_vi_step(None, C.c_uint64(1)),
+        lambda: L.mswb_vi_poll(None, None),
+        lambda: L.mswb_vi_finish(None, None, None, None),
+        lambda: L.mswb_vi_posteriors(None, None, C.c_uint64(0), C.c_uint64(0), None),
+        lambda: L.mswb_bootstrap_resample(None, None, C.c_int32(1), C.c_uint64(0), C.c_int(0), C.c_uint64(1), None),
+        lambda: L.mswb_ctx_sync(None),
+    ]
+    for call in calls:
+        assert call() != 0
+        assert len(L.mswb_last_error()) > 0
+    L.mswb_ctx_destroy(None); L.mswb_aln_destroy(None); L.mswb_lik_destroy(None)      # destroying nothing is fine
+
+
+def test_pattern_hash_host_entry(mswb, oracle):
+    rng = np.random.default_rng(5)
+    assert mswb.pattern_hash([0]) == 0x517cc1b727220a95 and mswb.pattern_hash([]) == 0
+    for _ in range(50):
+        t = np.sort(rng.choice(60000, size=int(rng.integers(1, 90)), replace=False))
+        assert mswb.pattern_hash(t) == oracle.pattern_hash(t)
