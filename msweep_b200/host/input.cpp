@@ -5,6 +5,9 @@
 #include "input.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
 #include <fstream>
@@ -55,6 +58,17 @@ Grouping read_grouping(const std::string &path, char delimiter, size_t column) {
 }
 
 namespace {
+
+struct StageClock {
+  const bool on = getenv("MSWB_PARSE_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char *what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "  [parse] %-18s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 struct Strand {
   uint64_t n_lines = 0;
@@ -151,14 +165,22 @@ Strand parse_strand(const FileView &buf, uint64_t T, int n_threads) {
   }
   for (int t = 1; t <= n_threads; ++t) cut[t] = std::max(cut[t], cut[t - 1]);
 
-  std::vector<std::vector<uint64_t>> keys(n_threads);       // flat bit index read_id*T + target (mSWEEP_alignment.hpp:64)
+  StageClock clk;
+  // Per thread: the columns of its lines back to back, plus (read id, first column, count) per line.  A target id
+  // >= T belongs to a later row (flat bit index read_id*T + target, mSWEEP_alignment.hpp:64): those rare hits go to
+  // a side list as explicit (row, column) pairs.
+  struct Line { uint64_t read; uint64_t off; uint32_t n; };
+  std::vector<std::vector<uint32_t>> cols(n_threads);
+  std::vector<std::vector<Line>> line_tab(n_threads);
+  std::vector<std::vector<std::pair<uint64_t, uint32_t>>> spill(n_threads);
   std::vector<uint64_t> lines(n_threads, 0), bad_line(n_threads, 0);
   std::vector<std::string> bad_text(n_threads);
 #pragma omp parallel for schedule(static, 1) num_threads(n_threads)
   for (int t = 0; t < n_threads; ++t) {
     const char *p = base + cut[t], *end = base + cut[t + 1];
-    std::vector<uint64_t> &out = keys[t];
-    out.reserve((size_t)(end - p) / 5);
+    std::vector<uint32_t> &out = cols[t];
+    out.reserve((size_t)(end - p) / 4);
+    line_tab[t].reserve((size_t)(end - p) / 128 + 16);
     while (p < end) {
       const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
       if (!eol) eol = end;
@@ -166,17 +188,19 @@ Strand parse_strand(const FileView &buf, uint64_t T, int n_threads) {
       const char *q = p;
       uint64_t read_id = 0, tgt = 0;
       bool ok = parse_token(q, eol, read_id);
+      const uint64_t off = out.size();
       while (ok && q < eol) {
         ++q;                                       // the single ' ' delimiter
-        if (q > eol) break;
-        if (q == eol) { break; }                   // trailing delimiter: getline yields no further token
+        if (q >= eol) break;                       // trailing delimiter: getline yields no further token
         ok = parse_token(q, eol, tgt);
-        if (ok) out.push_back(read_id * T + tgt);
+        if (ok) { if (tgt < T) out.push_back((uint32_t)tgt); else spill[t].emplace_back(read_id + tgt / T, (uint32_t)(tgt % T)); }
       }
       if (!ok && !bad_line[t]) { bad_line[t] = lines[t]; bad_text[t].assign(p, eol); }
+      if (ok) line_tab[t].push_back(Line{read_id, off, (uint32_t)(out.size() - off)});
       p = eol + 1;
     }
   }
+  clk.lap("tokenise");
   uint64_t before = 0;
   for (int t = 0; t < n_threads; ++t) {
     if (bad_line[t]) throw std::runtime_error("File format not supported on line " + std::to_string(before + bad_line[t]) +
@@ -185,21 +209,29 @@ Strand parse_strand(const FileView &buf, uint64_t T, int n_threads) {
   }
   Strand s;
   s.n_lines = before;
-  // bucket by row (= flat / T); rows at or beyond the line count are never visited by collapse()
+  // bucket by row, one atomic per LINE (not per hit); rows at or beyond the line count are never visited by collapse()
   const uint64_t R = s.n_lines;
   s.row_ptr.assign(R + 1, 0);
-  // counting sort by row, all threads at once (relaxed atomics; the order inside a row is fixed by the sort below)
 #pragma omp parallel for schedule(static, 1) num_threads(n_threads)
-  for (int t = 0; t < n_threads; ++t)
-    for (uint64_t k : keys[t]) { const uint64_t r = k / T; if (r < R) __atomic_fetch_add(&s.row_ptr[r + 1], 1, __ATOMIC_RELAXED); }
+  for (int t = 0; t < n_threads; ++t) {
+    for (const Line &l : line_tab[t]) if (l.read < R && l.n) __atomic_fetch_add(&s.row_ptr[l.read + 1], (uint64_t)l.n, __ATOMIC_RELAXED);
+    for (const auto &rc : spill[t]) if (rc.first < R) __atomic_fetch_add(&s.row_ptr[rc.first + 1], 1, __ATOMIC_RELAXED);
+  }
   for (uint64_t r = 0; r < R; ++r) s.row_ptr[r + 1] += s.row_ptr[r];
   s.cols.resize(s.row_ptr[R]);
   std::vector<uint64_t> fill(s.row_ptr.begin(), s.row_ptr.end() - 1);
 #pragma omp parallel for schedule(static, 1) num_threads(n_threads)
   for (int t = 0; t < n_threads; ++t) {
-    for (uint64_t k : keys[t]) { const uint64_t r = k / T; if (r < R) s.cols[__atomic_fetch_add(&fill[r], 1, __ATOMIC_RELAXED)] = (uint32_t)(k % T); }
-    std::vector<uint64_t>().swap(keys[t]);
+    for (const Line &l : line_tab[t]) {
+      if (l.read >= R || !l.n) continue;
+      const uint64_t pos = __atomic_fetch_add(&fill[l.read], (uint64_t)l.n, __ATOMIC_RELAXED);
+      std::memcpy(s.cols.data() + pos, cols[t].data() + l.off, (size_t)l.n * sizeof(uint32_t));
+    }
+    for (const auto &rc : spill[t]) if (rc.first < R) s.cols[__atomic_fetch_add(&fill[rc.first], 1, __ATOMIC_RELAXED)] = rc.second;
+    std::vector<uint32_t>().swap(cols[t]);
+    std::vector<Line>().swap(line_tab[t]);
   }
+  clk.lap("bucket by row");
   // ascending + unique inside each row (a bit can only be set once)
   std::vector<uint64_t> len(R);
 #pragma omp parallel for schedule(static) num_threads(n_threads)
@@ -217,6 +249,7 @@ Strand parse_strand(const FileView &buf, uint64_t T, int n_threads) {
   }
   s.row_ptr[R] = w;
   s.cols.resize(w);
+  clk.lap("sort + compact");
   return s;
 }
 
