@@ -15,6 +15,7 @@
  *   rcg_optl -> rcgpar::em_torch   src/mSWEEP.cpp:200-203                   mswb_vi_run (MSWB_ALGO_EM)
  *   rcgpar::mixture_components[_torch]  src/mSWEEP.cpp:419-423, 512-516     theta output of mswb_vi_run
  *   Sample::store_probs / write_probs   src/Sample.cpp:63-85                mswb_vi_posteriors (on demand)
+ *   mGEMS::BinFromMatrix hand-off       src/mSWEEP.cpp:437-469              mswb_vi_assign / _fetch
  *   BootstrapSample::resample_counts    src/BootstrapSample.cpp:60-73       mswb_bootstrap_resample
  *   bootstrap loop                 src/mSWEEP.cpp:496-518                   mswb_bootstrap_run
  *
@@ -160,6 +161,17 @@ MSWB_API int  mswb_vi_finish(mswb_vi *vi, double *theta, double *N_k, mswb_vi_st
 /* log-posteriors of the LAST run for local classes [ec_begin, ec_end) (local indices), written as
  * K_kept x (ec_end-ec_begin) group-major — what rcg_optl returns, tile by tile. */
 MSWB_API int  mswb_vi_posteriors(mswb_ctx *ctx, mswb_lik *lik, uint64_t ec_begin, uint64_t ec_end, double *gamma);
+
+/* Thresholded class -> group assignment, the hand-off to read binning (src/mSWEEP.cpp:437-469 ->
+ * mGEMS::BinFromMatrix with Alignment::get_aligned_reads, include/mSWEEP_alignment.hpp:241; mGEMS v1.3.3 is
+ * off-tree, rule restated from its published description).  Local class j — all of its reads — joins the
+ * bin of kept group k when the LAST run's log-posterior gamma(k, j) >= log_threshold[k] (mGEMS: the log of
+ * the group's abundance; pass +inf to skip a group).  bin_ptr (K_kept + 1) receives the CSR offsets; the
+ * member read ids (ascending inside each bin) wait on the device for mswb_vi_assign_fetch, which copies
+ * bin_ptr[K_kept] ids out and releases them.  `aln` is the alignment the likelihood was built from. */
+MSWB_API int  mswb_vi_assign(mswb_ctx *ctx, mswb_lik *lik, const mswb_aln *aln, const double *log_threshold,
+                    uint64_t *bin_ptr);
+MSWB_API int  mswb_vi_assign_fetch(mswb_lik *lik, uint32_t *read_ids);
 
 /* ---- (3) bootstrap ------------------------------------------------------------------------- */
 enum { MSWB_RNG_LIBSTDCXX_EXACT = 0, MSWB_RNG_PHILOX = 1 };

@@ -249,6 +249,16 @@ class Likelihood:
         _check(lib().mswb_vi_posteriors(self.ctx.h, self.h, C.c_uint64(ec_begin), C.c_uint64(ec_end), _p(out)))
         return out
 
+    def assign(self, aln: "Alignment", log_threshold) -> list[np.ndarray]:
+        """mswb_vi_assign + _fetch: bins[k] = ascending read ids of the local classes with log-posterior >= log_threshold[k]."""
+        thr = np.ascontiguousarray(log_threshold, np.float64)
+        assert thr.shape == (self.n_groups,)
+        ptr = np.zeros(self.n_groups + 1, np.uint64)
+        _check(lib().mswb_vi_assign(self.ctx.h, self.h, aln.h, _p(thr), _p(ptr)))
+        flat = np.zeros(max(1, int(ptr[-1])), np.uint32)
+        _check(lib().mswb_vi_assign_fetch(self.h, _p(flat)))
+        return [flat[int(ptr[k]):int(ptr[k + 1])].copy() for k in range(self.n_groups)]
+
     # ---- bootstrap -----------------------------------------------------------------------------
     def bootstrap_resample(self, seed: int, n_replicates: int, bootstrap_count: int = 0, rng_mode=RNG_EXACT) -> np.ndarray:
         out = np.zeros((n_replicates, self.n_ecs_total), np.uint32)

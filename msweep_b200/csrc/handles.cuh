@@ -69,6 +69,10 @@ struct mswb_lik {
   mswb::DevBuf<double> step;     // [N x Kp] RCG search direction
   mswb::DevBuf<double> last_dg;  // [K] digamma(N_k) of the last EM pass (posteriors on demand)
   int last_algo = -1;
+
+  // result of the last mswb_vi_assign, waiting for mswb_vi_assign_fetch
+  mswb::DevBuf<uint32_t> assign_reads;
+  uint64_t assign_total = 0;
 };
 
 namespace mswb {
@@ -78,4 +82,6 @@ namespace mswb {
 void lik_ensure_logl(mswb_lik *L);     // fp64 log-likelihood (RCG, exports)
 void lik_ensure_linear(mswb_lik *L);   // P = exp(logl - rowmax) in the storage precision (EM)
 void lik_ensure_sparse(mswb_lik *L);   // hit lists (MSWB_STORE_SPARSE)
+// K x n tile of log-posteriors of the last run for classes [ec_begin, ec_begin + n), on the device (vi.cu)
+void posterior_tile_dev(mswb_ctx *ctx, mswb_lik *lik, uint64_t ec_begin, uint64_t n, double *tile);
 } // namespace mswb

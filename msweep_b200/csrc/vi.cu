@@ -240,6 +240,26 @@ __global__ void posterior_tile_kernel(int source, const double *__restrict__ gam
 
 } // namespace mswb
 
+namespace mswb {
+// K x n tile of log-posteriors for classes [ec_begin, ec_begin + n) of the shard, on the device (group-major).
+void posterior_tile_dev(mswb_ctx *ctx, mswb_lik *lik, uint64_t ec_begin, uint64_t n, double *tile) {
+  MSWB_REQUIRE(lik->last_algo >= 0, "no optimisation has been run on this likelihood");
+  MSWB_REQUIRE(lik->storage != MSWB_STORE_SPARSE, "posterior export is not available in sparse storage (build the likelihood dense)");
+  const int K = (int)lik->K;
+  const int blocks = (int)std::min<uint64_t>(ceil_div(n, 8), (uint64_t)ctx->n_sms * 8);
+  if (lik->last_algo == MSWB_ALGO_RCG) {
+    posterior_tile_kernel<double><<<blocks, 256, 0, ctx->stream>>>(0, lik->gamma.p, nullptr, (int)lik->Kp, nullptr, 0, nullptr, ec_begin, n, K, tile);
+  } else if (lik->logl.p) {
+    posterior_tile_kernel<double><<<blocks, 256, 0, ctx->stream>>>(1, nullptr, lik->logl.p, (int)lik->Kp, nullptr, 0, lik->last_dg.p, ec_begin, n, K, tile);
+  } else if (lik->storage == MSWB_STORE_F32) {
+    posterior_tile_kernel<float><<<blocks, 256, 0, ctx->stream>>>(2, nullptr, nullptr, 0, lik->P32.p, (int)lik->Kp32, lik->last_dg.p, ec_begin, n, K, tile);
+  } else {
+    posterior_tile_kernel<double><<<blocks, 256, 0, ctx->stream>>>(2, nullptr, nullptr, 0, lik->P64.p, (int)lik->Kp, lik->last_dg.p, ec_begin, n, K, tile);
+  }
+  MSWB_LAUNCHED();
+}
+} // namespace mswb
+
 // =====================================================================================================
 // session
 // =====================================================================================================
@@ -764,25 +784,12 @@ int mswb_vi_posteriors(mswb_ctx *ctx, mswb_lik *lik, uint64_t ec_begin, uint64_t
   return guarded([&] {
     MSWB_REQUIRE(ctx && lik && gamma, "NULL argument");
     MSWB_REQUIRE(ec_begin <= ec_end && ec_end <= lik->N, "class range out of bounds");
-    MSWB_REQUIRE(lik->last_algo >= 0, "no optimisation has been run on this likelihood");
     MSWB_CUDA(cudaSetDevice(ctx->device));
     const uint64_t n = ec_end - ec_begin;
     if (n == 0) return;
     DevBuf<double> tile;
     tile.alloc((size_t)n * lik->K);
-    const int K = (int)lik->K;
-    const int blocks = (int)std::min<uint64_t>(ceil_div(n, 8), (uint64_t)ctx->n_sms * 8);
-    MSWB_REQUIRE(lik->storage != MSWB_STORE_SPARSE, "posterior export is not available in sparse storage (build the likelihood dense)");
-    if (lik->last_algo == MSWB_ALGO_RCG) {
-      posterior_tile_kernel<double><<<blocks, 256, 0, ctx->stream>>>(0, lik->gamma.p, nullptr, (int)lik->Kp, nullptr, 0, nullptr, ec_begin, n, K, tile.p);
-    } else if (lik->logl.p) {
-      posterior_tile_kernel<double><<<blocks, 256, 0, ctx->stream>>>(1, nullptr, lik->logl.p, (int)lik->Kp, nullptr, 0, lik->last_dg.p, ec_begin, n, K, tile.p);
-    } else if (lik->storage == MSWB_STORE_F32) {
-      posterior_tile_kernel<float><<<blocks, 256, 0, ctx->stream>>>(2, nullptr, nullptr, 0, lik->P32.p, (int)lik->Kp32, lik->last_dg.p, ec_begin, n, K, tile.p);
-    } else {
-      posterior_tile_kernel<double><<<blocks, 256, 0, ctx->stream>>>(2, nullptr, nullptr, 0, lik->P64.p, (int)lik->Kp, lik->last_dg.p, ec_begin, n, K, tile.p);
-    }
-    MSWB_LAUNCHED();
+    mswb::posterior_tile_dev(ctx, lik, ec_begin, n, tile.p);
     d2h(gamma, tile.p, (size_t)n * lik->K, ctx->stream);
     MSWB_CUDA(cudaStreamSynchronize(ctx->stream));
   });

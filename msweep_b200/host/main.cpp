@@ -3,8 +3,9 @@
 //
 // Kept from the reference: the flags of the hot path with their defaults and meaning, the order of the
 // stages, the messages and exit codes of the failure sites, and the <prefix>_abundances.txt format
-// (src/PlainSample.cpp:32-71, src/BootstrapSample.cpp:75-130).  Not here (out of scope):
-// read binning, likelihood dumps, RATE, output compression, the compact alignment format (gzip input is read).
+// (src/PlainSample.cpp:32-71, src/BootstrapSample.cpp:75-130), --run-rate (src/Sample.cpp:99-151) and the
+// --bin-reads hand-off (src/mSWEEP.cpp:437-469).  Not here (out of scope): likelihood dumps,
+// output compression, the compact alignment format (gzip input is read).
 // New: --algorithm takes the B200 backends (rcgb200 | emb200; the reference's rcggpu / emgpu are accepted
 // as aliases and rcgcpu is refused: there is no CPU path in this binary), and --gpus N.
 #include "input.hpp"
@@ -48,13 +49,14 @@ struct Args {
   }
 };
 
-const std::set<std::string> kBool = {"verbose", "version", "cite", "help", "no-fit-model", "print-timings", "write-probs", "print-probs"};
+const std::set<std::string> kBool = {"verbose", "version", "cite", "help", "no-fit-model", "print-timings", "write-probs", "print-probs",
+                                     "bin-reads", "run-rate"};
 const std::set<std::string> kValued = {"themisto-1", "themisto-2", "themisto", "i", "o", "themisto-mode", "t", "max-iters", "tol",
                                        "algorithm", "emprecision", "iters", "seed", "bootstrap-count", "q", "e", "alphas",
-                                       "zero-inflation", "min-hits", "gpus", "rng", "dump-alignment", "storage"};
-const std::set<std::string> kUnsupported = {"bin-reads", "target-groups", "min-abundance",
-                                            "write-likelihood", "write-likelihood-bitseq", "compress", "compression-level",
-                                            "read-likelihood", "run-rate"};
+                                       "zero-inflation", "min-hits", "gpus", "rng", "dump-alignment", "storage",
+                                       "target-groups", "min-abundance"};
+const std::set<std::string> kUnsupported = {"write-likelihood", "write-likelihood-bitseq", "compress", "compression-level",
+                                            "read-likelihood"};
 
 Args parse(int argc, char **argv) {
   Args a;
@@ -108,6 +110,10 @@ const char *kHelp =
     "  --zero-inflation             likelihood of zero hits against a group (default: 0.01)\n"
     "  --min-hits                   only consider groups with at least this many aligned reads (default: 0)\n"
     "  --write-probs, --print-probs write / print the read-class to group probabilities (<prefix>_probs.tsv)\n"
+    "  --bin-reads                  assign reads to groups (mGEMS rule) and write <group>.bin files to the directory of -o\n"
+    "  --target-groups a[,b]        only bin these groups (default: all estimated groups)\n"
+    "  --min-abundance              only bin groups with at least this relative abundance\n"
+    "  --run-rate                   add the RATE and KLD columns to the abundances\n"
     "  --no-fit-model, --verbose, --version, --cite, --help, --print-timings\n";
 
 void cite() {
@@ -220,7 +226,8 @@ int main(int argc, char *argv[]) {
     const std::string store = args.str("storage", "dense");
     if (store == "sparse") {
       if (vi.algo != MSWB_ALGO_EM) throw std::runtime_error("--storage sparse needs --algorithm emb200 (RCG keeps dense per-class state)");
-      if (args.has("write-probs") || args.has("print-probs")) throw std::runtime_error("--storage sparse cannot export the probability matrix; use --storage dense");
+      if (args.has("write-probs") || args.has("print-probs") || args.has("bin-reads"))
+        throw std::runtime_error("--storage sparse cannot export the probability matrix; use --storage dense");
       storage = MSWB_STORE_SPARSE;
     } else if (store != "dense") throw std::runtime_error("Unknown --storage `" + store + "` (one of dense, sparse)");
     vi.tol = args.num<double>("tol", 1e-6);
@@ -278,9 +285,11 @@ int main(int argc, char *argv[]) {
 
   std::vector<std::vector<std::vector<double>>> results_by_gpu(n_gpus);   // [gpu][0 = plain, 1.. = replicates][group]
   const bool want_probs = args.has("write-probs") || args.has("print-probs");
+  const bool bin_reads = args.has("bin-reads");
+  std::vector<std::vector<std::vector<uint32_t>>> bins_by_gpu(n_gpus);   // [gpu][kept group][read id]: bins of the GPU's class shard
   std::vector<std::string> probs_rows(n_gpus);   // formatted rows of each GPU's class shard, in class order
   std::vector<std::string> errors(n_gpus);
-  std::vector<int> failed_stage(n_gpus, 0);   // 1 = EC/likelihood, 2 = estimation, 3 = bootstrap
+  std::vector<int> failed_stage(n_gpus, 0);   // 1 = EC/likelihood, 2 = estimation, 3 = bootstrap, 4 = binning
   std::vector<bool> mask;
   uint64_t n_ecs = 0, n_aligned = 0, n_reads = 0;
   double t_ec = 0, t_lik = 0, t_vi = 0, t_boot = 0;
@@ -332,6 +341,28 @@ int main(int argc, char *argv[]) {
         }
         probs_rows[gpu] = os.str();
       }
+      if (bin_reads && (!bootstrap || gpu == 0)) {
+        // src/mSWEEP.cpp:437-456: targets default to every estimated group; --min-abundance filters them
+        // (mGEMS::FilterTargetGroups); a class joins a target's bin when its posterior reaches the group's abundance.
+        failed_stage[gpu] = 4;
+        std::vector<std::string> est_names;
+        for (size_t g = 0; g < grouping.names.size(); ++g) if (my_mask[g]) est_names.push_back(grouping.names[g]);
+        std::set<std::string> targets(est_names.begin(), est_names.end());
+        if (args.has("target-groups")) {
+          targets.clear();
+          for (auto &name : split(args.str("target-groups", ""), ',')) {
+            if (std::find(est_names.begin(), est_names.end(), name) == est_names.end())
+              throw std::runtime_error("Target group " + name + " is not among the estimated groups.");
+            targets.insert(name);
+          }
+        }
+        const double min_abundance = args.num<double>("min-abundance", 0.0);
+        std::vector<double> thr(ll.get_rows(), std::numeric_limits<double>::infinity());
+        for (size_t k = 0; k < est_names.size(); ++k)
+          if (targets.count(est_names[k]) && !(args.has("min-abundance") && res[0][k] < min_abundance)) thr[k] = std::log(res[0][k]);
+        bins_by_gpu[gpu] = ll.assign(aln, thr);
+        failed_stage[gpu] = 2;
+      }
       if (bootstrap) {
         failed_stage[gpu] = 3;
         if (gpu == 0) log("Running estimation with " + std::to_string(iters) + " bootstrap iterations");
@@ -356,7 +387,8 @@ int main(int argc, char *argv[]) {
   for (int g = 0; g < n_gpus; ++g) {
     if (!failed_stage[g]) continue;
     const char *what = failed_stage[g] == 1 ? "Building the log-likelihood array failed:\n  "
-                     : failed_stage[g] == 2 ? "Estimating relative abundances failed:\n  " : "Bootstrap iteration failed:\n  ";
+                     : failed_stage[g] == 2 ? "Estimating relative abundances failed:\n  "
+                     : failed_stage[g] == 4 ? "Binning the reads failed:\n  " : "Bootstrap iteration failed:\n  ";
     std::cerr << what << errors[g] << "\nexiting\n";
     return 1;
   }
@@ -371,6 +403,31 @@ int main(int argc, char *argv[]) {
   // names of estimated vs pruned groups (src/mSWEEP.cpp:425-435)
   std::vector<std::string> estimated, zero;
   for (size_t g = 0; g < grouping.names.size(); ++g) (mask[g] ? estimated : zero).push_back(grouping.names[g]);
+
+  if (args.has("run-rate"))
+    std::cerr << "WARNING: --run-rate is an experimental option that has not been thoroughly tested and is subject to change.\n" << std::endl;
+
+  if (bin_reads) {
+    // one file per target group in the directory -o points to (src/OutfileDesignator.cpp:80-94), one read per line.
+    // Read ids are written 1-based, the numbering mGEMS extract counts fastq records in (mGEMS is off-tree: assumption).
+    std::string dir = ".";
+    const std::string o = args.str("o", "");
+    if (o.find('/') != std::string::npos) dir = o.substr(0, o.rfind('/'));
+    for (size_t k = 0; k < estimated.size(); ++k) {
+      std::vector<uint32_t> bin;
+      for (int g = 0; g < (bootstrap ? 1 : n_gpus); ++g) bin.insert(bin.end(), bins_by_gpu[g][k].begin(), bins_by_gpu[g][k].end());
+      if (n_gpus > 1 && !bootstrap) std::sort(bin.begin(), bin.end());
+      bool wanted = !args.has("target-groups");
+      if (!wanted) { const auto t = split(args.str("target-groups", ""), ','); wanted = std::find(t.begin(), t.end(), estimated[k]) != t.end(); }
+      if (wanted && args.has("min-abundance") && results[0][k] < args.num<double>("min-abundance", 0.0)) wanted = false;
+      if (!wanted) continue;
+      std::ofstream of(dir + '/' + estimated[k] + ".bin");
+      if (!of.good()) { std::cerr << "Writing the bin for target group " << estimated[k] << " failed:\n  Can't write to bin file.\nexiting\n"; return 1; }
+      std::string text;
+      for (uint32_t r : bin) { text += std::to_string((uint64_t)r + 1); text += '\n'; }
+      of << text;
+    }
+  }
 
   if (want_probs) {
     try {
@@ -393,10 +450,22 @@ int main(int argc, char *argv[]) {
 
   try {
     const std::string o = args.str("o", "");
-    if (o.empty()) {
-      write_abundances(std::cout, n_reads, n_aligned, estimated, zero, results, iters);
+    std::ofstream file;
+    if (!o.empty()) file.open(o + "_abundances.txt");                 // src/OutfileDesignator.cpp:104-114
+    std::ostream &of = o.empty() ? std::cout : file;
+    if (args.has("run-rate")) {
+      // src/mSWEEP.cpp:524-548: mean_theta, RATE and KLD per group; the bootstrap columns are not written in this mode
+      if (!of.good()) throw std::runtime_error("Can't write to abundances file.");
+      const auto kld = b200::dirichlet_kld(results[0], (double)n_aligned);
+      of << "#mSWEEP_version:" << '\t' << MSWEEP_BUILD_VERSION << '\n';
+      of << "#num_reads:" << '\t' << n_reads << '\n';
+      of << "#num_aligned:" << '\t' << n_aligned << '\n';
+      of << "#c_id" << '\t' << "mean_theta" << '\t' << "RATE" << '\t' << "KLD" << '\n';
+      for (size_t i = 0; i < estimated.size(); ++i)
+        of << estimated[i] << '\t' << results[0][i] << '\t' << kld.second[i] << '\t' << std::exp(kld.first[i]) << '\n';
+      for (size_t i = 0; i < zero.size(); ++i) of << zero[i] << '\t' << (double)0.0 << '\t' << (double)0.0 << '\t' << (double)0.0 << '\n';
+      of.flush();
     } else {
-      std::ofstream of(o + "_abundances.txt");                        // src/OutfileDesignator.cpp:104-114
       write_abundances(of, n_reads, n_aligned, estimated, zero, results, iters);
     }
   } catch (std::exception &e) {

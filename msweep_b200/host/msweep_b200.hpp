@@ -17,6 +17,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <cmath>
 #include <vector>
 
 namespace b200 {
@@ -116,6 +117,19 @@ public:
     return out;
   }
 
+  // Read bins, the job of mGEMS::BinFromMatrix at src/mSWEEP.cpp:437-469: bins[k] = ascending ids of the reads whose
+  // class has log-posterior >= log_threshold[k] for kept group k (+inf skips a group).  Classes of this rank's shard.
+  std::vector<std::vector<uint32_t>> assign(const Alignment &aln, const std::vector<double> &log_threshold) {
+    if (log_threshold.size() != n_groups_) throw std::runtime_error("thresholds must have one value per group");
+    std::vector<uint64_t> ptr(n_groups_ + 1);
+    check(mswb_vi_assign(ctx_->get(), h_, aln.get(), log_threshold.data(), ptr.data()));
+    std::vector<uint32_t> flat(ptr[n_groups_]);
+    check(mswb_vi_assign_fetch(h_, flat.data()));
+    std::vector<std::vector<uint32_t>> bins(n_groups_);
+    for (uint32_t k = 0; k < n_groups_; ++k) bins[k].assign(flat.begin() + ptr[k], flat.begin() + ptr[k + 1]);
+    return bins;
+  }
+
   // resample + re-estimate, src/mSWEEP.cpp:496-518; rows of replicates owned by other ranks stay NaN.
   std::vector<std::vector<double>> bootstrap(const std::vector<double> &alpha0, const ViOptions &o, uint64_t iters,
                                              uint64_t bootstrap_count, int32_t seed, int replica_rank = 0,
@@ -157,6 +171,37 @@ inline std::vector<double> rcg_optl(const Context &ctx, Likelihood &ll, const st
   if (log) *log << std::endl;
   if (report) *report = ViReport{st.bound, st.gnorm, st.iters, st.resets, st.converged != 0};
   return theta;
+}
+
+// The digamma series mSWEEP carries for RATE (src/Sample.cpp:87-97): recurrence up to 7, then the expansion in 1/(x - 1/2).
+inline double digamma(double x) {
+  double r = 0.0;
+  for (; x < 7.0; x += 1.0) r -= 1.0 / x;
+  x -= 0.5;
+  const double i2 = 1.0 / (x * x), i4 = i2 * i2;
+  return r + std::log(x) + i2 / 24.0 - 7.0 / 960.0 * i4 + 31.0 / 8064.0 * i4 * i2 - 127.0 / 30720.0 * i4 * i4;
+}
+
+// --run-rate (Sample::dirichlet_kld + Sample::get_rates, src/Sample.cpp:99-151).  The reference sums exp(gamma) once
+// per read of every class, i.e. alphas[k] = the expected read count of group k = theta[k] * counts_total, which
+// is what the optimiser already holds; the K x N matrix is not needed.  Returns {log_KLD, RATE}.
+inline std::pair<std::vector<double>, std::vector<double>> dirichlet_kld(const std::vector<double> &theta, double counts_total) {
+  const size_t K = theta.size();
+  std::vector<double> alphas(K), log_kld(K), rate(K);
+  double alpha0 = 0.0;
+  for (size_t k = 0; k < K; ++k) { alphas[k] = theta[k] * counts_total; alpha0 += alphas[k]; }
+  for (size_t k = 0; k < K; ++k) {
+    const double a = alphas[k];
+    const double kld = std::lgamma(alpha0) - std::lgamma(alpha0 - a) - std::lgamma(a) + a * (digamma(a) - digamma(alpha0));
+    log_kld[k] = std::log(std::max(kld, 1e-16));
+  }
+  double mx = 0.0;                                       // starts at 0, not at the first element (:138-142)
+  for (double v : log_kld) mx = mx > v ? mx : v;
+  double sum = 0.0;
+  for (double v : log_kld) sum += std::exp(v - mx);
+  const double lse = std::log(sum) + mx;
+  for (size_t k = 0; k < K; ++k) rate[k] = std::exp(log_kld[k] - lse);
+  return {log_kld, rate};
 }
 
 } // namespace b200

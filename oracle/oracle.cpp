@@ -487,6 +487,49 @@ std::vector<double> mixture_components(const double *gamma, uint32_t K, uint64_t
   return theta;
 }
 
+// Sample::dirichlet_kld (src/Sample.cpp:99-131): alphas[k] adds exp(gamma_kj) once per read of class j (the read
+// count recovered as round(exp(log c_j))), then the KL divergence of the Dirichlet marginal of group k, floored
+// at 1e-16.  Sample::get_rates (:133-151): softmax of the log-KLDs with the running maximum started at 0.
+RateResult dirichlet_kld(const double *gamma, uint32_t K, uint64_t N, const double *log_counts) {
+  std::vector<double> alphas(K, 0.0);
+  for (uint32_t k = 0; k < K; ++k)
+    for (uint64_t j = 0; j < N; ++j) {
+      const size_t reads_in_class = (size_t)std::round(std::exp(log_counts[j]));
+      for (size_t r = 0; r < reads_in_class; ++r) alphas[k] += std::exp(gamma[(size_t)k * N + j]);
+    }
+  double alpha0 = 0.0;
+  for (uint32_t k = 0; k < K; ++k) alpha0 += alphas[k];
+  RateResult out;
+  out.log_kld.resize(K);
+  out.rate.resize(K);
+  for (uint32_t k = 0; k < K; ++k) {
+    const double a = alphas[k];
+    const double kld = std::lgamma(alpha0) - std::lgamma(alpha0 - a) - std::lgamma(a) + a * (digamma_series(a) - digamma_series(alpha0));
+    out.log_kld[k] = std::log(std::max(kld, 1e-16));
+  }
+  double top = 0.0;
+  for (uint32_t k = 0; k < K; ++k) top = top > out.log_kld[k] ? top : out.log_kld[k];
+  double total = 0.0;
+  for (uint32_t k = 0; k < K; ++k) total += std::exp(out.log_kld[k] - top);
+  const double log_total = std::log(total) + top;
+  for (uint32_t k = 0; k < K; ++k) out.rate[k] = std::exp(out.log_kld[k] - log_total);
+  return out;
+}
+
+std::vector<std::vector<uint32_t>> bin_reads(const double *gamma, uint32_t K, uint64_t N, const std::vector<double> &theta,
+                                             const std::vector<uint8_t> &want, const std::vector<uint64_t> &read_ptr,
+                                             const std::vector<uint32_t> &read_ids) {
+  std::vector<std::vector<uint32_t>> bins(K);
+  for (uint32_t k = 0; k < K; ++k) {
+    if (!want[k]) continue;
+    const double threshold = std::log(theta[k]);
+    for (uint64_t j = 0; j < N; ++j)
+      if (gamma[(size_t)k * N + j] >= threshold) bins[k].insert(bins[k].end(), read_ids.begin() + read_ptr[j], read_ids.begin() + read_ptr[j + 1]);
+    std::sort(bins[k].begin(), bins[k].end());
+  }
+  return bins;
+}
+
 // =============================================================================================
 // Bootstrap
 // =============================================================================================

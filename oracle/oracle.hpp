@@ -119,6 +119,17 @@ ViResult em_optl(const double *logl, uint32_t K, uint64_t N, const double *log_c
 // rcgpar::mixture_components (called at src/mSWEEP.cpp:420)
 std::vector<double> mixture_components(const double *gamma, uint32_t K, uint64_t N, const double *log_counts);
 
+// --run-rate: Sample::dirichlet_kld and Sample::get_rates (src/Sample.cpp:99-151).  PINNED by the in-tree code.
+struct RateResult { std::vector<double> log_kld, rate; };
+RateResult dirichlet_kld(const double *gamma, uint32_t K, uint64_t N, const double *log_counts);
+
+// --bin-reads: the rule of mGEMS::BinFromMatrix as called at src/mSWEEP.cpp:437-469 (mGEMS v1.3.3 is OFF-TREE,
+// CMakeLists.txt:318-320: PARITY UNPINNED, restated from the published description).  bins[k] = ascending ids of
+// the reads whose class has gamma(k, j) >= log(theta[k]), for the groups with want[k] != 0.
+std::vector<std::vector<uint32_t>> bin_reads(const double *gamma, uint32_t K, uint64_t N, const std::vector<double> &theta,
+                                             const std::vector<uint8_t> &want, const std::vector<uint64_t> &read_ptr,
+                                             const std::vector<uint32_t> &read_ids);
+
 // ---------------------------------------------------------------------------------------------
 // Bootstrap (src/BootstrapSample.cpp:33-73, include/Sample.hpp:163-174)
 // ---------------------------------------------------------------------------------------------

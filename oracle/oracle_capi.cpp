@@ -156,6 +156,28 @@ int orc_vi_run(int algo, const double *logl, uint32_t K, uint64_t N, const doubl
   });
 }
 
+// ---- RATE and read bins -----------------------------------------------------------------------
+int orc_dirichlet_kld(const double *gamma, uint32_t K, uint64_t N, const double *log_counts, double *log_kld, double *rate) {
+  return guarded([&] {
+    const RateResult r = dirichlet_kld(gamma, K, N, log_counts);
+    copy_out(r.log_kld, log_kld);
+    copy_out(r.rate, rate);
+  });
+}
+// bin_ptr: K+1 offsets; read_ids: capacity entries (call with read_ids == NULL first to size it)
+int orc_bin_reads(const double *gamma, uint32_t K, uint64_t N, const double *theta, const uint8_t *want, const uint64_t *read_ptr,
+                  const uint32_t *read_ids_in, uint64_t *bin_ptr, uint32_t *read_ids) {
+  return guarded([&] {
+    const auto bins = bin_reads(gamma, K, N, std::vector<double>(theta, theta + K), std::vector<uint8_t>(want, want + K),
+                                std::vector<uint64_t>(read_ptr, read_ptr + N + 1), std::vector<uint32_t>(read_ids_in, read_ids_in + read_ptr[N]));
+    bin_ptr[0] = 0;
+    for (uint32_t k = 0; k < K; ++k) {
+      if (read_ids) std::memcpy(read_ids + bin_ptr[k], bins[k].data(), bins[k].size() * sizeof(uint32_t));
+      bin_ptr[k + 1] = bin_ptr[k] + bins[k].size();
+    }
+  });
+}
+
 // ---- bootstrap --------------------------------------------------------------------------------
 // Sequential replicates from ONE generator, as the reference's loop does (src/mSWEEP.cpp:498-502).
 int orc_bootstrap_resample(const uint64_t *ec_counts, uint64_t N, int32_t seed, uint64_t bootstrap_count,

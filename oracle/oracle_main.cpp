@@ -22,7 +22,7 @@ int main(int argc, char **argv) {
     std::string k = argv[i];
     k = k.substr(k[1] == '-' ? 2 : 1);
     if (k == "verbose") continue;
-    if (k == "write-probs") { kv[k] = "1"; continue; }
+    if (k == "write-probs" || k == "run-rate" || k == "bin-reads") { kv[k] = "1"; continue; }
     if (i + 1 >= argc) { std::cerr << "missing value for " << k << "\n"; return 1; }
     kv[k] = argv[++i];
   }
@@ -82,7 +82,33 @@ int main(int argc, char **argv) {
       }
       pf << std::endl;
     }
+    if (kv.count("bin-reads")) {   // src/mSWEEP.cpp:437-469, src/OutfileDesignator.cpp:80-94
+      std::vector<uint8_t> want(K, kv.count("target-groups") ? 0 : 1);
+      if (kv.count("target-groups")) {
+        std::stringstream ss(kv["target-groups"]); std::string name;
+        while (std::getline(ss, name, ',')) for (uint32_t k = 0; k < K; ++k) if (est[k] == name) want[k] = 1;
+      }
+      if (kv.count("min-abundance")) for (uint32_t k = 0; k < K; ++k) if (results[0][k] < std::stod(kv["min-abundance"])) want[k] = 0;
+      const auto bins = bin_reads(first_gamma.data(), K, ec.n_ecs(), results[0], want, ec.read_ptr, ec.read_ids);
+      std::string dir = ".";
+      const std::string o = get("o", "oracle");
+      if (o.find('/') != std::string::npos) dir = o.substr(0, o.rfind('/'));
+      for (uint32_t k = 0; k < K; ++k) {
+        if (!want[k]) continue;
+        std::ofstream bf(dir + '/' + est[k] + ".bin");
+        for (uint32_t r : bins[k]) bf << (uint64_t)r + 1 << '\n';   // 1-based, as mGEMS extract counts reads (assumption)
+      }
+    }
     std::ofstream of(get("o", "oracle") + "_abundances.txt");
+    if (kv.count("run-rate")) {    // src/mSWEEP.cpp:524-548
+      const RateResult rr = dirichlet_kld(first_gamma.data(), K, ec.n_ecs(), lik.log_counts.data());
+      of << "#mSWEEP_version:" << '\t' << get("version-string", "oracle") << '\n';
+      of << "#num_reads:" << '\t' << reads.n_reads << '\n';
+      of << "#num_aligned:" << '\t' << n_aligned << '\n';
+      of << "#c_id" << '\t' << "mean_theta" << '\t' << "RATE" << '\t' << "KLD" << '\n';
+      for (size_t i = 0; i < est.size(); ++i) of << est[i] << '\t' << results[0][i] << '\t' << rr.rate[i] << '\t' << std::exp(rr.log_kld[i]) << '\n';
+      for (size_t i = 0; i < zero.size(); ++i) of << zero[i] << '\t' << 0.0 << '\t' << 0.0 << '\t' << 0.0 << '\n';
+    } else
     write_abundances(of, get("version-string", "oracle"), reads.n_reads, n_aligned, est, zero, results, iters);
   } catch (const std::exception &e) {
     std::cerr << "oracle failed:\n  " << e.what() << "\nexiting\n";

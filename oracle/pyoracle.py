@@ -66,6 +66,8 @@ class _Lib:
         L.orc_vi_run.argtypes = [C.c_int, _f64p, C.c_uint32, C.c_uint64, _f64p, _f64p, C.c_double, C.c_uint64] + [C.c_void_p] * 8
         L.orc_bootstrap_resample.argtypes = [_u64p, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, _u32p]
         L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_dirichlet_kld.argtypes = [_f64p, C.c_uint32, C.c_uint64, _f64p, _f64p, _f64p]
+        L.orc_bin_reads.argtypes = [_f64p, C.c_uint32, C.c_uint64, _f64p, C.c_void_p, _u64p, _u32p, _u64p, C.c_void_p]
 
     def check(self, rc: int) -> None:
         if rc != 0:
@@ -275,6 +277,31 @@ def bootstrap_resample(ec_counts, seed: int, n_replicates: int, bootstrap_count:
     out = np.zeros((n_replicates, len(c)), np.uint32)
     L.check(L.lib.orc_bootstrap_resample(c, len(c), seed, bootstrap_count, n_replicates, out))
     return out
+
+
+def dirichlet_kld(gamma, log_counts):
+    """Sample::dirichlet_kld + get_rates (src/Sample.cpp:99-151): (log_KLD[K], RATE[K]) from the (K, N) log-posteriors."""
+    L = lib()
+    gamma = np.ascontiguousarray(gamma, np.float64)
+    K, N = gamma.shape
+    log_kld, rate = np.zeros(K), np.zeros(K)
+    L.check(L.lib.orc_dirichlet_kld(gamma, K, N, np.ascontiguousarray(log_counts, np.float64), log_kld, rate))
+    return log_kld, rate
+
+
+def bin_reads(gamma, theta, want, read_ptr, read_ids) -> list[np.ndarray]:
+    """The mGEMS rule (off-tree, unpinned): bins[k] = ascending read ids of the classes with gamma[k, j] >= log(theta[k])."""
+    L = lib()
+    gamma = np.ascontiguousarray(gamma, np.float64)
+    K, N = gamma.shape
+    theta = np.ascontiguousarray(theta, np.float64)
+    want = np.ascontiguousarray(want, np.uint8)
+    rp, ri = np.ascontiguousarray(read_ptr, np.uint64), np.ascontiguousarray(read_ids, np.uint32)
+    ptr = np.zeros(K + 1, np.uint64)
+    L.check(L.lib.orc_bin_reads(gamma, K, N, theta, want.ctypes.data, rp, ri, ptr, None))
+    out = np.zeros(max(1, int(ptr[K])), np.uint32)
+    L.check(L.lib.orc_bin_reads(gamma, K, N, theta, want.ctypes.data, rp, ri, ptr, out.ctypes.data))
+    return [out[int(ptr[k]):int(ptr[k + 1])].copy() for k in range(K)]
 
 
 def set_num_threads(n: int, fast: bool = False) -> None:

@@ -132,3 +132,50 @@ def test_write_probs(data):
         assert a.shape == b.shape and np.array_equal(a[:, 0], np.arange(len(a)))
         assert np.max(np.abs(a - b)) < 2e-6
         assert np.max(np.abs(a[:, 1:].sum(axis=1) - 1.0)) < 1e-4
+
+
+def test_run_rate_columns(data):
+    """--run-rate (src/Sample.cpp:99-151, src/mSWEEP.cpp:524-548): mean_theta, RATE and KLD per group."""
+    d, wl, paths, g = data
+    (h, names, vals), (h2, names2, vals2), err = run_both(d, paths, g, ["--run-rate"], "rate")
+    assert "WARNING: --run-rate is an experimental option" in err
+    assert h[-1] == h2[-1] == "#c_id\tmean_theta\tRATE\tKLD"
+    assert names == names2 and vals.shape == vals2.shape == (len(names), 3)
+    assert np.max(np.abs(vals[:, 0] - vals2[:, 0])) < 2e-6
+    assert np.allclose(vals[:, 1], vals2[:, 1], rtol=1e-4, atol=1e-9)      # RATE
+    assert np.allclose(vals[:, 2], vals2[:, 2], rtol=1e-4, atol=1e-12)     # KLD
+    assert abs(vals[:, 1].sum() - 1.0) < 1e-4
+
+
+def test_bin_reads_files(data):
+    """--bin-reads: one <group>.bin per target group next to the -o prefix, the reads of every class whose posterior
+    reaches the group's abundance."""
+    d, wl, paths, g = data
+    dirs = []
+    for who in ("ours", "ref"):
+        (d / f"bins_{who}").mkdir()
+        dirs.append(d / f"bins_{who}")
+    common = ["--themisto-1", paths[0], "--themisto-2", paths[1], "-i", g, "-t", "4", "--bin-reads", "--min-abundance", "0.01"]
+    r = subprocess.run([CLI, *common, "-o", str(dirs[0] / "x")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r2 = subprocess.run([ORACLE, *common, "-o", str(dirs[1] / "x")], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    ours = sorted(f for f in os.listdir(dirs[0]) if f.endswith(".bin"))
+    ref = sorted(f for f in os.listdir(dirs[1]) if f.endswith(".bin"))
+    assert ours == ref and 1 <= len(ours) < len(wl.group_names)       # --min-abundance drops the absent groups
+    total = moved = 0
+    for f in ours:
+        a = np.loadtxt(dirs[0] / f, dtype=np.int64, ndmin=1)
+        b = np.loadtxt(dirs[1] / f, dtype=np.int64, ndmin=1)
+        assert np.all(np.diff(a) > 0) and a.min() >= 1 and a.max() <= wl.n_reads
+        total += b.size
+        moved += np.setxor1d(a, b).size
+    assert total > 0 and moved <= 1e-3 * total
+    # --target-groups restricts the bins; an unknown group fails like the reference's binning stage does
+    (d / "bins_one").mkdir()
+    one = ours[0][:-4]
+    r = subprocess.run([CLI, *common[:-2], "--target-groups", one, "-o", str(d / "bins_one" / "x")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert sorted(f for f in os.listdir(d / "bins_one") if f.endswith(".bin")) == [one + ".bin"]
+    r = subprocess.run([CLI, *common[:-2], "--target-groups", "no_such_group", "-o", str(d / "bins_one" / "y")], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("Binning the reads failed:")

@@ -121,6 +121,39 @@ def test_em_posteriors(case, oracle, mswb, ctx):
     assert np.max(np.abs(np.exp(gam) - np.exp(ref.gamma))) < 1e-9
 
 
+@pytest.mark.parametrize("algo", ["rcg", "em"])
+def test_read_bins_follow_the_threshold_rule(case, oracle, mswb, ctx, algo):
+    """mswb_vi_assign (the --bin-reads hand-off): a class, with all of its reads, joins group k's bin when its
+    log-posterior reaches log(theta_k).  Same posteriors in, identical bins out (integers: bit-exact)."""
+    name, wl, ec, aln = case
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+    got = lik.vi_run(mswb.ALGO_RCG if algo == "rcg" else mswb.ALGO_EM, tol=1e-6, max_iters=30)
+    gam = lik.posteriors()
+    K = lik.n_groups
+    want = np.ones(K, np.uint8)
+    want[1::3] = 0
+    with np.errstate(divide="ignore"):
+        thr = np.where(want == 1, np.log(got.theta), np.inf)
+    bins = lik.assign(aln, thr)
+    ref = oracle.bin_reads(gam, got.theta, want, ec.read_ptr, ec.read_ids)
+    assert len(bins) == K
+    for k in range(K):
+        assert np.array_equal(bins[k], ref[k]), (name, k)
+        if not want[k]:
+            assert bins[k].size == 0
+    assert sum(b.size for b in bins) > 0
+    # no threshold at all: every group takes every aligned read, ascending
+    everything = lik.assign(aln, np.full(K, -np.inf))
+    all_reads = np.sort(ec.read_ids)
+    assert all(np.array_equal(b, all_reads) for b in everything)
+    # the oracle's own run of the optimiser lands on the same bins up to classes sitting on a threshold
+    ref_l = oracle.lik_build(ec, wl.group_of_target, wl.group_sizes)
+    r = oracle.vi_run(algo, ref_l.logl, ref_l.log_counts, tol=1e-6, max_iters=30, want_gamma=True)
+    own = oracle.bin_reads(r.gamma, r.theta, want, ec.read_ptr, ec.read_ids)
+    moved = sum(np.setxor1d(bins[k], own[k]).size for k in range(K))
+    assert moved <= 1e-3 * max(1, sum(b.size for b in own))
+
+
 def test_fp32_storage_tolerance(case, oracle, mswb, ctx):
     """fp32 storage of the linear-domain likelihood (EM only), fp64 accumulation across classes.
     Tolerance stated separately, as north_star asks.  Compared at a FIXED iteration count: the ELBO

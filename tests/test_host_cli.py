@@ -43,7 +43,7 @@ def test_version_help_cite():
     (["-i", "g"], "No pseudoalignment files"),
     (["-i", "g", "--themisto-1", "a"], "must be given together"),
     (["-i", "g", "--themisto", "a", "--bogus", "1"], "Unknown argument"),
-    (["-i", "g", "--themisto", "a", "--bin-reads"], "outside the scope"),
+    (["-i", "g", "--themisto", "a", "--write-likelihood"], "outside the scope"),
     (["-i", "g", "--themisto", "a", "-o", "/nonexistent_dir_xyz/out"], "does not seem to exist"),
 ])
 def test_argument_errors(argv, msg):
@@ -152,3 +152,28 @@ def test_gzip_input_is_read_transparently(oracle, tmp_path):
         gz.append(p + ".gz")
     R, T, rp, tg = dump(tmp_path, gz, gpath)
     assert np.array_equal(rp, wl.row_ptr) and np.array_equal(tg, wl.targets)
+
+
+def test_rate_helper_matches_the_oracle(oracle, tmp_path):
+    """b200::dirichlet_kld (host shim) takes theta and the aligned-read total; the oracle follows
+    Sample::dirichlet_kld (src/Sample.cpp:99-131) literally, read by read, from the K x N posteriors."""
+    rng = np.random.default_rng(5)
+    K, N = 7, 300
+    gamma = rng.normal(0, 3, size=(K, N))
+    gamma -= np.log(np.exp(gamma).sum(axis=0))
+    counts = rng.integers(1, 40, size=N).astype(np.float64)
+    theta = (np.exp(gamma) * counts).sum(axis=1) / counts.sum()
+    ref_log_kld, ref_rate = oracle.dirichlet_kld(gamma, np.log(counts))
+    src = tmp_path / "rate.cpp"
+    src.write_text('#include "msweep_b200.hpp"\n#include <cstdio>\n#include <cstdlib>\n'
+                   'int main(int argc, char **argv) { std::vector<double> t; for (int i = 2; i < argc; ++i) t.push_back(std::atof(argv[i]));\n'
+                   '  auto r = b200::dirichlet_kld(t, std::atof(argv[1]));\n'
+                   '  for (size_t k = 0; k < t.size(); ++k) std::printf("%.17g %.17g\\n", r.first[k], r.second[k]); return 0; }\n')
+    exe = tmp_path / "rate"
+    lib = os.path.join(ROOT, "msweep_b200", "lib")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "msweep_b200", "host"),
+                    str(src), "-o", str(exe), "-L", lib, "-lmsweep_b200", f"-Wl,-rpath,{lib}"], check=True)
+    out = subprocess.run([str(exe), repr(float(counts.sum())), *[repr(float(x)) for x in theta]], capture_output=True, text=True, check=True)
+    got = np.array([[float(x) for x in line.split()] for line in out.stdout.splitlines()])
+    assert np.allclose(got[:, 0], ref_log_kld, rtol=1e-9, atol=1e-9)
+    assert np.allclose(got[:, 1], ref_rate, rtol=1e-9)

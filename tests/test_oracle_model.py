@@ -94,6 +94,34 @@ def test_closed_forms(oracle):
     assert th[0] == pytest.approx(0.5, abs=1e-12) and th[1] == pytest.approx(0.5, abs=1e-12)
 
 
+def test_rate_against_the_closed_form(oracle):
+    """Sample::dirichlet_kld / get_rates (src/Sample.cpp:99-151) — in-tree formulas, checked against scipy."""
+    from scipy.special import digamma, gammaln
+    rng = np.random.default_rng(3)
+    K, N = 5, 200
+    gamma = rng.normal(0, 2, size=(K, N))
+    gamma -= np.log(np.exp(gamma).sum(axis=0))
+    counts = rng.integers(1, 30, size=N).astype(np.float64)
+    log_kld, rate = oracle.dirichlet_kld(gamma, np.log(counts))
+    a = (np.exp(gamma) * counts).sum(axis=1)
+    a0 = a.sum()
+    kld = np.maximum(gammaln(a0) - gammaln(a0 - a) - gammaln(a) + a * (digamma(a) - digamma(a0)), 1e-16)
+    assert np.allclose(log_kld, np.log(kld), rtol=1e-8, atol=1e-8)
+    top = max(0.0, np.log(kld).max())                      # the running maximum starts at 0 (:138-142)
+    expect = np.exp(np.log(kld) - (np.log(np.exp(np.log(kld) - top).sum()) + top))
+    assert np.allclose(rate, expect, rtol=1e-8)
+    assert rate.sum() == pytest.approx(1.0, abs=1e-12)
+
+
+def test_bin_rule(oracle):
+    gamma = np.log(np.array([[0.9, 0.5, 0.05], [0.1, 0.5, 0.95]]))
+    theta = np.array([0.5, 0.5])
+    read_ptr, read_ids = np.array([0, 2, 3, 6], np.uint64), np.array([4, 9, 1, 0, 2, 7], np.uint32)
+    bins = oracle.bin_reads(gamma, theta, np.ones(2, np.uint8), read_ptr, read_ids)
+    assert bins[0].tolist() == [1, 4, 9] and bins[1].tolist() == [0, 1, 2, 7]
+    assert oracle.bin_reads(gamma, theta, np.array([0, 1], np.uint8), read_ptr, read_ids)[0].size == 0
+
+
 def test_zero_count_classes_are_ignored(oracle, case):
     """Bootstrap feeds log(0) = -inf for classes that were not resampled (src/BootstrapSample.cpp:67-72)."""
     _, _, lik = case
