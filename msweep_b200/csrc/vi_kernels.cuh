@@ -830,18 +830,36 @@ em_sparse_pass_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__res
   __syncthreads();
   double z = 0.0, elbo = 0.0;
   int fault = 0;
+  // The pass is bound by load latency, not by bytes: everything a class needs is requested before anything is used
+  // (its five per-class values together, then its first HEAD hits together), and the hits stay in registers for the
+  // scatter.  Terms are added in hit order whatever the chunking, so the sums do not depend on HEAD.
+  constexpr int HEAD = 8;
   for (unsigned long long j = blockIdx.x * 256ull + threadIdx.x; j < N; j += (unsigned long long)gridDim.x * 256ull) {
     const double c = counts[j];
-    if (!(c > 0.0)) continue;
     const unsigned long long a = nz_ptr[j], b = nz_ptr[j + 1];
-    const double p0 = P0[j];
+    const double p0 = P0[j], m = rowmax[j];
+    if (!(c > 0.0)) continue;
+    const unsigned long long n = b - a;
+    double dp[HEAD];
+    uint32_t gr[HEAD];
+#pragma unroll
+    for (int u = 0; u < HEAD; ++u) {
+      const bool on = (unsigned long long)u < n;
+      dp[u] = on ? nz_dP[a + u] : 0.0;
+      gr[u] = on ? nz_grp[a + u] : 0u;
+    }
     double s = p0 * wsum;
-    for (unsigned long long e = a; e < b; ++e) s = fma(nz_dP[e], s_w[nz_grp[e]], s);
+#pragma unroll
+    for (int u = 0; u < HEAD; ++u) s = fma(dp[u], s_w[gr[u]], s);          // a padded slot adds dp = 0: s unchanged
+    for (unsigned long long e = a + HEAD; e < b; ++e) s = fma(nz_dP[e], s_w[nz_grp[e]], s);
     if (!(s > 0.0) || isinf(s)) { fault = 1; continue; }
     const double r = c / s;
     z = fma(r, p0, z);
-    elbo = fma(c, log(s) + rowmax[j], elbo);
-    for (unsigned long long e = a; e < b; ++e) atomicAdd(&s_acc[nz_grp[e]], r * nz_dP[e]);
+    elbo = fma(c, log(s) + m, elbo);
+#pragma unroll
+    for (int u = 0; u < HEAD; ++u)
+      if ((unsigned long long)u < n) atomicAdd(&s_acc[gr[u]], r * dp[u]);
+    for (unsigned long long e = a + HEAD; e < b; ++e) atomicAdd(&s_acc[nz_grp[e]], r * nz_dP[e]);
   }
   __syncthreads();
   double *out = partials + (unsigned long long)blockIdx.x * pstride;

@@ -134,10 +134,12 @@ def generate(n_reads: int, n_targets: int, n_groups: int, *, n_present: int = 5,
 
 def generate_ec_patterns(n_patterns: int, n_groups: int, group_size: int, *, n_present: int = 50, n_related: int = 3,
                          q_hit: float = 0.65, q_related: float = 0.15, seed: int = 20231019,
-                         chunk: int = 1 << 20, dup_factor: float = 0.0) -> Workload:
+                         chunk: int = 1 << 20, dup_factor: float = 0.0, n_pool: int = 0) -> Workload:
     """Bench-scale generator (config 3): every read gets its own freshly drawn pattern, block grouping
     (targets of lineage g are g*S .. g*S+S-1) so rows come out sorted without a sort.  With
-    dup_factor > 0 a fraction of reads repeat the previous read's pattern (EC counts > 1)."""
+    dup_factor > 0 a fraction of reads repeat the previous read's pattern (EC counts > 1).  With n_pool > 0 the
+    related lineages come from a fixed pool of that many lineages (the present ones included), so that every other
+    lineage receives no hit at all (config 4: most lineages empty, --min-hits 1 prunes them)."""
     rng = np.random.Generator(np.random.Philox(seed))
     K, S = n_groups, group_size
     T = K * S
@@ -149,12 +151,20 @@ def generate_ec_patterns(n_patterns: int, n_groups: int, group_size: int, *, n_p
     truth = np.zeros(K)
     truth[present] = theta
     L = 1 + n_related
+    pool = None
+    if n_pool > 0:
+        others = np.setdiff1d(np.arange(K), present)
+        extra = rng.choice(others, size=max(0, min(n_pool, K) - len(present)), replace=False)
+        pool = np.sort(np.concatenate([present, extra]))
     ptr_parts, tgt_parts, base = [np.zeros(1, np.uint64)], [], 0
     thr_src, thr_rel = int(q_hit * 256), int(q_related * 256)
     for c0 in range(0, n_patterns, chunk):
         n = min(chunk, n_patterns - c0)
         s = present[rng.choice(len(present), size=n, p=theta)]
-        rel = (s[:, None] + rng.integers(1, K, size=(n, n_related))) % K
+        if pool is None:
+            rel = (s[:, None] + rng.integers(1, K, size=(n, n_related))) % K
+        else:
+            rel = pool[rng.integers(0, len(pool), size=(n, n_related))]
         lin = np.sort(np.concatenate([s[:, None], rel], axis=1), axis=1)              # ascending lineages
         is_src = lin == s[:, None]
         thr = np.where(is_src, thr_src, thr_rel).astype(np.uint8)
