@@ -41,6 +41,13 @@ template <int TPR_, int KITER_, int R_> struct Tile {
   static constexpr int WPG = TPR / 32;   // warps per row group
 };
 
+// Barrier over the TPR threads of one row group: a named barrier (bar.sync id, count) when the CTA holds several groups,
+// so that groups drift apart instead of marching in CTA-wide lockstep; the CTA barrier when the row spans the CTA.
+template <class TL> __device__ __forceinline__ void group_sync(int g) {
+  if constexpr (TL::G == 1) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(TL::TPR) : "memory");   // ids 1..G (G <= 8), 0 is __syncthreads
+}
+
 // ---- TMA bulk copy + mbarrier (inline PTX; SASS: UBLKCP / SYNCS) -------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -122,31 +129,6 @@ template <int NSRC> struct RowPipe {
     }
   }
 };
-
-// ---- reductions along a row -------------------------------------------------------------------------
-// scratch: 2 * NW * R doubles.  Two buffers alternate so that one __syncthreads per call is enough.
-template <class TL, bool IS_MAX> __device__ __forceinline__ void group_reduce(double (&v)[TL::R], double *scratch, int &phase) {
-#pragma unroll
-  for (int r = 0; r < TL::R; ++r) v[r] = IS_MAX ? warp_max(v[r]) : warp_sum(v[r]);
-  if constexpr (TL::WPG > 1) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *buf = scratch + phase * (TL::NW * TL::R);
-    phase ^= 1;
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < TL::R; ++r) buf[warp * TL::R + r] = v[r];
-    }
-    __syncthreads();
-    const int w0 = (warp / TL::WPG) * TL::WPG;
-#pragma unroll
-    for (int r = 0; r < TL::R; ++r) {
-      double a = buf[w0 * TL::R + r];
-#pragma unroll
-      for (int w = 1; w < TL::WPG; ++w) a = IS_MAX ? fmax(a, buf[(w0 + w) * TL::R + r]) : a + buf[(w0 + w) * TL::R + r];
-      v[r] = a;
-    }
-  }
-}
 
 // ---- per-CTA partial vector: fold the G row groups in group order, then one coalesced store ---------
 // acc[i][v] belongs to column VEC*(t + TPR*i) + v.  comb: TPR*KITER*VEC doubles when G > 1.
@@ -311,7 +293,7 @@ em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ 
       double *buf = s_red + phase * (TL::NW * R);
       phase ^= 1;
       if ((lane & (R == 4 ? 7 : (R == 2 ? 15 : 31))) == 0) buf[warp * R + rid] = k;
-      __syncthreads();
+      group_sync<TL>(g);
       tot = 0.0;
       if (lane < R) {
         const int w0 = (warp / WPG) * WPG;
@@ -472,7 +454,7 @@ __device__ __forceinline__ double rows_reduce(const double (&v)[TL::R], double *
     double *buf = scratch + phase * (TL::NW * R);
     phase ^= 1;
     if ((lane & (R == 4 ? 7 : (R == 2 ? 15 : 31))) == 0) buf[warp * R + rid] = k;
-    __syncthreads();
+    group_sync<TL>(warp / TL::WPG);
     double tot = IS_MAX ? -INFINITY : 0.0;
     if (lane < R) {
       const int w0 = (warp / TL::WPG) * TL::WPG;
