@@ -18,6 +18,9 @@ for K, T, R in ((7, 70, 600), (300, 1500, 800), (1100, 3300, 300)):
             r = lik.vi_run(M.ALGO_RCG, max_iters=6, tol=-1e300)
             assert abs(r.theta.sum() - 1) < 1e-9
             lik.posteriors(0, min(50, lik.n_ecs)); lik.export_logl(); lik.export_hit_counts()
+            with np.errstate(divide="ignore"):
+                bins = lik.assign(aln, np.log(r.theta))
+            assert sum(b.size for b in bins) > 0
             lik.bootstrap_run(1, seed=3, max_iters=4)
             lik.bootstrap_resample(3, 1, rng_mode=M.RNG_PHILOX)
         lik.close()
