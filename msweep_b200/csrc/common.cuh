@@ -40,20 +40,31 @@ extern std::atomic<uint64_t> g_launches;
   do { ::mswb::g_launches.fetch_add(1, std::memory_order_relaxed); MSWB_CUDA(cudaGetLastError()); } while (0)
 
 // ---- device buffers ---------------------------------------------------------------------------
+// cudaMalloc / cudaFree of the multi-GB matrices cost tens to hundreds of milliseconds (page tables, an implicit device
+// synchronisation): blocks of 64 MB and more go back to a small per-device cache instead and are handed out again to
+// requests of a similar size.  The cache is emptied when an allocation fails and when a context is destroyed (ctx.cu).
+void *dev_alloc(size_t bytes, size_t *capacity);
+void dev_free(void *p, size_t capacity);
+void dev_cache_flush(int device);
+
 template <typename T> struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
+  size_t cap = 0;   // bytes of the underlying block
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-  DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = 0; o.cap = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = 0; o.cap = 0; }
+    return *this;
+  }
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p) dev_free(p, cap); p = nullptr; n = 0; cap = 0; }
   void alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    MSWB_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    p = static_cast<T *>(dev_alloc(count * sizeof(T), &cap));
     n = count;
   }
   void ensure(size_t count) { if (count > n) alloc(count); }

@@ -4,11 +4,76 @@
 #include <dlfcn.h>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace mswb {
 static thread_local std::string t_last_error;
 void set_last_error(const std::string &msg) { t_last_error = msg; }
 std::atomic<uint64_t> g_launches{0};
+
+// ---- device block cache (common.cuh) ------------------------------------------------------------
+namespace {
+struct CachedBlock { void *p; size_t bytes; int device; };
+std::mutex g_cache_mu;
+std::vector<CachedBlock> g_cache;
+constexpr size_t CACHE_MIN_BYTES = (size_t)64 << 20;
+} // namespace
+
+void dev_cache_flush(int device) {
+  std::vector<CachedBlock> mine;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    for (size_t i = 0; i < g_cache.size();)
+      if (g_cache[i].device == device) { mine.push_back(g_cache[i]); g_cache[i] = g_cache.back(); g_cache.pop_back(); } else ++i;
+  }
+  for (const CachedBlock &b : mine) cudaFree(b.p);
+}
+
+void *dev_alloc(size_t bytes, size_t *capacity) {
+  int device = 0;
+  cudaGetDevice(&device);
+  if (bytes >= CACHE_MIN_BYTES) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    size_t best = g_cache.size();
+    for (size_t i = 0; i < g_cache.size(); ++i) {
+      const CachedBlock &b = g_cache[i];
+      if (b.device == device && b.bytes >= bytes && b.bytes - bytes <= bytes / 4 && (best == g_cache.size() || b.bytes < g_cache[best].bytes)) best = i;
+    }
+    if (best != g_cache.size()) {
+      void *p = g_cache[best].p;
+      *capacity = g_cache[best].bytes;
+      g_cache[best] = g_cache.back();
+      g_cache.pop_back();
+      return p;
+    }
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    dev_cache_flush(device);
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Error(std::string("CUDA error: ") + cudaGetErrorString(e) + " (cudaMalloc of " + std::to_string(bytes) + " bytes)");
+  }
+  *capacity = bytes;
+  return p;
+}
+
+void dev_free(void *p, size_t capacity) {
+  if (!p) return;
+  if (capacity >= CACHE_MIN_BYTES) {
+    int device = 0;
+    cudaGetDevice(&device);
+    cudaDeviceSynchronize();   // what cudaFree would have done: nothing in flight still uses the block
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    g_cache.push_back(CachedBlock{p, capacity, device});
+    return;
+  }
+  cudaFree(p);
+}
 } // namespace mswb
 
 // ---- NCCL, resolved at run time -----------------------------------------------------------------
@@ -132,6 +197,7 @@ void mswb_ctx_destroy(mswb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->nccl_comm) nccl().CommDestroy(ctx->nccl_comm);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  mswb::dev_cache_flush(ctx->device);
   delete ctx;
 }
 
