@@ -332,6 +332,8 @@ template <int RMAX, int KITER> constexpr int rows_for() { return RMAX / KITER >=
 // Log-domain (RCG) sweeps: measured best with 256-thread CTAs throughout (16 warps per SM hide the longer
 // dependency chains of these sweeps better than the tighter 160/192/224-thread rows do: K = 1500 runs at 4.3 TB/s on
 // Tile<192,4,.> and K = 300 at 2.9 on Tile<96,2,.> against 5.3-5.5 on the power-of-two shapes), KITER = 4 from 65 pieces.
+// Three pieces per thread pay only for 641-768 pieces (K = 1500: 4.35 -> 4.6 TB/s); at 150-600 pieces they lose 3-7 %
+// to KITER = 4 although fewer lanes idle: these sweeps want bytes in flight per thread, not busy lanes.
 #define MSWB_TILE_DISPATCH_RCG(slots, RMAX, ...)                                             \
   do {                                                                                       \
     const int _s = (int)(slots);                                                             \
@@ -340,6 +342,7 @@ template <int RMAX, int KITER> constexpr int rows_for() { return RMAX / KITER >=
     else if (_s <= 128) MSWB_SHAPE_CASE(32, 4, RMAX, __VA_ARGS__)                            \
     else if (_s <= 256) MSWB_SHAPE_CASE(64, 4, RMAX, __VA_ARGS__)                            \
     else if (_s <= 512) MSWB_SHAPE_CASE(128, 4, RMAX, __VA_ARGS__)                           \
+    else if (_s > 640 && _s <= 768) MSWB_SHAPE_CASE(256, 3, RMAX, __VA_ARGS__)               \
     else if (_s <= 1024) MSWB_SHAPE_CASE(256, 4, RMAX, __VA_ARGS__)                          \
     else if (_s <= 2048) MSWB_SHAPE_CASE(256, 8, RMAX, __VA_ARGS__)                          \
     else if (_s <= 4096) MSWB_SHAPE_CASE(512, 8, RMAX, __VA_ARGS__)                          \

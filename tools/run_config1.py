@@ -32,6 +32,7 @@ r = subprocess.run([os.path.join(root, "msweep_b200", "bin", "mSWEEP_b200"), *co
 t_ours = time.time() - t0
 assert r.returncode == 0, r.stderr
 stages = json.loads(r.stderr.strip().splitlines()[-1])
+parse_stages = [l.strip() for l in r.stderr.splitlines() if l.startswith("  [parse]")]     # with MSWB_PARSE_TIMING=1
 
 
 def vals(p):
@@ -45,5 +46,5 @@ h1 = [l for l in open(os.path.join(d, "ours_abundances.txt")).read().splitlines(
 h2 = [l for l in open(os.path.join(d, "ref_abundances.txt")).read().splitlines() if l.startswith("#")][1:]
 print(json.dumps({"config": f"1: {a.reads} paired reads x 3000 refs / 50 lineages, rcg, -t {a.threads}, bootstrap iters {a.iters}",
                   "input_mb": sum(os.path.getsize(p) for p in paths) / 1e6, "generate_s": round(t_gen, 1),
-                  "oracle_cli_s": round(t_ref, 2), "msweep_b200_cli_s": round(t_ours, 2), "stages": stages,
+                  "oracle_cli_s": round(t_ref, 2), "msweep_b200_cli_s": round(t_ours, 2), "stages": stages, "parse_stages": parse_stages,
                   "same_header": h1 == h2, "same_names": n1 == n2, "max_abs_theta_diff": float(np.max(np.abs(v1 - v2)))}))
