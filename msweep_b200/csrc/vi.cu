@@ -317,13 +317,19 @@ template <int RMAX, int KITER> constexpr int rows_for() { return RMAX / KITER >=
     case 224: MSWB_SHAPE_CASE(224, KITERV, RMAX, __VA_ARGS__) break;                         \
     default: MSWB_SHAPE_CASE(256, KITERV, RMAX, __VA_ARGS__) break;                          \
   }
-#define MSWB_TILE_DISPATCH(slots, RMAX, ...)                                                 \
+// fp32 rows that would need 224 / 256 threads with more registers than two CTAs per SM allow (7-8 warps per SM: 0.75 of
+// the peak at K = 4000) take a 512-thread CTA with half the pieces instead (1.00).  fp64 keeps 256 x 8 (0.83 vs 0.74).
+#define MSWB_TILE_DISPATCH(slots, RMAX, IS_F32, ...)                                         \
   do {                                                                                       \
     const int _s = (int)(slots);                                                             \
     if (_s <= 32) MSWB_SHAPE_CASE(32, 1, RMAX, __VA_ARGS__)                                  \
     else if (_s <= 512) { const int _t = (int)round_up(ceil_div(_s, 2), 32); MSWB_SHAPE_BY_TPR(_t, 2, RMAX, __VA_ARGS__) }   \
-    else if (_s <= 1024) { const int _t = (int)round_up(ceil_div(_s, 4), 32); MSWB_SHAPE_BY_TPR_WIDE(_t, 4, RMAX, __VA_ARGS__) }  \
-    else if (_s <= 2048) { const int _t = (int)round_up(ceil_div(_s, 8), 32); MSWB_SHAPE_BY_TPR_WIDE(_t, 8, RMAX, __VA_ARGS__) }  \
+    else if (_s <= 1024) { const int _t = (int)round_up(ceil_div(_s, 4), 32);                \
+      if ((IS_F32) && _t >= 224) MSWB_SHAPE_CASE(512, 2, RMAX, __VA_ARGS__)                  \
+      else MSWB_SHAPE_BY_TPR_WIDE(_t, 4, RMAX, __VA_ARGS__) }                                \
+    else if (_s <= 2048) { const int _t = (int)round_up(ceil_div(_s, 8), 32);                \
+      if ((IS_F32) && _t >= 224) MSWB_SHAPE_CASE(512, 4, 4, __VA_ARGS__)                     \
+      else MSWB_SHAPE_BY_TPR_WIDE(_t, 8, RMAX, __VA_ARGS__) }                                \
     else if (_s <= 4096) MSWB_SHAPE_CASE(512, 8, RMAX, __VA_ARGS__)                          \
     else if (_s <= 8192) MSWB_SHAPE_CASE(1024, 8, RMAX, __VA_ARGS__)                         \
     else throw Error("too many groups for the compiled tile shapes (max 16384 in fp64)");   \
@@ -334,6 +340,8 @@ template <int RMAX, int KITER> constexpr int rows_for() { return RMAX / KITER >=
 // Tile<192,4,.> and K = 300 at 2.9 on Tile<96,2,.> against 5.3-5.5 on the power-of-two shapes), KITER = 4 from 65 pieces.
 // Three pieces per thread pay only for 641-768 pieces (K = 1500: 4.35 -> 4.6 TB/s); at 150-600 pieces they lose 3-7 %
 // to KITER = 4 although fewer lanes idle: these sweeps want bytes in flight per thread, not busy lanes.
+// 1025-2048 pieces (K = 2050..4096): 512 threads x 4 pieces (126 registers, 16 warps per SM); 256 threads x 8 pieces
+// needs ~250 registers in sweep B, i.e. 8 warps per SM, and ran at 0.40 instead of 0.60-0.77 of the peak.
 #define MSWB_TILE_DISPATCH_RCG(slots, RMAX, ...)                                             \
   do {                                                                                       \
     const int _s = (int)(slots);                                                             \
@@ -344,7 +352,7 @@ template <int RMAX, int KITER> constexpr int rows_for() { return RMAX / KITER >=
     else if (_s <= 512) MSWB_SHAPE_CASE(128, 4, RMAX, __VA_ARGS__)                           \
     else if (_s > 640 && _s <= 768) MSWB_SHAPE_CASE(256, 3, RMAX, __VA_ARGS__)               \
     else if (_s <= 1024) MSWB_SHAPE_CASE(256, 4, RMAX, __VA_ARGS__)                          \
-    else if (_s <= 2048) MSWB_SHAPE_CASE(256, 8, RMAX, __VA_ARGS__)                          \
+    else if (_s <= 2048) MSWB_SHAPE_CASE(512, 4, RMAX, __VA_ARGS__)                          \
     else if (_s <= 4096) MSWB_SHAPE_CASE(512, 8, RMAX, __VA_ARGS__)                          \
     else if (_s <= 8192) MSWB_SHAPE_CASE(1024, 8, RMAX, __VA_ARGS__)                         \
     else throw Error("too many groups for the compiled tile shapes (max 16384 in fp64)");   \
@@ -354,17 +362,17 @@ constexpr size_t SMEM_BUDGET = 200 * 1024;   // dynamic shared memory for the st
 
 // Stage ring geometry for a sweep that streams `nsrc` arrays with rows of `row_bytes`, consumed in
 // units of `unit_rows` (= G*R).  stages == 0: the rows are too long to stage, use the direct kernel.
-PipeGeom pipe_geometry(size_t row_bytes, int unit_rows, int nsrc, int tpr) {
+PipeGeom pipe_geometry(size_t row_bytes, int unit_rows, int nsrc, int tpr, size_t budget = SMEM_BUDGET, size_t target = 32 * 1024) {
   PipeGeom g{0, 0, 0};
   if (tpr > 256) return g;
   const size_t unit_bytes = (size_t)unit_rows * row_bytes;
-  size_t target = 32 * 1024;
   if (const char *e = getenv("MSWB_STAGE_KB")) target = (size_t)atoi(e) * 1024;
   const int units = (int)std::max<size_t>(1, target / unit_bytes);
   g.stage_rows = unit_rows * units;
   g.stage_pitch = (unsigned)round_up((size_t)g.stage_rows * row_bytes, 128);
   const size_t per_stage = (size_t)nsrc * g.stage_pitch + 8;
-  int stages = (int)std::min<size_t>(8, SMEM_BUDGET / per_stage);
+  if (const char *e = getenv("MSWB_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
+  int stages = (int)std::min<size_t>(8, budget / per_stage);
   if (const char *e = getenv("MSWB_STAGES")) stages = std::min(stages, atoi(e));
   g.stages = stages >= 2 ? stages : 0;
   return g;
@@ -419,10 +427,15 @@ void launch_finalize(mswb_vi *vi, int nvals, int only_if_reset) {
   MSWB_LAUNCHED();
 }
 
-// Measured on B200 (1e6 x 2000 fp64): the log-domain sweeps run at 5.5 TB/s with direct streaming loads and
-// two CTAs per SM, 4.0 TB/s through the TMA stage ring; the EM sweep 6.5-6.7 vs 5.2 TB/s.  The ring is therefore
-// opt-in (MSWB_RCG_TMA=1 / MSWB_EM_TMA=1) and compiled for the full-width (TPR = 256) shapes only.
-bool want_rcg_pipe() { const char *e = getenv("MSWB_RCG_TMA"); return e && e[0] == '1'; }
+// Measured on B200 (1e6 x 2000 fp64).  A ring that takes the whole SM (200 KB, one CTA) loses to direct streaming
+// loads with two CTAs per SM: log-domain sweeps 4.0-4.3 vs 5.5 TB/s, EM sweep 5.2 vs 6.5-6.7 TB/s — one CTA marches in
+// lockstep through load / exp / reduce phases.  A ring sized for TWO resident CTAs (100 KB, 16 KB stages: double
+// buffering for sweep B, three stages for sweep A) beats both for the exp-heavy sweeps: 5.65 TB/s at K = 2000, and
+// 5.3 vs 4.6 TB/s at K = 1500 — bytes in flight no longer depend on registers.  So: RCG sweeps of full-width rows
+// (TPR = 256, the only shapes the ring is compiled for) use the two-CTA ring by default (MSWB_RCG_TMA=0 turns it off);
+// the EM sweep, already at the copy peak with direct loads, keeps them (MSWB_EM_TMA=1 selects the one-CTA ring).
+constexpr size_t RCG_RING_BYTES = 100 * 1024, RCG_STAGE_BYTES = 16 * 1024;
+bool want_rcg_pipe() { const char *e = getenv("MSWB_RCG_TMA"); return !(e && e[0] == '0'); }
 bool want_em_pipe() { const char *e = getenv("MSWB_EM_TMA"); return e && e[0] == '1'; }
 
 // Batch -> CTA mapping of the direct EM sweep (see the kernel): chunked once the matrix is large.
@@ -461,7 +474,7 @@ template <class TL> void launch_sweep_a(mswb_vi *vi) {
   const int ld = (int)L->Kp;
   PipeGeom geom{0, 0, 0};
   if constexpr (TL::TPR == 256) {
-    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 2, TL::TPR);
+    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 2, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
     if (geom.stages) {
       auto kern = rcg_sweep_a_kernel<TL, true>;
       const size_t smem = pipe_smem_bytes(geom, 2);
@@ -484,7 +497,7 @@ template <class TL, int MODE, bool WRITE> void launch_sweep_b(mswb_vi *vi, int o
   double *gam = WRITE || MODE == 0 ? L->gamma.p : nullptr, *stp = MODE == 0 ? L->step.p : nullptr;
   PipeGeom geom{0, 0, 0};
   if constexpr (TL::TPR == 256) {
-    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 3, TL::TPR);
+    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 3, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
     if (geom.stages) {
       auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, true>;
       const size_t smem = pipe_smem_bytes(geom, 3);
@@ -518,9 +531,9 @@ void em_iteration(mswb_vi *vi) {
                                                      vi->ctl.p, vi->partials.p, vi->pstride, L->N, K);
     MSWB_LAUNCHED();
   } else if (vi->linear && L->storage == MSWB_STORE_F32) {
-    MSWB_TILE_DISPATCH(L->Kp32 / 4, 8, launch_em<float, TL>(vi, L->P32.p, (int)L->Kp32));
+    MSWB_TILE_DISPATCH(L->Kp32 / 4, 8, true, launch_em<float, TL>(vi, L->P32.p, (int)L->Kp32));
   } else if (vi->linear) {
-    MSWB_TILE_DISPATCH(L->Kp / 2, 8, launch_em<double, TL>(vi, L->P64.p, (int)L->Kp));
+    MSWB_TILE_DISPATCH(L->Kp / 2, 8, false, launch_em<double, TL>(vi, L->P64.p, (int)L->Kp));
   } else {
     MSWB_TILE_DISPATCH_RCG(L->Kp / 2, 4, launch_sweep_b<TL, 1, false>(vi, 0));
   }

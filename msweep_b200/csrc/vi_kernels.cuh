@@ -226,7 +226,10 @@ template <int R> __device__ __forceinline__ int holder_lane(int r) { return R ==
 template <typename ST, class TL> constexpr int em_min_blocks() {
   constexpr int VEC = 16 / (int)sizeof(ST);
   constexpr int est = 8 * TL::R * TL::KITER + 2 * TL::KITER * VEC + TL::KITER * VEC * ((int)sizeof(ST) / 4);
-  return est <= 100 && TL::NT <= 256 ? 2 : 1;
+  if (TL::NT > 256) return 1;
+  if (est <= 100) return 2;
+  // 160 / 192-thread CTAs still fit twice (204 / 170 registers each) — except fp32 with eight pieces, which needs ~240
+  return TL::NT <= 192 && (TL::KITER <= 4 || sizeof(ST) == 8) ? 2 : 1;
 }
 
 template <typename ST, class TL, bool PIPE>

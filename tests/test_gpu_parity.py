@@ -281,10 +281,12 @@ def test_dense_entry_all_tile_shapes(oracle, mswb, ctx, K, N):
         assert abs(got.bound - ref.bound) <= ELBO_RTOL * abs(ref.bound)
 
 
-@pytest.mark.parametrize("algo,K,env", [("em", 1000, "MSWB_EM_TMA"), ("rcg", 1100, "MSWB_RCG_TMA"), ("rcg", 2000, "MSWB_RCG_TMA")])
-def test_tma_stage_ring_variant(oracle, mswb, ctx, algo, K, env):
-    """The cp.async.bulk + mbarrier stage ring is opt-in (it measured slower than direct loads) but it
-    is shipped: it has to give the same answers as the direct path and the oracle."""
+@pytest.mark.parametrize("algo,K,env,value", [("em", 1000, "MSWB_EM_TMA", "1"), ("rcg", 1100, "MSWB_RCG_TMA", "0"),
+                                              ("rcg", 1500, "MSWB_RCG_TMA", "0"), ("rcg", 2000, "MSWB_RCG_TMA", "0")])
+def test_tma_stage_ring_variant(oracle, mswb, ctx, algo, K, env, value):
+    """Two ways of feeding the SM are shipped: direct streaming loads and the cp.async.bulk + mbarrier
+    stage ring.  Full-width RCG sweeps default to the ring, the EM sweep to direct loads; the environment switch selects
+    the other one, which has to give the same answers as the default path and the oracle."""
     rng = np.random.default_rng(K)
     N = 700
     logl = rng.normal(-6.0, 2.0, size=(K, N))
@@ -293,15 +295,16 @@ def test_tma_stage_ring_variant(oracle, mswb, ctx, algo, K, env):
     ref = oracle.vi_run(algo, logl, lc, tol=1e-7, max_iters=12)
     lik = mswb.Likelihood.from_dense(ctx, logl, lc)
     code = mswb.ALGO_RCG if algo == "rcg" else mswb.ALGO_EM
-    direct = lik.vi_run(code, tol=1e-7, max_iters=12)
-    os.environ[env] = "1"
+    default = lik.vi_run(code, tol=1e-7, max_iters=12)
+    os.environ[env] = value
     try:
-        ring = lik.vi_run(code, tol=1e-7, max_iters=12)
+        other = lik.vi_run(code, tol=1e-7, max_iters=12)
     finally:
         del os.environ[env]
-    assert ring.iters == ref.iters == direct.iters
-    assert np.max(np.abs(ring.theta - ref.theta)) < THETA_TOL and abs(ring.bound - ref.bound) <= ELBO_RTOL * abs(ref.bound)
-    assert np.max(np.abs(ring.theta - direct.theta)) < 1e-13
+    assert other.iters == ref.iters == default.iters
+    for got in (default, other):
+        assert np.max(np.abs(got.theta - ref.theta)) < THETA_TOL and abs(got.bound - ref.bound) <= ELBO_RTOL * abs(ref.bound)
+    assert np.max(np.abs(other.theta - default.theta)) < 1e-13
 
 
 def test_bootstrap_counts_bit_exact(oracle, mswb, ctx):
