@@ -435,7 +435,13 @@ void launch_finalize(mswb_vi *vi, int nvals, int only_if_reset) {
 // (TPR = 256, the only shapes the ring is compiled for) use the two-CTA ring by default (MSWB_RCG_TMA=0 turns it off);
 // the EM sweep, already at the copy peak with direct loads, keeps them (MSWB_EM_TMA=1 selects the one-CTA ring).
 constexpr size_t RCG_RING_BYTES = 100 * 1024, RCG_STAGE_BYTES = 16 * 1024;
-bool want_rcg_pipe() { const char *e = getenv("MSWB_RCG_TMA"); return !(e && e[0] == '0'); }
+bool want_rcg_pipe(int tpr = 256) {
+  const char *e = getenv("MSWB_RCG_TMA");
+  if (e && e[0] == '0') return false;
+  if (tpr == 256) return true;
+  const char *m = getenv("MSWB_RCG_TMA_MIN_TPR");
+  return m && tpr >= atoi(m);
+}
 bool want_em_pipe() { const char *e = getenv("MSWB_EM_TMA"); return e && e[0] == '1'; }
 
 // Batch -> CTA mapping of the direct EM sweep (see the kernel): chunked once the matrix is large.
@@ -473,8 +479,8 @@ template <class TL> void launch_sweep_a(mswb_vi *vi) {
   cudaStream_t s = vi->ctx->stream;
   const int ld = (int)L->Kp;
   PipeGeom geom{0, 0, 0};
-  if constexpr (TL::TPR == 256) {
-    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 2, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
+  if constexpr (TL::TPR >= 64 && TL::NT <= 256) {
+    if (want_rcg_pipe(TL::TPR)) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 2, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
     if (geom.stages) {
       auto kern = rcg_sweep_a_kernel<TL, true>;
       const size_t smem = pipe_smem_bytes(geom, 2);
@@ -496,8 +502,8 @@ template <class TL, int MODE, bool WRITE> void launch_sweep_b(mswb_vi *vi, int o
   const int ld = (int)L->Kp;
   double *gam = WRITE || MODE == 0 ? L->gamma.p : nullptr, *stp = MODE == 0 ? L->step.p : nullptr;
   PipeGeom geom{0, 0, 0};
-  if constexpr (TL::TPR == 256) {
-    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 3, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
+  if constexpr (TL::TPR >= 64 && TL::NT <= 256) {
+    if (want_rcg_pipe(TL::TPR)) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 3, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
     if (geom.stages) {
       auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, true>;
       const size_t smem = pipe_smem_bytes(geom, 3);
