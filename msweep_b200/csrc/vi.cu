@@ -430,18 +430,14 @@ void launch_finalize(mswb_vi *vi, int nvals, int only_if_reset) {
 // Measured on B200 (1e6 x 2000 fp64).  A ring that takes the whole SM (200 KB, one CTA) loses to direct streaming
 // loads with two CTAs per SM: log-domain sweeps 4.0-4.3 vs 5.5 TB/s, EM sweep 5.2 vs 6.5-6.7 TB/s — one CTA marches in
 // lockstep through load / exp / reduce phases.  A ring sized for TWO resident CTAs (100 KB, 16 KB stages: double
-// buffering for sweep B, three stages for sweep A) beats both for the exp-heavy sweeps: 5.65 TB/s at K = 2000, and
-// 5.3 vs 4.6 TB/s at K = 1500 — bytes in flight no longer depend on registers.  So: RCG sweeps of full-width rows
-// (TPR = 256, the only shapes the ring is compiled for) use the two-CTA ring by default (MSWB_RCG_TMA=0 turns it off);
-// the EM sweep, already at the copy peak with direct loads, keeps them (MSWB_EM_TMA=1 selects the one-CTA ring).
+// buffering for sweep B, three stages for sweep A) beats both for the exp-heavy sweeps — bytes in flight no longer
+// depend on registers: K = 2000 5.68 vs 5.46 TB/s, K = 1500 5.4 vs 4.6, K = 1000 5.75 vs 5.44, K = 700 4.68 vs 4.39,
+// K = 420 5.16 vs 4.93.  One-warp rows (TPR = 32, K <= 256) gain nothing consistent (K = 100 +6 %, K = 256 -4 %) and
+// keep direct loads.  So: RCG sweeps with rows of 64-256 threads use the two-CTA ring by default (MSWB_RCG_TMA=0 turns
+// it off); the EM sweep, already at the copy peak with direct loads, keeps them (MSWB_EM_TMA=1 selects the one-CTA ring,
+// compiled for TPR = 256 only).
 constexpr size_t RCG_RING_BYTES = 100 * 1024, RCG_STAGE_BYTES = 16 * 1024;
-bool want_rcg_pipe(int tpr = 256) {
-  const char *e = getenv("MSWB_RCG_TMA");
-  if (e && e[0] == '0') return false;
-  if (tpr == 256) return true;
-  const char *m = getenv("MSWB_RCG_TMA_MIN_TPR");
-  return m && tpr >= atoi(m);
-}
+bool want_rcg_pipe() { const char *e = getenv("MSWB_RCG_TMA"); return !(e && e[0] == '0'); }
 bool want_em_pipe() { const char *e = getenv("MSWB_EM_TMA"); return e && e[0] == '1'; }
 
 // Batch -> CTA mapping of the direct EM sweep (see the kernel): chunked once the matrix is large.
@@ -480,7 +476,7 @@ template <class TL> void launch_sweep_a(mswb_vi *vi) {
   const int ld = (int)L->Kp;
   PipeGeom geom{0, 0, 0};
   if constexpr (TL::TPR >= 64 && TL::NT <= 256) {
-    if (want_rcg_pipe(TL::TPR)) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 2, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
+    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 2, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
     if (geom.stages) {
       auto kern = rcg_sweep_a_kernel<TL, true>;
       const size_t smem = pipe_smem_bytes(geom, 2);
@@ -503,7 +499,7 @@ template <class TL, int MODE, bool WRITE> void launch_sweep_b(mswb_vi *vi, int o
   double *gam = WRITE || MODE == 0 ? L->gamma.p : nullptr, *stp = MODE == 0 ? L->step.p : nullptr;
   PipeGeom geom{0, 0, 0};
   if constexpr (TL::TPR >= 64 && TL::NT <= 256) {
-    if (want_rcg_pipe(TL::TPR)) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 3, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
+    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 3, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
     if (geom.stages) {
       auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, true>;
       const size_t smem = pipe_smem_bytes(geom, 3);
