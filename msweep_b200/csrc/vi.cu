@@ -335,22 +335,28 @@ template <int RMAX, int KITER> constexpr int rows_for() { return RMAX / KITER >=
     else throw Error("too many groups for the compiled tile shapes (max 16384 in fp64)");   \
   } while (0)
 
-// Log-domain (RCG) sweeps: measured best with 256-thread CTAs throughout (16 warps per SM hide the longer
-// dependency chains of these sweeps better than the tighter 160/192/224-thread rows do: K = 1500 runs at 4.3 TB/s on
-// Tile<192,4,.> and K = 300 at 2.9 on Tile<96,2,.> against 5.3-5.5 on the power-of-two shapes), KITER = 4 from 65 pieces.
-// Three pieces per thread pay only for 641-768 pieces (K = 1500: 4.35 -> 4.6 TB/s); at 150-600 pieces they lose 3-7 %
-// to KITER = 4 although fewer lanes idle: these sweeps want bytes in flight per thread, not busy lanes.
-// 1025-2048 pieces (K = 2050..4096): 512 threads x 4 pieces (126 registers, 16 warps per SM); 256 threads x 8 pieces
-// needs ~250 registers in sweep B, i.e. 8 warps per SM, and ran at 0.40 instead of 0.60-0.77 of the peak.
+// Log-domain (RCG) sweeps.  Rows of 64-256 threads are fed by the two-CTA TMA ring (launch_sweep_a / _b), which made
+// lane efficiency count: three pieces per thread and the 96 / 192 / 224-thread rows below each gained 4-20 % over the
+// next power-of-two shape once the ring was in (before it, with direct loads, they lost 3-7 %: fewer bytes in flight
+// per thread).  160-thread rows lost (K = 900: 0.85 -> 0.66 of the peak: five-warp CTAs, two per SM) and are not used.
+// One-warp rows (<= 128 pieces) keep direct loads.  1025-2048 pieces (K = 2050..4096): 512 threads x 4 pieces
+// (126 registers, 16 warps per SM); 256 threads x 8 pieces needs ~250 registers in sweep B and ran at 0.40 instead of
+// 0.60-0.77 of the peak.
 #define MSWB_TILE_DISPATCH_RCG(slots, RMAX, ...)                                             \
   do {                                                                                       \
     const int _s = (int)(slots);                                                             \
     if (_s <= 32) MSWB_SHAPE_CASE(32, 1, RMAX, __VA_ARGS__)                                  \
     else if (_s <= 64) MSWB_SHAPE_CASE(32, 2, RMAX, __VA_ARGS__)                             \
     else if (_s <= 128) MSWB_SHAPE_CASE(32, 4, RMAX, __VA_ARGS__)                            \
+    else if (_s <= 192) MSWB_SHAPE_CASE(64, 3, RMAX, __VA_ARGS__)                            \
     else if (_s <= 256) MSWB_SHAPE_CASE(64, 4, RMAX, __VA_ARGS__)                            \
+    else if (_s <= 288) MSWB_SHAPE_CASE(96, 3, RMAX, __VA_ARGS__)                            \
+    else if (_s <= 384) MSWB_SHAPE_CASE(128, 3, RMAX, __VA_ARGS__)                           \
     else if (_s <= 512) MSWB_SHAPE_CASE(128, 4, RMAX, __VA_ARGS__)                           \
-    else if (_s > 640 && _s <= 768) MSWB_SHAPE_CASE(256, 3, RMAX, __VA_ARGS__)               \
+    else if (_s <= 576) MSWB_SHAPE_CASE(192, 3, RMAX, __VA_ARGS__)                           \
+    else if (_s > 640 && _s <= 672) MSWB_SHAPE_CASE(224, 3, RMAX, __VA_ARGS__)               \
+    else if (_s <= 768) MSWB_SHAPE_CASE(256, 3, RMAX, __VA_ARGS__)                           \
+    else if (_s <= 896) MSWB_SHAPE_CASE(224, 4, RMAX, __VA_ARGS__)                           \
     else if (_s <= 1024) MSWB_SHAPE_CASE(256, 4, RMAX, __VA_ARGS__)                          \
     else if (_s <= 2048) MSWB_SHAPE_CASE(512, 4, RMAX, __VA_ARGS__)                          \
     else if (_s <= 4096) MSWB_SHAPE_CASE(512, 8, RMAX, __VA_ARGS__)                          \

@@ -257,7 +257,7 @@ def test_equal_patterns_far_apart_merge(oracle, mswb, ctx):
 
 
 @pytest.mark.parametrize("K,N", [(1, 37), (2, 1), (3, 1000), (33, 513), (65, 2049), (100, 333), (129, 700), (190, 450), (257, 300),
-                                 (330, 257), (400, 129), (460, 131), (600, 200), (1100, 150), (1300, 100), (1600, 70), (1900, 65),
+                                 (330, 257), (400, 129), (460, 131), (560, 90), (600, 200), (900, 110), (1100, 150), (1300, 100), (1500, 60), (1600, 70), (1900, 65),
                                  (2100, 64), (2600, 40), (3100, 33), (3700, 20), (5000, 12), (9000, 9)])
 def test_dense_entry_all_tile_shapes(oracle, mswb, ctx, K, N):
     """mswb_lik_from_dense over every compiled tile shape, ragged N, non-uniform prior, zero-count classes."""
