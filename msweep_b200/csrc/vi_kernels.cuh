@@ -10,13 +10,14 @@
 // bit-reproducible and identical however many CTAs ran).  The grid is persistent (one CTA per SM, or
 // a small multiple) and walks the row batches with a grid stride.
 //
-// How the rows reach the SM (template parameter PIPE):
+// How the rows reach the SM (template parameter PIPE; which one a sweep uses by default was measured, vi.cu):
 //   PIPE = true   whole row batches are pulled into a ring of shared-memory stages by the TMA unit
 //                 (cp.async.bulk global -> shared, completion on an mbarrier with expect_tx); one
 //                 elected thread keeps STAGES-1 batches in flight while all warps consume the oldest.
-//                 Bytes in flight per SM = (STAGES-1) x stage size, independent of register pressure
-//                 and occupancy — this is what keeps HBM busy.
-//   PIPE = false  direct 128-bit streaming loads into registers (fallback for rows too long to stage).
+//                 Bytes in flight per SM = (STAGES-1) x stage size, independent of register pressure.
+//                 Sized for two resident CTAs it is the default of the RCG sweeps with 64-256 threads per row.
+//   PIPE = false  direct 128-bit streaming loads into registers; the EM pass software-pipelines them one batch
+//                 ahead (two register buffers).  Default of the EM pass and of the remaining RCG shapes.
 #pragma once
 #include "common.cuh"
 #include "mathfn.cuh"
