@@ -73,7 +73,7 @@ struct StageClock {
 struct Strand {
   uint64_t n_lines = 0;
   std::vector<uint64_t> row_ptr;       // rows 0 .. n_rows-1, ascending unique columns
-  std::vector<uint32_t> cols;
+  raw_vector<uint32_t> cols;
 };
 
 // Read-only view of a whole file: mmap when possible (no copy, pages faulted in by the tokeniser threads), else a
@@ -170,7 +170,7 @@ Strand parse_strand(const FileView &buf, uint64_t T, int n_threads) {
   // >= T belongs to a later row (flat bit index read_id*T + target, mSWEEP_alignment.hpp:64): those rare hits go to
   // a side list as explicit (row, column) pairs.
   struct Line { uint64_t read; uint64_t off; uint32_t n; };
-  std::vector<std::vector<uint32_t>> cols(n_threads);
+  std::vector<std::unique_ptr<uint32_t[]>> cols(n_threads);     // uninitialised; a token takes at least two bytes of text
   std::vector<std::vector<Line>> line_tab(n_threads);
   std::vector<std::vector<std::pair<uint64_t, uint32_t>>> spill(n_threads);
   std::vector<uint64_t> lines(n_threads, 0), bad_line(n_threads, 0);
@@ -178,25 +178,49 @@ Strand parse_strand(const FileView &buf, uint64_t T, int n_threads) {
 #pragma omp parallel for schedule(static, 1) num_threads(n_threads)
   for (int t = 0; t < n_threads; ++t) {
     const char *p = base + cut[t], *end = base + cut[t + 1];
-    std::vector<uint32_t> &out = cols[t];
-    out.reserve((size_t)(end - p) / 4);
+    cols[t].reset(new uint32_t[(size_t)(end - p) / 2 + 2]);
+    uint32_t *const out0 = cols[t].get();
+    uint32_t *w = out0;
     line_tab[t].reserve((size_t)(end - p) / 128 + 16);
     while (p < end) {
       const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
       if (!eol) eol = end;
       ++lines[t];
+      uint32_t *const line_w = w;
+      const size_t spill0 = spill[t].size();
+      // Fast path: decimal numbers separated by single spaces, which is what Themisto writes.  Anything else
+      // (signs, tabs, junk after the digits) rewinds the line and goes through the stoul-compatible tokeniser below.
       const char *q = p;
-      uint64_t read_id = 0, tgt = 0;
-      bool ok = parse_token(q, eol, read_id);
-      const uint64_t off = out.size();
-      while (ok && q < eol) {
-        ++q;                                       // the single ' ' delimiter
-        if (q >= eol) break;                       // trailing delimiter: getline yields no further token
-        ok = parse_token(q, eol, tgt);
-        if (ok) { if (tgt < T) out.push_back((uint32_t)tgt); else spill[t].emplace_back(read_id + tgt / T, (uint32_t)(tgt % T)); }
+      uint64_t read_id = 0;
+      unsigned d;
+      bool clean = q < eol && (d = (unsigned)(*q - '0')) <= 9;
+      if (clean) {
+        do { read_id = read_id * 10 + d; ++q; } while (q < eol && (d = (unsigned)(*q - '0')) <= 9);
+        while (q < eol) {
+          if (*q != ' ') { clean = false; break; }
+          if (++q >= eol) break;                              // trailing delimiter: getline yields no further token
+          if ((d = (unsigned)(*q - '0')) > 9) { clean = false; break; }
+          uint64_t v = 0;
+          do { v = v * 10 + d; ++q; } while (q < eol && (d = (unsigned)(*q - '0')) <= 9);
+          if (v < T) *w++ = (uint32_t)v; else spill[t].emplace_back(read_id + v / T, (uint32_t)(v % T));
+        }
+      }
+      bool ok = clean;
+      if (!clean) {
+        w = line_w;
+        spill[t].resize(spill0);
+        q = p;
+        uint64_t tgt = 0;
+        ok = parse_token(q, eol, read_id);
+        while (ok && q < eol) {
+          ++q;                                       // the single ' ' delimiter
+          if (q >= eol) break;
+          ok = parse_token(q, eol, tgt);
+          if (ok) { if (tgt < T) *w++ = (uint32_t)tgt; else spill[t].emplace_back(read_id + tgt / T, (uint32_t)(tgt % T)); }
+        }
       }
       if (!ok && !bad_line[t]) { bad_line[t] = lines[t]; bad_text[t].assign(p, eol); }
-      if (ok) line_tab[t].push_back(Line{read_id, off, (uint32_t)(out.size() - off)});
+      if (ok) line_tab[t].push_back(Line{read_id, (uint64_t)(line_w - out0), (uint32_t)(w - line_w)}); else w = line_w;
       p = eol + 1;
     }
   }
@@ -225,10 +249,10 @@ Strand parse_strand(const FileView &buf, uint64_t T, int n_threads) {
     for (const Line &l : line_tab[t]) {
       if (l.read >= R || !l.n) continue;
       const uint64_t pos = __atomic_fetch_add(&fill[l.read], (uint64_t)l.n, __ATOMIC_RELAXED);
-      std::memcpy(s.cols.data() + pos, cols[t].data() + l.off, (size_t)l.n * sizeof(uint32_t));
+      std::memcpy(s.cols.data() + pos, cols[t].get() + l.off, (size_t)l.n * sizeof(uint32_t));
     }
     for (const auto &rc : spill[t]) if (rc.first < R) s.cols[__atomic_fetch_add(&fill[rc.first], 1, __ATOMIC_RELAXED)] = rc.second;
-    std::vector<uint32_t>().swap(cols[t]);
+    cols[t].reset();
     std::vector<Line>().swap(line_tab[t]);
   }
   clk.lap("bucket by row");
@@ -279,23 +303,38 @@ ReadTable read_themisto(const std::vector<std::string> &paths, uint64_t n_target
     auto row = [](const Strand &x, uint64_t r, const uint32_t *&a, const uint32_t *&b) {
       if (r < x.n_lines) { a = x.cols.data() + x.row_ptr[r]; b = x.cols.data() + x.row_ptr[r + 1]; } else { a = b = nullptr; }
     };
+    if (isect) {
+      // the intersection of row r fits inside the first strand's row r: one pass writes it there, a second one packs
 #pragma omp parallel for schedule(static) num_threads(n_threads)
-    for (uint64_t r = 0; r < R; ++r) {
-      const uint32_t *a0, *a1, *b0, *b1;
-      row(acc, r, a0, a1); row(s, r, b0, b1);
-      uint64_t c = 0;
-      if (isect) { while (a0 < a1 && b0 < b1) { if (*a0 < *b0) ++a0; else if (*b0 < *a0) ++b0; else { ++c; ++a0; ++b0; } } }
-      else { while (a0 < a1 && b0 < b1) { if (*a0 < *b0) ++a0; else if (*b0 < *a0) ++b0; else { ++a0; ++b0; } ++c; } c += (uint64_t)(a1 - a0) + (uint64_t)(b1 - b0); }
-      len[r] = c;
-    }
-    for (uint64_t r = 0; r < R; ++r) m.row_ptr[r + 1] = m.row_ptr[r] + len[r];
-    m.cols.resize(m.row_ptr[R]);
+      for (uint64_t r = 0; r < R; ++r) {
+        const uint32_t *a0, *a1, *b0, *b1;
+        row(acc, r, a0, a1); row(s, r, b0, b1);
+        uint32_t *o = const_cast<uint32_t *>(a0), *const o0 = o;
+        while (a0 < a1 && b0 < b1) { if (*a0 < *b0) ++a0; else if (*b0 < *a0) ++b0; else { *o++ = *a0; ++a0; ++b0; } }
+        len[r] = (uint64_t)(o - o0);
+      }
+      for (uint64_t r = 0; r < R; ++r) m.row_ptr[r + 1] = m.row_ptr[r] + len[r];
+      m.cols.resize(m.row_ptr[R]);
 #pragma omp parallel for schedule(static) num_threads(n_threads)
-    for (uint64_t r = 0; r < R; ++r) {
-      const uint32_t *a0, *a1, *b0, *b1;
-      row(acc, r, a0, a1); row(s, r, b0, b1);
-      uint32_t *o = m.cols.data() + m.row_ptr[r];
-      if (isect) std::set_intersection(a0, a1, b0, b1, o); else std::set_union(a0, a1, b0, b1, o);
+      for (uint64_t r = 0; r < R; ++r)
+        if (len[r]) std::memcpy(m.cols.data() + m.row_ptr[r], acc.cols.data() + acc.row_ptr[r], len[r] * sizeof(uint32_t));
+    } else {
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+      for (uint64_t r = 0; r < R; ++r) {
+        const uint32_t *a0, *a1, *b0, *b1;
+        row(acc, r, a0, a1); row(s, r, b0, b1);
+        uint64_t c = 0;
+        while (a0 < a1 && b0 < b1) { if (*a0 < *b0) ++a0; else if (*b0 < *a0) ++b0; else { ++a0; ++b0; } ++c; }
+        len[r] = c + (uint64_t)(a1 - a0) + (uint64_t)(b1 - b0);
+      }
+      for (uint64_t r = 0; r < R; ++r) m.row_ptr[r + 1] = m.row_ptr[r] + len[r];
+      m.cols.resize(m.row_ptr[R]);
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+      for (uint64_t r = 0; r < R; ++r) {
+        const uint32_t *a0, *a1, *b0, *b1;
+        row(acc, r, a0, a1); row(s, r, b0, b1);
+        std::set_union(a0, a1, b0, b1, m.cols.data() + m.row_ptr[r]);
+      }
     }
     (void)Ra;
     acc = std::move(m);

@@ -13,6 +13,8 @@
 #include <cstdint>
 #include <functional>
 #include <limits>
+#include <memory>
+#include <new>
 #include <ostream>
 #include <stdexcept>
 #include <string>
@@ -43,12 +45,22 @@ private:
   int rank_ = 0, world_ = 1;
 };
 
+// std::vector whose resize() leaves trivially constructible elements uninitialised: the parser sizes hundreds of
+// megabytes and then fills them from all threads; a zero-fill by one thread first would cost more than the fill.
+template <class T> struct default_init_allocator : std::allocator<T> {
+  template <class U> struct rebind { using other = default_init_allocator<U>; };
+  template <class U, class... A> void construct(U *p, A &&...a) {
+    if constexpr (sizeof...(A) == 0) ::new ((void *)p) U; else ::new ((void *)p) U(std::forward<A>(a)...);
+  }
+};
+template <class T> using raw_vector = std::vector<T, default_init_allocator<T>>;
+
 // The strand-merged pseudoalignment as the reference's Alignment holds it after read() (one bit per
 // (read, target)), in CSR form: row r = ascending target ids of read r.
 struct ReadTable {
   uint64_t n_reads = 0, n_targets = 0;
   std::vector<uint64_t> row_ptr{0};
-  std::vector<uint32_t> targets;
+  raw_vector<uint32_t> targets;
 };
 
 // mSWEEP::Alignment after collapse() (include/mSWEEP_alignment.hpp:137-241).
