@@ -370,7 +370,7 @@ constexpr size_t SMEM_BUDGET = 200 * 1024;   // dynamic shared memory for the st
 // units of `unit_rows` (= G*R).  stages == 0: the rows are too long to stage, use the direct kernel.
 PipeGeom pipe_geometry(size_t row_bytes, int unit_rows, int nsrc, int tpr, size_t budget = SMEM_BUDGET, size_t target = 32 * 1024) {
   PipeGeom g{0, 0, 0};
-  if (tpr > 256) return g;
+  if (tpr > 512) return g;
   const size_t unit_bytes = (size_t)unit_rows * row_bytes;
   if (const char *e = getenv("MSWB_STAGE_KB")) target = (size_t)atoi(e) * 1024;
   const int units = (int)std::max<size_t>(1, target / unit_bytes);
@@ -438,8 +438,9 @@ void launch_finalize(mswb_vi *vi, int nvals, int only_if_reset) {
 // lockstep through load / exp / reduce phases.  A ring sized for TWO resident CTAs (100 KB, 16 KB stages: double
 // buffering for sweep B, three stages for sweep A) beats both for the exp-heavy sweeps — bytes in flight no longer
 // depend on registers: K = 2000 5.68 vs 5.46 TB/s, K = 1500 5.4 vs 4.6, K = 1000 5.75 vs 5.44, K = 700 4.68 vs 4.39,
-// K = 420 5.16 vs 4.93.  One-warp rows (TPR = 32, K <= 256) gain nothing consistent (K = 100 +6 %, K = 256 -4 %) and
-// keep direct loads.  So: RCG sweeps with rows of 64-256 threads use the two-CTA ring by default (MSWB_RCG_TMA=0 turns
+// K = 420 5.16 vs 4.93.  The 512-thread rows (K = 2050..4096) hold one CTA per SM either way and take the ring with the
+// whole 200 KB (K = 3000: 4.35 vs 3.84 TB/s).  One-warp rows (TPR = 32, K <= 256) gain nothing consistent (K = 100
+// +6 %, K = 256 -4 %) and keep direct loads.  So: RCG sweeps with rows of 64-256 threads use the two-CTA ring by default (MSWB_RCG_TMA=0 turns
 // it off); the EM sweep, already at the copy peak with direct loads, keeps them (MSWB_EM_TMA=1 selects the one-CTA ring,
 // compiled for TPR = 256 only).
 constexpr size_t RCG_RING_BYTES = 100 * 1024, RCG_STAGE_BYTES = 16 * 1024;
@@ -481,8 +482,8 @@ template <class TL> void launch_sweep_a(mswb_vi *vi) {
   cudaStream_t s = vi->ctx->stream;
   const int ld = (int)L->Kp;
   PipeGeom geom{0, 0, 0};
-  if constexpr (TL::TPR >= 64 && TL::NT <= 256) {
-    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 2, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
+  if constexpr (TL::TPR >= 64 && TL::NT <= 512) {
+    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 2, TL::TPR, TL::NT <= 256 ? RCG_RING_BYTES : SMEM_BUDGET, TL::NT <= 256 ? RCG_STAGE_BYTES : 2 * RCG_STAGE_BYTES);
     if (geom.stages) {
       auto kern = rcg_sweep_a_kernel<TL, true>;
       const size_t smem = pipe_smem_bytes(geom, 2);
@@ -504,8 +505,8 @@ template <class TL, int MODE, bool WRITE> void launch_sweep_b(mswb_vi *vi, int o
   const int ld = (int)L->Kp;
   double *gam = WRITE || MODE == 0 ? L->gamma.p : nullptr, *stp = MODE == 0 ? L->step.p : nullptr;
   PipeGeom geom{0, 0, 0};
-  if constexpr (TL::TPR >= 64 && TL::NT <= 256) {
-    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 3, TL::TPR, RCG_RING_BYTES, RCG_STAGE_BYTES);
+  if constexpr (TL::TPR >= 64 && TL::NT <= 512) {
+    if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 3, TL::TPR, TL::NT <= 256 ? RCG_RING_BYTES : SMEM_BUDGET, TL::NT <= 256 ? RCG_STAGE_BYTES : 2 * RCG_STAGE_BYTES);
     if (geom.stages) {
       auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, true>;
       const size_t smem = pipe_smem_bytes(geom, 3);
