@@ -101,6 +101,35 @@ def test_parser_quirks_match_reference_semantics(oracle, tmp_path):
     assert rows[0] == [1, 3, 5, 9] and rows[2] == [7] and rows[1] == [] and rows[4] == [2] and rows[3] == []
 
 
+def test_parser_fast_and_slow_paths_agree(oracle, tmp_path):
+    """Well-formed lines take the tokeniser's fast path; a sign, a tab, junk glued to a number or a CR rewind the line into
+    the std::stoul-compatible path.  Mixed at random (with target ids >= T, which spill into later rows) against the oracle."""
+    rng = np.random.default_rng(12)
+    T, R = 40, 3000
+    g = tmp_path / "g.txt"
+    g.write_text("".join(f"g{i % 4}\n" for i in range(T)))
+    lines = []
+    for r in rng.permutation(R):
+        toks = [str(int(t)) for t in rng.integers(0, T + 25, size=rng.integers(0, 9))]
+        if rng.random() < 0.3:
+            for i in range(len(toks)):
+                kind = rng.integers(0, 5)
+                toks[i] = {0: "+" + toks[i], 1: "\t" + toks[i], 2: toks[i] + "x7", 3: toks[i] + ".5", 4: toks[i]}[int(kind)]
+        line = " ".join([str(int(r))] + toks)
+        trailing = rng.random() < 0.1
+        if trailing:
+            line += " "
+        # (a CR after a trailing space would be a token of its own, which std::stoul rejects: "File format not supported")
+        lines.append(line + ("\r\n" if not trailing and rng.random() < 0.05 else "\n"))
+    a = tmp_path / "a.aln"
+    a.write_text("".join(lines))
+    for threads in (1, 5):
+        Rn, Tn, rp, tg = dump(tmp_path, [str(a)], str(g), threads=threads)
+        n, rp_o, tg_o = oracle.read_themisto([str(a)], T, "intersection")
+        assert Rn == n == R
+        assert np.array_equal(rp, rp_o) and np.array_equal(tg, tg_o)
+
+
 @pytest.mark.parametrize("content,line", [("0 1\nx 2\n", 2), ("0 1\n1  2\n", 2), ("0 1\n\n", 2), ("0 a\n", 1)])
 def test_parser_errors_name_the_line(tmp_path, content, line):
     g = tmp_path / "g.txt"
