@@ -439,8 +439,9 @@ void launch_finalize(mswb_vi *vi, int nvals, int only_if_reset) {
 // buffering for sweep B, three stages for sweep A) beats both for the exp-heavy sweeps — bytes in flight no longer
 // depend on registers: K = 2000 5.68 vs 5.46 TB/s, K = 1500 5.4 vs 4.6, K = 1000 5.75 vs 5.44, K = 700 4.68 vs 4.39,
 // K = 420 5.16 vs 4.93.  The 512-thread rows (K = 2050..4096) hold one CTA per SM either way and take the ring with the
-// whole 200 KB (K = 3000: 4.35 vs 3.84 TB/s).  One-warp rows (TPR = 32, K <= 256) gain nothing consistent (K = 100
-// +6 %, K = 256 -4 %) and keep direct loads.  So: RCG sweeps with rows of 64-256 threads use the two-CTA ring by default (MSWB_RCG_TMA=0 turns
+// whole 200 KB (K = 3000: 4.35 vs 3.84 TB/s).  Of the one-warp rows (TPR = 32, K <= 256) only the two-piece shape
+// (33-64 pieces, K = 66..128) takes the ring: K = 70 +8 %, K = 100 +6 %, K = 128 -1 %; with one or four pieces per
+// thread it gained nothing consistent (K = 50 +1 %, K = 150 -1 %, K = 256 -4 %) and those keep direct loads.  So: RCG sweeps with rows of 64-256 threads use the two-CTA ring by default (MSWB_RCG_TMA=0 turns
 // it off); the EM sweep, already at the copy peak with direct loads, keeps them (MSWB_EM_TMA=1 selects the one-CTA ring,
 // compiled for TPR = 256 only).
 constexpr size_t RCG_RING_BYTES = 100 * 1024, RCG_STAGE_BYTES = 16 * 1024;
@@ -482,7 +483,7 @@ template <class TL> void launch_sweep_a(mswb_vi *vi) {
   cudaStream_t s = vi->ctx->stream;
   const int ld = (int)L->Kp;
   PipeGeom geom{0, 0, 0};
-  if constexpr (TL::TPR >= 64 && TL::NT <= 512) {
+  if constexpr ((TL::TPR >= 64 || (TL::TPR == 32 && TL::KITER == 2)) && TL::NT <= 512) {
     if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 2, TL::TPR, TL::NT <= 256 ? RCG_RING_BYTES : SMEM_BUDGET, TL::NT <= 256 ? RCG_STAGE_BYTES : 2 * RCG_STAGE_BYTES);
     if (geom.stages) {
       auto kern = rcg_sweep_a_kernel<TL, true>;
@@ -505,7 +506,7 @@ template <class TL, int MODE, bool WRITE> void launch_sweep_b(mswb_vi *vi, int o
   const int ld = (int)L->Kp;
   double *gam = WRITE || MODE == 0 ? L->gamma.p : nullptr, *stp = MODE == 0 ? L->step.p : nullptr;
   PipeGeom geom{0, 0, 0};
-  if constexpr (TL::TPR >= 64 && TL::NT <= 512) {
+  if constexpr ((TL::TPR >= 64 || (TL::TPR == 32 && TL::KITER == 2)) && TL::NT <= 512) {
     if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 3, TL::TPR, TL::NT <= 256 ? RCG_RING_BYTES : SMEM_BUDGET, TL::NT <= 256 ? RCG_STAGE_BYTES : 2 * RCG_STAGE_BYTES);
     if (geom.stages) {
       auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, true>;
