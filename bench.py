@@ -244,7 +244,9 @@ def main():
         h2d = wl.row_ptr.nbytes + wl.targets.nbytes + wl.group_of_target.nbytes + wl.group_sizes.nbytes + 8 * N_GROUPS
         e2e = {"value": n_job * a.steps / sec, "unit": "EC-iter/s", "vi_iters_per_s": a.steps / sec, "seconds": sec,
                "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": (8 * N_GROUPS + 64) / a.steps,
-               "what": "mswb_ec_build + mswb_lik_build + mswb_vi_run(K iterations) from host CSR buffers, theta back on the host"}
+               "what": "mswb_ec_build + mswb_lik_build + mswb_vi_run(K iterations) from host CSR buffers, theta back on the host",
+               "allocator": "the library's device block cache is warm (the resident leg ran first): a cold process pays the "
+                            "cudaMalloc of the matrix once on top (0.2-0.4 s at 100 GB)"}
         lik.close(); aln.close()
 
     # ---- side series on the same inputs (N = 1 only): the fp64 forms of the sweep, which cannot hold the full shard ----
