@@ -3,6 +3,7 @@
 // product's mSWEEP_b200 binary against the restated reference end to end, file against file.
 #include "oracle.hpp"
 
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -22,11 +23,16 @@ int main(int argc, char **argv) {
     std::string k = argv[i];
     k = k.substr(k[1] == '-' ? 2 : 1);
     if (k == "verbose") continue;
-    if (k == "write-probs" || k == "run-rate" || k == "bin-reads") { kv[k] = "1"; continue; }
+    if (k == "write-probs" || k == "run-rate" || k == "bin-reads" || k == "print-timings") { kv[k] = "1"; continue; }
     if (i + 1 >= argc) { std::cerr << "missing value for " << k << "\n"; return 1; }
     kv[k] = argv[++i];
   }
   auto get = [&](const std::string &k, const std::string &d) { return kv.count(k) ? kv[k] : d; };
+  // stage timers for the CPU baseline: parse, collapse, likelihood, optimiser, bootstrap, write
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&]() { const auto t = std::chrono::steady_clock::now(); const double s = std::chrono::duration<double>(t - t_last).count(); t_last = t; return s; };
+  double t_parse = 0, t_collapse = 0, t_lik = 0, t_vi = 0, t_boot = 0;
+  uint64_t vi_iters = 0;
   try {
 #ifdef _OPENMP
     omp_set_num_threads(std::stoi(get("t", "1")));
@@ -41,10 +47,13 @@ int main(int argc, char **argv) {
     std::vector<std::istream*> strands;
     for (auto &f : files) strands.push_back(&f);
     ReadTable reads = read_themisto(strands, grouping.group_of_target.size(), get("themisto-mode", "intersection"));
+    t_parse = lap();
     EcTable ec = collapse(reads);
+    t_collapse = lap();
     const uint64_t min_hits = std::stoull(get("min-hits", "0"));
     Likelihood lik = build_likelihood(ec, grouping, std::stod(get("q", "0.65")), std::stod(get("e", "0.01")),
                                       std::stod(get("zero-inflation", "0.01")), min_hits, false);
+    t_lik = lap();
     const uint32_t K = lik.n_groups;
     std::vector<double> prior(K, 1.0);
     if (kv.count("alphas")) { prior.clear(); std::stringstream ss(kv["alphas"]); std::string p; while (std::getline(ss, p, ',')) prior.push_back(std::stod(p)); }
@@ -56,16 +65,18 @@ int main(int argc, char **argv) {
     auto estimate = [&](const std::vector<double> &lc) {
       ViResult r = rcg ? rcg_optl(lik.logl.data(), K, ec.n_ecs(), lc.data(), prior.data(), tol, max_iters)
                        : em_optl(lik.logl.data(), K, ec.n_ecs(), lc.data(), prior.data(), tol, max_iters);
-      if (first_gamma.empty()) first_gamma = r.gamma;
+      if (first_gamma.empty()) { first_gamma = r.gamma; vi_iters = r.iters; }
       return mixture_components(r.gamma.data(), K, ec.n_ecs(), lc.data());
     };
     std::vector<std::vector<double>> results;
     results.push_back(estimate(lik.log_counts));
+    t_vi = lap();
     const uint64_t iters = std::stoull(get("iters", "0"));
     if (iters) {
       Bootstrapper bs(ec.count, (int32_t)std::stoull(get("seed", "26012023")), std::stoull(get("bootstrap-count", "0")));
       for (uint64_t r = 0; r < iters; ++r) results.push_back(estimate(bs.resample_counts()));
     }
+    t_boot = lap();
     std::vector<std::string> est, zero;
     for (size_t g = 0; g < grouping.names.size(); ++g) (lik.groups_mask[g] ? est : zero).push_back(grouping.names[g]);
     uint64_t n_aligned = 0;
@@ -110,6 +121,11 @@ int main(int argc, char **argv) {
       for (size_t i = 0; i < zero.size(); ++i) of << zero[i] << '\t' << 0.0 << '\t' << 0.0 << '\t' << 0.0 << '\n';
     } else
     write_abundances(of, get("version-string", "oracle"), reads.n_reads, n_aligned, est, zero, results, iters);
+    if (kv.count("print-timings"))
+      std::cerr << "{\"parse_s\": " << t_parse << ", \"collapse_s\": " << t_collapse << ", \"likelihood_s\": " << t_lik
+                << ", \"optimiser_s\": " << t_vi << ", \"optimiser_iters\": " << vi_iters
+                << ", \"optimiser_s_per_iter\": " << (vi_iters ? t_vi / (double)vi_iters : 0.0) << ", \"bootstrap_s\": " << t_boot
+                << ", \"write_s\": " << lap() << ", \"n_ecs\": " << ec.n_ecs() << ", \"threads\": " << get("t", "1") << "}" << std::endl;
   } catch (const std::exception &e) {
     std::cerr << "oracle failed:\n  " << e.what() << "\nexiting\n";
     return 1;

@@ -24,9 +24,10 @@ common = ["--themisto-1", paths[0], "--themisto-2", paths[1], "-i", g, "-t", str
 if a.iters:
     common += ["--iters", str(a.iters), "--seed", "7"]
 t0 = time.time()
-r = subprocess.run([os.path.join(root, "oracle", "msweep_oracle"), *common, "-o", os.path.join(d, "ref"), "--algorithm", "rcgcpu"], capture_output=True, text=True)
+r = subprocess.run([os.path.join(root, "oracle", "msweep_oracle"), *common, "-o", os.path.join(d, "ref"), "--algorithm", "rcgcpu", "--print-timings"], capture_output=True, text=True)
 t_ref = time.time() - t0
 assert r.returncode == 0, r.stderr
+oracle_stages = json.loads(r.stderr.strip().splitlines()[-1])
 t0 = time.time()
 r = subprocess.run([os.path.join(root, "msweep_b200", "bin", "mSWEEP_b200"), *common, "-o", os.path.join(d, "ours"), "--print-timings"], capture_output=True, text=True)
 t_ours = time.time() - t0
@@ -46,5 +47,5 @@ h1 = [l for l in open(os.path.join(d, "ours_abundances.txt")).read().splitlines(
 h2 = [l for l in open(os.path.join(d, "ref_abundances.txt")).read().splitlines() if l.startswith("#")][1:]
 print(json.dumps({"config": f"1: {a.reads} paired reads x 3000 refs / 50 lineages, rcg, -t {a.threads}, bootstrap iters {a.iters}",
                   "input_mb": sum(os.path.getsize(p) for p in paths) / 1e6, "generate_s": round(t_gen, 1),
-                  "oracle_cli_s": round(t_ref, 2), "msweep_b200_cli_s": round(t_ours, 2), "stages": stages, "parse_stages": parse_stages,
+                  "oracle_cli_s": round(t_ref, 2), "oracle_stages": oracle_stages, "host_cores": os.cpu_count(), "msweep_b200_cli_s": round(t_ours, 2), "stages": stages, "parse_stages": parse_stages,
                   "same_header": h1 == h2, "same_names": n1 == n2, "max_abs_theta_diff": float(np.max(np.abs(v1 - v2)))}))
