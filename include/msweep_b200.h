@@ -68,6 +68,14 @@ MSWB_API int  mswb_ctx_create(int device, int rank, int world_size, const void *
  * (ncclCommInitAll — no bootstrap network, so it is much quicker than n calls of mswb_ctx_create).  out[n]. */
 MSWB_API int  mswb_ctx_create_group(int n, const int *devices, mswb_ctx **out);
 MSWB_API void mswb_ctx_destroy(mswb_ctx *ctx);
+/* Device blocks of 64 MB and more that the library has released are parked for reuse (cudaMalloc / cudaFree of a
+ * 100 GB matrix cost 0.2-0.4 s), up to MSWB_CACHE_GB gigabytes per device (default: a quarter of its memory).
+ * An embedding process that needs the memory back calls this: every parked block of ctx's device is cudaFree'd. */
+MSWB_API int  mswb_ctx_trim(mswb_ctx *ctx);
+/* Aborts the NCCL communicator of ctx (ncclCommAbort): collectives this rank is waiting in end with an error instead
+ * of waiting for a peer that has failed.  May be called from another host thread than the one driving ctx; a process
+ * that holds several ranks calls it on every context when one of them fails.  The context can still be destroyed. */
+MSWB_API int  mswb_ctx_abort(mswb_ctx *ctx);
 /* Creates the CUDA primary context of `device` (seconds on a cold process); call it from a side thread while
  * the host is still parsing its inputs so that mswb_ctx_create returns immediately afterwards. */
 MSWB_API int  mswb_device_warmup(int device);

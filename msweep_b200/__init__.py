@@ -94,6 +94,14 @@ class Context:
     def sync(self) -> None:
         _check(lib().mswb_ctx_sync(self.h))
 
+    def trim(self) -> None:
+        """mswb_ctx_trim: hand the parked device blocks of this context's GPU back to the driver."""
+        _check(lib().mswb_ctx_trim(self.h))
+
+    def abort(self) -> None:
+        """mswb_ctx_abort: abort the NCCL communicator (a peer failed); pending collectives end with an error."""
+        _check(lib().mswb_ctx_abort(self.h))
+
     def shard_range(self, n_ecs: int) -> tuple[int, int]:
         a, b = C.c_uint64(), C.c_uint64()
         _check(lib().mswb_shard_range(self.h, C.c_uint64(n_ecs), C.byref(a), C.byref(b)))

@@ -43,28 +43,29 @@ extern std::atomic<uint64_t> g_launches;
 // cudaMalloc / cudaFree of the multi-GB matrices cost tens to hundreds of milliseconds (page tables, an implicit device
 // synchronisation): blocks of 64 MB and more go back to a small per-device cache instead and are handed out again to
 // requests of a similar size.  The cache is emptied when an allocation fails and when a context is destroyed (ctx.cu).
-void *dev_alloc(size_t bytes, size_t *capacity);
-void dev_free(void *p, size_t capacity);
+void *dev_alloc(size_t bytes, size_t *capacity, int *device);
+void dev_free(void *p, size_t capacity, int device);   // device: the one the block was allocated on
 void dev_cache_flush(int device);
 
 template <typename T> struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
   size_t cap = 0;   // bytes of the underlying block
+  int dev = 0;      // device the block lives on
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = 0; o.cap = 0; }
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), cap(o.cap), dev(o.dev) { o.p = nullptr; o.n = 0; o.cap = 0; }
   DevBuf &operator=(DevBuf &&o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = 0; o.cap = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; dev = o.dev; o.p = nullptr; o.n = 0; o.cap = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
-  void release() { if (p) dev_free(p, cap); p = nullptr; n = 0; cap = 0; }
+  void release() { if (p) dev_free(p, cap, dev); p = nullptr; n = 0; cap = 0; }
   void alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    p = static_cast<T *>(dev_alloc(count * sizeof(T), &cap));
+    p = static_cast<T *>(dev_alloc(count * sizeof(T), &cap, &dev));
     n = count;
   }
   void ensure(size_t count) { if (count > n) alloc(count); }
@@ -98,6 +99,9 @@ template <typename T> void d2h(T *dst, const T *src_dev, size_t count, cudaStrea
 }
 
 inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+// The linear-domain likelihood, the counts and the row maxima are padded with zero rows to a multiple of ROW_PAD
+// classes (>= the rows of one CTA batch of every tile shape): the EM sweep carries no row-bounds predicates.
+constexpr int ROW_PAD = 256;
 inline uint64_t round_up(uint64_t a, uint64_t b) { return ceil_div(a, b) * b; }
 
 // ---- device math ------------------------------------------------------------------------------
@@ -166,7 +170,7 @@ struct mswb_ctx {
   int n_sms = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  void *nccl_comm = nullptr;
+  std::atomic<void *> nccl_comm{nullptr};   // (mswb_ctx_abort may take it away from another thread)
   mswb::DevBuf<double> comm_buf;       // staging for the per-pass all-reduce
   void allreduce_sum(double *buf_dev, size_t count);           // no-op when world == 1
   void allreduce_sum_u64(unsigned long long *buf_dev, size_t count);

@@ -29,9 +29,10 @@ void dev_cache_flush(int device) {
   for (const CachedBlock &b : mine) cudaFree(b.p);
 }
 
-void *dev_alloc(size_t bytes, size_t *capacity) {
+void *dev_alloc(size_t bytes, size_t *capacity, int *device_out) {
   int device = 0;
   cudaGetDevice(&device);
+  *device_out = device;
   if (bytes >= CACHE_MIN_BYTES) {
     std::lock_guard<std::mutex> lock(g_cache_mu);
     size_t best = g_cache.size();
@@ -62,17 +63,29 @@ void *dev_alloc(size_t bytes, size_t *capacity) {
   return p;
 }
 
-void dev_free(void *p, size_t capacity) {
+// Blocks of 64 MB and more are parked for reuse under the device they were allocated on — whatever device is
+// current in the calling thread — as long as the parked total of that device stays under the cap (MSWB_CACHE_GB,
+// default a quarter of the device's memory); mswb_ctx_trim / mswb_ctx_destroy hand everything back to the driver.
+void dev_free(void *p, size_t capacity, int device) {
   if (!p) return;
+  int current = 0;
+  cudaGetDevice(&current);
+  if (current != device) cudaSetDevice(device);
+  bool parked = false;
   if (capacity >= CACHE_MIN_BYTES) {
-    int device = 0;
-    cudaGetDevice(&device);
+    static size_t cap_bytes = 0;
+    if (cap_bytes == 0) {
+      if (const char *e = getenv("MSWB_CACHE_GB")) cap_bytes = (size_t)(atof(e) * 1073741824.0) + 1;
+      else { size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b); cap_bytes = total_b / 4 + 1; }
+    }
     cudaDeviceSynchronize();   // what cudaFree would have done: nothing in flight still uses the block
     std::lock_guard<std::mutex> lock(g_cache_mu);
-    g_cache.push_back(CachedBlock{p, capacity, device});
-    return;
+    size_t held = 0;
+    for (const CachedBlock &b : g_cache) if (b.device == device) held += b.bytes;
+    if (held + capacity <= cap_bytes) { g_cache.push_back(CachedBlock{p, capacity, device}); parked = true; }
   }
-  cudaFree(p);
+  if (!parked) cudaFree(p);
+  if (current != device) cudaSetDevice(current);
 }
 } // namespace mswb
 
@@ -86,6 +99,7 @@ struct NcclApi {
   int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
   int (*CommInitAll)(void **, int, const int *) = nullptr;
   int (*CommDestroy)(void *) = nullptr;
+  int (*CommAbort)(void *) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
@@ -104,6 +118,7 @@ static NcclApi &nccl() {
     api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
     api.CommInitAll = (decltype(api.CommInitAll))dlsym(api.handle, "ncclCommInitAll");
     api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+    api.CommAbort = (decltype(api.CommAbort))dlsym(api.handle, "ncclCommAbort");
     api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
   });
@@ -122,11 +137,15 @@ static NcclApi &nccl() {
 
 void mswb_ctx::allreduce_sum(double *buf_dev, size_t count) {
   if (world == 1 || count == 0) return;
-  MSWB_NCCL(nccl().AllReduce(buf_dev, buf_dev, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, nccl_comm, stream));
+  void *comm = nccl_comm.load();
+  MSWB_REQUIRE(comm, "the communicator of this context has been aborted (a peer rank failed)");
+  MSWB_NCCL(nccl().AllReduce(buf_dev, buf_dev, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, stream));
 }
 void mswb_ctx::allreduce_sum_u64(unsigned long long *buf_dev, size_t count) {
   if (world == 1 || count == 0) return;
-  MSWB_NCCL(nccl().AllReduce(buf_dev, buf_dev, count, /*ncclUint64*/ 5, /*ncclSum*/ 0, nccl_comm, stream));
+  void *comm = nccl_comm.load();
+  MSWB_REQUIRE(comm, "the communicator of this context has been aborted (a peer rank failed)");
+  MSWB_NCCL(nccl().AllReduce(buf_dev, buf_dev, count, /*ncclUint64*/ 5, /*ncclSum*/ 0, comm, stream));
 }
 
 extern "C" {
@@ -167,7 +186,9 @@ int mswb_ctx_create(int device, int rank, int world_size, const void *nccl_id, v
       MSWB_REQUIRE(nccl_id, "nccl_id is required when world_size > 1");
       NcclUniqueId id;
       std::memcpy(&id, nccl_id, sizeof(id));
-      MSWB_NCCL(nccl().CommInitRank(&ctx->nccl_comm, world_size, id, rank));
+      void *comm = nullptr;
+      MSWB_NCCL(nccl().CommInitRank(&comm, world_size, id, rank));
+      ctx->nccl_comm = comm;
     }
     *out = ctx.release();
   });
@@ -191,14 +212,33 @@ int mswb_ctx_create_group(int n, const int *devices, mswb_ctx **out) {
   });
 }
 
+int mswb_ctx_abort(mswb_ctx *ctx) {
+  return mswb::guarded([&] {
+    MSWB_REQUIRE(ctx, "ctx is NULL");
+    void *comm = ctx->nccl_comm.exchange(nullptr);
+    if (!comm) return;
+    MSWB_REQUIRE(nccl().CommAbort, "ncclCommAbort is not available in the loaded NCCL");
+    MSWB_NCCL(nccl().CommAbort(comm));     // pending collectives of this rank end with an error instead of waiting for ever
+  });
+}
+
 void mswb_ctx_destroy(mswb_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  if (ctx->nccl_comm) nccl().CommDestroy(ctx->nccl_comm);
+  if (void *comm = ctx->nccl_comm.exchange(nullptr)) nccl().CommDestroy(comm);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   mswb::dev_cache_flush(ctx->device);
   delete ctx;
+}
+
+int mswb_ctx_trim(mswb_ctx *ctx) {
+  return mswb::guarded([&] {
+    MSWB_REQUIRE(ctx, "ctx is NULL");
+    MSWB_CUDA(cudaSetDevice(ctx->device));
+    MSWB_CUDA(cudaStreamSynchronize(ctx->stream));
+    mswb::dev_cache_flush(ctx->device);
+  });
 }
 
 int mswb_device_warmup(int device) {

@@ -29,7 +29,7 @@ struct mswb_lik {
   uint32_t K = 0;              // groups kept after --min-hits (rows of the reference's matrix)
   uint32_t Kp = 0;             // device row stride in elements
   uint64_t N = 0;              // classes in this rank's shard
-  uint64_t N_pad = 0;          // N rounded up to ROW_PAD (64): counts / rowmax / P carry zero rows up to here
+  uint64_t N_pad = 0;          // N rounded up to ROW_PAD (common.cuh): counts / rowmax / P carry zero rows up to here
   uint64_t ec_begin = 0;       // first global class index of the shard
   uint64_t N_total = 0;        // classes over all ranks
   int storage = MSWB_STORE_F64;

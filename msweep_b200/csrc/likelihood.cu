@@ -183,7 +183,8 @@ sparse_fill_kernel(const uint64_t *__restrict__ pat_ptr, const uint32_t *__restr
         const uint32_t g = group_of_target[pat_targets[p]];
         const unsigned c = atomicExch(&row[g], 0u);
         const int pos = pos_of_group[g];
-        if (c > 0u && pos >= 0) { mine = true; pos_u = (uint32_t)pos; v = exp(lut[lut_off[pos] + c] - m) - p0; }
+        // the sparse pass wants (class index inside its 32-class chunk, group) in one word: top 8 bits, low 24 bits
+        if (c > 0u && pos >= 0) { mine = true; pos_u = (uint32_t)pos | ((uint32_t)(j & 31u) << 24); v = exp(lut[lut_off[pos] + c] - m) - p0; }
       }
       const unsigned ballot = __ballot_sync(0xffffffffu, mine);
       if (mine) {
@@ -447,7 +448,20 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
     MSWB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const uint64_t T = aln->n_targets;
-    for (uint64_t t = 0; t < T; ++t) MSWB_REQUIRE(group_of_target[t] < n_groups, "group indicator out of range");
+    // The hit count of a class in group g indexes row g of the ragged lookup table (0 .. size(g)): the sizes must be
+    // the number of targets the indicators put in each group, exactly what the reference's Grouping holds
+    // (include/Grouping.hpp:62-83); anything smaller would send the lookup into the next group's row.
+    {
+      std::vector<uint64_t> tally(n_groups, 0);
+      for (uint64_t t = 0; t < T; ++t) {
+        MSWB_REQUIRE(group_of_target[t] < n_groups, "group indicator out of range");
+        ++tally[group_of_target[t]];
+      }
+      for (uint32_t g = 0; g < n_groups; ++g)
+        MSWB_REQUIRE(group_sizes[g] == tally[g], "group_sizes[" + std::to_string(g) + "] = " + std::to_string(group_sizes[g]) +
+                                                     " but the indicators put " + std::to_string(tally[g]) + " targets in that group");
+    }
+    MSWB_REQUIRE(storage != MSWB_STORE_SPARSE || n_groups < (1u << 24), "sparse storage packs the group in 24 bits");
 
     std::unique_ptr<mswb_lik> L(new mswb_lik);
     L->ctx = ctx;
@@ -475,7 +489,7 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
       L->ec_begin = lo;
     }
     L->N = hi - lo;
-    L->N_pad = round_up(L->N, 64);
+    L->N_pad = round_up(L->N, ROW_PAD);
     L->n_targets = T;
     L->from_patterns = true;
     L->l0 = std::log(zero_inflation);
@@ -565,7 +579,7 @@ int mswb_lik_from_dense(mswb_ctx *ctx, const double *logl, uint32_t n_groups, ui
     L->K_all = L->K = n_groups;
     L->Kp = (uint32_t)round_up(n_groups, 2);
     L->N = n_ecs_local;
-    L->N_pad = round_up(n_ecs_local, 64);
+    L->N_pad = round_up(n_ecs_local, ROW_PAD);
     L->storage = storage;
     L->mask.assign(n_groups, 1);
     L->kept.resize(n_groups);

@@ -15,28 +15,12 @@
 using namespace mswb;
 
 // =====================================================================================================
-// control kernels (one CTA; K-sized work)
+// control kernels (one CTA; K-sized work).  The control STEPS live in vi_kernels.cuh: on one GPU they run in the
+// tail of the sweeps (or of finalize_ctl_kernel); these wrappers serve several GPUs, where the all-reduce sits between.
 // =====================================================================================================
 namespace mswb {
 
 constexpr int CTL_NT = 256;
-
-struct ViArrays {
-  double *alpha0, *N_k, *dg, *w;   // [K]   dg = digamma(N_k) (EM) or digamma(N_k) - 1 (RCG)
-  double *dg_prev;                  // [K]   EM: the digamma vector the LAST pass used (posteriors on demand)
-  double *red;                      // [K + 2] reduced sums of the last sweep
-  double *trace_bound, *trace_gnorm;
-  unsigned char *trace_reset;
-  unsigned long long trace_cap;
-};
-
-__device__ __forceinline__ void trace_push(const ViArrays &a, ViCtl *ctl, double gnorm, int reset) {
-  if (ctl->iter < a.trace_cap) {
-    a.trace_bound[ctl->iter] = ctl->bound;
-    a.trace_gnorm[ctl->iter] = gnorm;
-    a.trace_reset[ctl->iter] = (unsigned char)reset;
-  }
-}
 
 // N_k = alpha0 + total/K (what gamma = log(1/K) gives), first digamma vector, control block reset.
 __global__ void vi_init_kernel(ViArrays a, ViCtl *ctl, int K, int algo, double tol, unsigned long long max_iters,
@@ -59,114 +43,23 @@ __global__ void vi_init_kernel(ViArrays a, ViCtl *ctl, int K, int algo, double t
     ctl->bound_const = bound_const; ctl->tol = tol; ctl->sum_counts = sum_counts; ctl->dg_max = mx;
     ctl->iter = 0; ctl->max_iters = max_iters; ctl->resets = 0;
     ctl->use_old = 0; ctl->didreset = 0; ctl->converged = 0; ctl->fault = 0;
+    ctl->stall = 0; ctl->ticket = 0u; ctl->pad_ = 0;
     ctl->done = max_iters == 0 ? 1 : 0;
   }
 }
 
-// EM: N_k, bound, convergence test, then the next digamma / weight vector.
-// red[k] = sum_j P(j,k) c_j / S_j (without w_k), red[K] = sum_j c_j (log S_j + M_j).
-__global__ void em_ctl_kernel(ViArrays a, ViCtl *ctl, int K, int linear) {
+__global__ void __launch_bounds__(CTL_NT) em_ctl_kernel(ViArrays a, ViCtl *ctl, int K, int sparse) {
   if (ctl->done) return;
   __shared__ double scratch[32];
-  double lg = 0.0, dga = 0.0;
-  for (int k = threadIdx.x; k < K; k += CTL_NT) {
-    const double A = linear ? a.w[k] * (a.red[k] + a.red[K + 1]) : a.red[k];   // red[K+1]: the share every group gets (sparse pass), else 0
-    const double nk = a.alpha0[k] + A;
-    a.N_k[k] = nk;
-    lg += lgamma(nk);
-    dga += a.dg[k] * A;
-  }
-  lg = block_sum<CTL_NT>(lg, scratch);
-  dga = block_sum<CTL_NT>(dga, scratch);
-  double mx = -INFINITY;
-  for (int k = threadIdx.x; k < K; k += CTL_NT) {
-    const double dg = digamma_series(a.N_k[k]);
-    a.dg_prev[k] = a.dg[k];
-    a.dg[k] = dg;
-    mx = fmax(mx, dg);
-  }
-  mx = block_max<CTL_NT>(mx, scratch);
-  for (int k = threadIdx.x; k < K; k += CTL_NT) a.w[k] = exp(a.dg[k] - mx);
-  if (threadIdx.x == 0) {
-    // linear: log-normaliser of class j is log S_j + M_j + dg_max, and sum_k q (logl - gamma) = lse_j - sum_k q dg_k
-    const double data = linear ? a.red[K] + ctl->sum_counts * ctl->dg_max - dga : a.red[K];
-    const double bound = data + lg + ctl->bound_const;
-    ctl->oldbound = ctl->bound;
-    ctl->bound = bound;
-    trace_push(a, ctl, 0.0, 0);
-    ctl->iter += 1;
-    if (ctl->iter > 1 && fabs(bound - ctl->oldbound) < ctl->tol) ctl->converged = 1;
-    if (ctl->converged || ctl->iter >= ctl->max_iters || ctl->fault) ctl->done = 1;
-    ctl->dg_max = mx;
-  }
+  em_ctl_step<CTL_NT>(a, ctl, K, sparse, scratch);
 }
 
-// RCG, after sweep A: Fletcher-Reeves coefficient.  partials (world == 1) or red[K+1] (after all-reduce).
-__global__ void rcg_ctl_a_kernel(ViArrays a, ViCtl *ctl, int K, const double *partials, int pstride, int n_ctas) {
+// stage 0: after sweep B.  stage 1: after the restart sweep the host enqueued for a stalled optimisation.
+__global__ void __launch_bounds__(CTL_NT) rcg_ctl_b_kernel(ViArrays a, ViCtl *ctl, int K, int stage, int stall_on_reject) {
   if (ctl->done) return;
+  if (stage == 0 ? ctl->stall != 0 : !ctl->didreset) return;
   __shared__ double scratch[32];
-  double nn;
-  if (partials) {
-    double acc = 0.0;
-    for (int c = threadIdx.x; c < n_ctas; c += CTL_NT) acc += partials[(size_t)c * pstride + K + 1];
-    nn = block_sum<CTL_NT>(acc, scratch);
-  } else {
-    nn = a.red[K + 1];
-  }
-  if (threadIdx.x == 0) {
-    const double beta = nn / ctl->oldnorm;
-    ctl->newnorm = nn;
-    ctl->oldnorm = nn;
-    ctl->beta = beta;
-    // the direction memory is empty before the first accepted step (the reference starts it at zero)
-    ctl->use_old = (!ctl->didreset && beta > 0.0 && ctl->iter > 0) ? 1 : 0;
-    ctl->didreset = 0;
-  }
-}
-// World > 1: bring sweep A's per-CTA partial norms to red[K+1] for the all-reduce.
-__global__ void rcg_norm_partial_kernel(ViArrays a, const ViCtl *ctl, int K, const double *partials, int pstride, int n_ctas) {
-  if (ctl->done) return;
-  __shared__ double scratch[32];
-  double acc = 0.0;
-  for (int c = threadIdx.x; c < n_ctas; c += CTL_NT) acc += partials[(size_t)c * pstride + K + 1];
-  acc = block_sum<CTL_NT>(acc, scratch);
-  if (threadIdx.x == 0) a.red[K + 1] = acc;
-}
-
-// RCG, after sweep B (stage 0) or after the restart sweep (stage 1).
-// red[k] = sum_j c_j q(j,k), red[K] = sum_jk c_j q (logl - gamma).
-__global__ void rcg_ctl_b_kernel(ViArrays a, ViCtl *ctl, int K, int stage) {
-  if (ctl->done) return;
-  if (stage == 1 && !ctl->didreset) return;
-  __shared__ double scratch[32];
-  __shared__ int s_accept;
-  double lg = 0.0;
-  for (int k = threadIdx.x; k < K; k += CTL_NT) lg += lgamma(a.alpha0[k] + a.red[k]);
-  lg = block_sum<CTL_NT>(lg, scratch);
-  const double cand = a.red[K] + lg + ctl->bound_const;
-  if (threadIdx.x == 0) {
-    if (stage == 0 && cand < ctl->bound) {
-      // the conjugate direction lost ground: drop it, redo the step from the same N_k (restart sweep)
-      ctl->didreset = 1;
-      ctl->resets += 1;
-      s_accept = 0;
-    } else {
-      s_accept = 1;
-      ctl->oldbound = ctl->bound;
-      ctl->bound = cand;
-      trace_push(a, ctl, ctl->newnorm, stage);
-      ctl->iter += 1;
-      if (stage == 0 && cand - ctl->oldbound < ctl->tol) ctl->converged = 1;
-      if (ctl->converged || ctl->iter >= ctl->max_iters) ctl->done = 1;
-    }
-  }
-  __syncthreads();
-  if (!s_accept) return;
-  for (int k = threadIdx.x; k < K; k += CTL_NT) {
-    const double nk = a.alpha0[k] + a.red[k];
-    a.N_k[k] = nk;
-    a.dg[k] = digamma_series(nk) - 1.0;
-  }
+  rcg_ctl_b_step<CTL_NT>(a, ctl, K, stage, stall_on_reject, scratch);
 }
 
 __global__ void fill_kernel(double *p, size_t n, double v) {
@@ -268,15 +161,16 @@ struct mswb_vi {
   mswb_lik *lik = nullptr;
   mswb_vi_opts opts{};
   int K = 0;
-  bool linear = true;            // EM in the linear domain (P) vs log domain (logl)
   DevBuf<ViCtl> ctl;
-  DevBuf<double> alpha0, N_k, dg, dg_prev, w, red, partials, trace_bound, trace_gnorm, own_counts, block_sums;
+  DevBuf<double> alpha0, N_k, dg, dg_prev, w, red, seg, partials, trace_bound, trace_gnorm, own_counts, block_sums;
   DevBuf<unsigned char> trace_reset;
   const double *counts = nullptr;   // device, [N]
   double sum_counts = 0.0;
   std::vector<double> alpha0_host;
   ViArrays arrays{};
   int pstride = 0, grid = 0, max_grid = 0;
+  int tail_max = 16384;          // partial values (grid x columns) the last CTA of a sweep may reduce on its own
+  double fx_scale = 1.0;         // fixed-point scale of the sparse pass (vi_kernels.cuh)
   uint64_t enqueued = 0;
   uint64_t pass_bytes = 0;
   // optional kernel timing
@@ -319,10 +213,19 @@ template <int RMAX, int KITER> constexpr int rows_for() { return RMAX / KITER >=
   }
 // fp32 rows that would need 224 / 256 threads with more registers than two CTAs per SM allow (7-8 warps per SM: 0.75 of
 // the peak at K = 4000) take a 512-thread CTA with half the pieces instead (1.00).  fp64 keeps 256 x 8 (0.83 vs 0.74).
+// Short rows (<= 32 pieces, K <= 64 in fp64 / 128 in fp32): sub-warp row groups.  W lanes x KITER pieces with R rows per
+// group and batch; a warp works on (32 / W) x R rows at once and every lane owns one row's division and logarithm.
+// MSWB_SMALL=0 falls back to one warp per row (the round-1 shape), for A/B runs.
+static bool want_small_shapes() { const char *e = getenv("MSWB_SMALL"); return !(e && e[0] == '0'); }
 #define MSWB_TILE_DISPATCH(slots, RMAX, IS_F32, ...)                                         \
   do {                                                                                       \
     const int _s = (int)(slots);                                                             \
-    if (_s <= 32) MSWB_SHAPE_CASE(32, 1, RMAX, __VA_ARGS__)                                  \
+    if (_s <= 2 && want_small_shapes()) { using TL = Tile<2, 1, 2>; __VA_ARGS__; }           \
+    else if (_s <= 4 && want_small_shapes()) { using TL = Tile<4, 1, 4>; __VA_ARGS__; }      \
+    else if (_s <= 8 && want_small_shapes()) { using TL = Tile<8, 1, 8>; __VA_ARGS__; }      \
+    else if (_s <= 16 && want_small_shapes()) { using TL = Tile<16, 1, 8>; __VA_ARGS__; }    \
+    else if (_s <= 32 && want_small_shapes()) { using TL = Tile<16, 2, 4>; __VA_ARGS__; }    \
+    else if (_s <= 32) MSWB_SHAPE_CASE(32, 1, RMAX, __VA_ARGS__)                             \
     else if (_s <= 512) { const int _t = (int)round_up(ceil_div(_s, 2), 32); MSWB_SHAPE_BY_TPR(_t, 2, RMAX, __VA_ARGS__) }   \
     else if (_s <= 1024) { const int _t = (int)round_up(ceil_div(_s, 4), 32);                \
       if ((IS_F32) && _t >= 224) MSWB_SHAPE_CASE(512, 2, RMAX, __VA_ARGS__)                  \
@@ -345,7 +248,12 @@ template <int RMAX, int KITER> constexpr int rows_for() { return RMAX / KITER >=
 #define MSWB_TILE_DISPATCH_RCG(slots, RMAX, ...)                                             \
   do {                                                                                       \
     const int _s = (int)(slots);                                                             \
-    if (_s <= 32) MSWB_SHAPE_CASE(32, 1, RMAX, __VA_ARGS__)                                  \
+    if (_s <= 2 && want_small_shapes()) { using TL = Tile<2, 1, 2>; __VA_ARGS__; }                          \
+    else if (_s <= 4 && want_small_shapes()) { using TL = Tile<4, 1, (RMAX) >= 8 ? 4 : 2>; __VA_ARGS__; }   \
+    else if (_s <= 8 && want_small_shapes()) { using TL = Tile<8, 1, (RMAX) >= 8 ? 8 : 4>; __VA_ARGS__; }   \
+    else if (_s <= 16 && want_small_shapes()) { using TL = Tile<16, 1, (RMAX) >= 8 ? 8 : 4>; __VA_ARGS__; } \
+    else if (_s <= 32 && want_small_shapes()) { using TL = Tile<16, 2, (RMAX) >= 8 ? 4 : 2>; __VA_ARGS__; } \
+    else if (_s <= 32) MSWB_SHAPE_CASE(32, 1, RMAX, __VA_ARGS__)                             \
     else if (_s <= 64) MSWB_SHAPE_CASE(32, 2, RMAX, __VA_ARGS__)                             \
     else if (_s <= 128) MSWB_SHAPE_CASE(32, 4, RMAX, __VA_ARGS__)                            \
     else if (_s <= 192) MSWB_SHAPE_CASE(64, 3, RMAX, __VA_ARGS__)                            \
@@ -426,10 +334,25 @@ struct PassTimer {
   void stop() { if (on) MSWB_CUDA(cudaEventRecord(vi->events[slot].second, vi->ctx->stream)); }
 };
 
-void launch_finalize(mswb_vi *vi, int nvals, int only_if_reset) {
-  const int nt = 128;
-  finalize_partials_kernel<<<(nvals + nt - 1) / nt, nt, 0, vi->ctx->stream>>>(
-      vi->partials.p, vi->pstride, vi->grid, nvals, vi->red.p, vi->ctl.p, only_if_reset);
+// How the partial vectors of a sweep with `grid` CTAs and `nvals` columns get summed: by the sweep's last CTA when that
+// is a small job (2: and the control step with it, one GPU; 1: several GPUs), else by finalize_ctl_kernel (0).
+int tail_mode(const mswb_vi *vi, int grid, int nvals) {
+  if ((long long)grid * nvals > vi->tail_max) return 0;
+  return vi->ctx->world == 1 ? 2 : 1;
+}
+// Small problems are bound by launch latency, not by bytes: cap the grid at one CTA per SM there so that the last
+// CTA's reduction stays a few microseconds.
+int grid_cap(const mswb_vi *vi, int nvals) {
+  const mswb_lik *L = vi->lik;
+  const bool small = (uint64_t)L->N * L->K * 8 <= ((uint64_t)64 << 20);
+  if (!small) return vi->max_grid;
+  return std::max(1, std::min(vi->max_grid, std::max(vi->ctx->n_sms, vi->tail_max / nvals)));
+}
+
+// ctl_mode: -1 none, 0 EM dense, 1 EM sparse, 2 RCG stage 0 (finalize_ctl_kernel)
+void launch_finalize(mswb_vi *vi, int nvals, int ctl_mode, int ignore_stall = 0) {
+  finalize_ctl_kernel<<<(nvals + FIN_NT - 1) / FIN_NT, FIN_NT, 0, vi->ctx->stream>>>(
+      vi->partials.p, vi->pstride, vi->grid, nvals, vi->arrays, vi->ctl.p, vi->K, ctl_mode, ignore_stall);
   MSWB_LAUNCHED();
 }
 
@@ -455,55 +378,65 @@ static bool em_chunked(const mswb_lik *L) {
   return (size_t)L->N_pad * L->K * el > ((size_t)16 << 30);   // measured: +1.2 % at 100 GB, neutral at 24 GB
 }
 
-template <typename ST, class TL> void launch_em(mswb_vi *vi, const ST *P, int ld) {
+// returns the tail mode the sweep was launched with
+template <typename ST, class TL> int launch_em(mswb_vi *vi, const ST *P, int ld) {
   mswb_lik *L = vi->lik;
   cudaStream_t s = vi->ctx->stream;
+  const int nvals = vi->K + RED_EXTRA, cap = grid_cap(vi, nvals);
   PipeGeom geom{0, 0, 0};
   if constexpr (TL::TPR == 256) {
     if (want_em_pipe()) geom = pipe_geometry((size_t)ld * sizeof(ST), TL::G * TL::R, 1, TL::TPR);
     if (geom.stages) {
       auto kern = em_lin_pass_kernel<ST, TL, true>;
       const size_t smem = pipe_smem_bytes(geom, 1);
-      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N_pad, (uint64_t)geom.stage_rows), vi->max_grid);
-      kern<<<vi->grid, TL::NT, smem, s>>>(P, ld, L->rowmax.p, vi->counts, vi->w.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N_pad,
-                                          vi->K, geom);
+      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N_pad, (uint64_t)geom.stage_rows), cap);
+      const int tail = tail_mode(vi, vi->grid, nvals);
+      kern<<<vi->grid, TL::NT, smem, s>>>(P, ld, L->rowmax.p, vi->counts, vi->arrays, vi->ctl.p, vi->partials.p, vi->pstride, L->N_pad,
+                                          vi->K, geom, tail);
       MSWB_LAUNCHED();
-      return;
+      return tail;
     }
   }
   if (em_chunked(L)) geom.stage_rows = 1;
   auto kern = em_lin_pass_kernel<ST, TL, false>;
-  vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, L->N_pad / (TL::G * TL::R), vi->max_grid);
-  kern<<<vi->grid, TL::NT, 0, s>>>(P, ld, L->rowmax.p, vi->counts, vi->w.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N_pad, vi->K, geom);
+  vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, L->N_pad / (TL::G * TL::R), cap);
+  const int tail = tail_mode(vi, vi->grid, nvals);
+  kern<<<vi->grid, TL::NT, 0, s>>>(P, ld, L->rowmax.p, vi->counts, vi->arrays, vi->ctl.p, vi->partials.p, vi->pstride, L->N_pad, vi->K,
+                                   geom, tail);
   MSWB_LAUNCHED();
+  return tail;
 }
 
 template <class TL> void launch_sweep_a(mswb_vi *vi) {
   mswb_lik *L = vi->lik;
   cudaStream_t s = vi->ctx->stream;
   const int ld = (int)L->Kp;
+  const int cap = grid_cap(vi, vi->K + 1);
   PipeGeom geom{0, 0, 0};
   if constexpr ((TL::TPR >= 64 || (TL::TPR == 32 && TL::KITER == 2)) && TL::NT <= 512) {
     if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 2, TL::TPR, TL::NT <= 256 ? RCG_RING_BYTES : SMEM_BUDGET, TL::NT <= 256 ? RCG_STAGE_BYTES : 2 * RCG_STAGE_BYTES);
     if (geom.stages) {
       auto kern = rcg_sweep_a_kernel<TL, true>;
       const size_t smem = pipe_smem_bytes(geom, 2);
-      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N, (uint64_t)geom.stage_rows), vi->max_grid);
-      kern<<<vi->grid, TL::NT, smem, s>>>(L->logl.p, L->gamma.p, ld, vi->dg.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N, vi->K, geom);
+      const int ga = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N, (uint64_t)geom.stage_rows), cap);
+      kern<<<ga, TL::NT, smem, s>>>(L->logl.p, L->gamma.p, ld, vi->arrays, vi->ctl.p, vi->partials.p, vi->pstride, L->N, vi->K, geom);
       MSWB_LAUNCHED();
       return;
     }
   }
   auto kern = rcg_sweep_a_kernel<TL, false>;
-  vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, ceil_div(L->N, (uint64_t)TL::G * TL::R), vi->max_grid);
-  kern<<<vi->grid, TL::NT, 0, s>>>(L->logl.p, L->gamma.p, ld, vi->dg.p, vi->ctl.p, vi->partials.p, vi->pstride, L->N, vi->K, geom);
+  const int ga = persistent_grid(vi->ctx, kern, TL::NT, 0, ceil_div(L->N, (uint64_t)TL::G * TL::R), cap);
+  kern<<<ga, TL::NT, 0, s>>>(L->logl.p, L->gamma.p, ld, vi->arrays, vi->ctl.p, vi->partials.p, vi->pstride, L->N, vi->K, geom);
   MSWB_LAUNCHED();
 }
 
-template <class TL, int MODE, bool WRITE> void launch_sweep_b(mswb_vi *vi, int only_if_reset) {
+// force_tail >= 0 overrides the tail mode (the restart sweep always reduces in its last CTA: it is rare).
+// Returns the tail mode used.
+template <class TL, int MODE, bool WRITE> int launch_sweep_b(mswb_vi *vi, int only_if_reset, int force_tail = -1) {
   mswb_lik *L = vi->lik;
   cudaStream_t s = vi->ctx->stream;
   const int ld = (int)L->Kp;
+  const int nvals = vi->K + 1, cap = grid_cap(vi, nvals);
   double *gam = WRITE || MODE == 0 ? L->gamma.p : nullptr, *stp = MODE == 0 ? L->step.p : nullptr;
   PipeGeom geom{0, 0, 0};
   if constexpr ((TL::TPR >= 64 || (TL::TPR == 32 && TL::KITER == 2)) && TL::NT <= 512) {
@@ -511,85 +444,105 @@ template <class TL, int MODE, bool WRITE> void launch_sweep_b(mswb_vi *vi, int o
     if (geom.stages) {
       auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, true>;
       const size_t smem = pipe_smem_bytes(geom, 3);
-      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N, (uint64_t)geom.stage_rows), vi->max_grid);
-      kern<<<vi->grid, TL::NT, smem, s>>>(L->logl.p, gam, stp, ld, vi->dg.p, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N,
-                                          vi->K, only_if_reset, geom);
+      vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N, (uint64_t)geom.stage_rows), cap);
+      const int tail = force_tail >= 0 ? force_tail : tail_mode(vi, vi->grid, nvals);
+      kern<<<vi->grid, TL::NT, smem, s>>>(L->logl.p, gam, stp, ld, vi->arrays, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N,
+                                          vi->K, only_if_reset, geom, tail);
       MSWB_LAUNCHED();
-      return;
+      return tail;
     }
   }
   auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, false>;
-  vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, ceil_div(L->N, (uint64_t)TL::G * TL::R), vi->max_grid);
-  kern<<<vi->grid, TL::NT, 0, s>>>(L->logl.p, gam, stp, ld, vi->dg.p, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N, vi->K,
-                                   only_if_reset, geom);
+  vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, ceil_div(L->N, (uint64_t)TL::G * TL::R), cap);
+  const int tail = force_tail >= 0 ? force_tail : tail_mode(vi, vi->grid, nvals);
+  kern<<<vi->grid, TL::NT, 0, s>>>(L->logl.p, gam, stp, ld, vi->arrays, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N, vi->K,
+                                   only_if_reset, geom, tail);
   MSWB_LAUNCHED();
+  return tail;
 }
 
+// One EM / VB iteration.  One GPU: the pass (its last CTA reduces and takes the control step) — ONE launch — or the
+// pass + finalize_ctl_kernel when the partial vectors are too many for one CTA.  Several GPUs: pass, [finalize],
+// all-reduce of K + 3 doubles, control kernel.
 void em_iteration(mswb_vi *vi) {
   mswb_lik *L = vi->lik;
-  cudaStream_t s = vi->ctx->stream;
-  const int K = vi->K;
+  mswb_ctx *ctx = vi->ctx;
+  cudaStream_t s = ctx->stream;
+  const int K = vi->K, nvals = K + RED_EXTRA;
+  const int sparse = L->storage == MSWB_STORE_SPARSE ? 1 : 0;
+  int tail = 0;
   PassTimer timer(vi);
-  if (vi->linear && L->storage == MSWB_STORE_SPARSE) {
-    const size_t smem = (size_t)2 * K * sizeof(double);
+  if (sparse) {
+    const size_t smem = em_sparse_smem_bytes(K);
     MSWB_REQUIRE(smem <= 200 * 1024, "too many groups for the sparse EM pass (weights and accumulators live in shared memory)");
-    if (smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(em_sparse_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    MSWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_sparse_pass_kernel, 256, smem));
-    vi->grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)vi->ctx->n_sms * std::max(1, per_sm), std::min<uint64_t>(ceil_div(L->N, 256), (uint64_t)vi->max_grid)));
-    em_sparse_pass_kernel<<<vi->grid, 256, smem, s>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_dP.p, L->P0.p, L->rowmax.p, vi->counts, vi->w.p,
-                                                     vi->ctl.p, vi->partials.p, vi->pstride, L->N, K);
+    vi->grid = persistent_grid(ctx, em_sparse_pass_kernel, SP_NT, smem, ceil_div(L->N, (uint64_t)SP_NT), grid_cap(vi, nvals));
+    tail = tail_mode(vi, vi->grid, nvals);
+    em_sparse_pass_kernel<<<vi->grid, SP_NT, smem, s>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_dP.p, L->P0.p, L->rowmax.p, vi->counts,
+                                                       vi->arrays, vi->ctl.p, vi->partials.p, vi->pstride, L->N, L->nnz, K, vi->fx_scale, tail);
     MSWB_LAUNCHED();
-  } else if (vi->linear && L->storage == MSWB_STORE_F32) {
-    MSWB_TILE_DISPATCH(L->Kp32 / 4, 8, true, launch_em<float, TL>(vi, L->P32.p, (int)L->Kp32));
-  } else if (vi->linear) {
-    MSWB_TILE_DISPATCH(L->Kp / 2, 8, false, launch_em<double, TL>(vi, L->P64.p, (int)L->Kp));
+  } else if (L->storage == MSWB_STORE_F32) {
+    MSWB_TILE_DISPATCH(L->Kp32 / 4, 8, true, tail = launch_em<float, TL>(vi, L->P32.p, (int)L->Kp32));
   } else {
-    MSWB_TILE_DISPATCH_RCG(L->Kp / 2, 4, launch_sweep_b<TL, 1, false>(vi, 0));
+    MSWB_TILE_DISPATCH(L->Kp / 2, 8, false, tail = launch_em<double, TL>(vi, L->P64.p, (int)L->Kp));
   }
   timer.stop();
-  launch_finalize(vi, vi->linear ? K + 2 : K + 1, 0);
-  vi->ctx->allreduce_sum(vi->red.p, vi->linear ? K + 2 : K + 1);
-  em_ctl_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, vi->linear ? 1 : 0);
+  if (ctx->world == 1) {
+    if (tail == 0) launch_finalize(vi, nvals, sparse);
+    return;
+  }
+  if (tail == 0) launch_finalize(vi, nvals, -1);
+  ctx->allreduce_sum(vi->red.p, nvals);
+  em_ctl_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, sparse);
   MSWB_LAUNCHED();
 }
 
+// One RCG iteration.
+//   one GPU     : sweep A (its last CTA sums the gradient norm), sweep B (computes the Fletcher-Reeves ratio itself;
+//                 its last CTA, or finalize_ctl_kernel, reduces and takes the control step), then the restart sweep,
+//                 which exits at once unless the control step rejected the move: 3-4 launches, no host round trip.
+//   several GPUs: sweep A, all-reduce(1), sweep B, [finalize], all-reduce(K + 1), control kernel: two collectives.
+//                 A rejected move sets ctl->stall; everything enqueued behind it exits at once and the host enqueues
+//                 the restart (sweep, reduction, all-reduce, control) at its next poll — restarts are rare, and a
+//                 third collective per iteration is not.
 void rcg_iteration(mswb_vi *vi) {
   mswb_lik *L = vi->lik;
   mswb_ctx *ctx = vi->ctx;
   cudaStream_t s = ctx->stream;
   const int K = vi->K;
   const int slots = L->Kp / 2;
-  // sweep A: gradient norm
   {
     PassTimer timer(vi);
     MSWB_TILE_DISPATCH_RCG(slots, 8, launch_sweep_a<TL>(vi));   // (one row per batch / three CTAs per SM measured the same: 5456 vs 5445 GB/s)
     timer.stop();
   }
-  if (ctx->world > 1) {
-    rcg_norm_partial_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, vi->partials.p, vi->pstride, vi->grid);
-    MSWB_LAUNCHED();
-    ctx->allreduce_sum(vi->red.p + K + 1, 1);
-    rcg_ctl_a_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, nullptr, 0, 0);
-  } else {
-    rcg_ctl_a_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, vi->partials.p, vi->pstride, vi->grid);
-  }
-  MSWB_LAUNCHED();
-  // sweep B: step, renormalise, N_k, bound
+  ctx->allreduce_sum(vi->red.p + K + RED_AUX, 1);
+  int tail = 0;
   {
     PassTimer timer(vi);
-    MSWB_TILE_DISPATCH_RCG(slots, 4, launch_sweep_b<TL, 0, true>(vi, 0));
+    MSWB_TILE_DISPATCH_RCG(slots, 4, tail = (launch_sweep_b<TL, 0, true>(vi, 0)));
     timer.stop();
   }
-  launch_finalize(vi, K + 1, 0);
+  if (ctx->world == 1) {
+    if (tail == 0) launch_finalize(vi, K + 1, 2);
+    MSWB_TILE_DISPATCH_RCG(slots, 4, (launch_sweep_b<TL, 1, true>(vi, 1, 2)));
+    return;
+  }
+  if (tail == 0) launch_finalize(vi, K + 1, -1);
   ctx->allreduce_sum(vi->red.p, K + 1);
-  rcg_ctl_b_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, 0);
+  rcg_ctl_b_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, 0, 1);
   MSWB_LAUNCHED();
-  // restart sweep: runs only when the control block says so (device-side decision, no host round trip)
-  MSWB_TILE_DISPATCH_RCG(slots, 4, launch_sweep_b<TL, 1, true>(vi, 1));
-  launch_finalize(vi, K + 1, 1);
+}
+
+// Several GPUs: the restart of a stalled optimisation (every rank stalls at the same iteration: the decision is taken
+// on all-reduced values).
+void rcg_restart_stalled(mswb_vi *vi) {
+  mswb_lik *L = vi->lik;
+  mswb_ctx *ctx = vi->ctx;
+  const int K = vi->K;
+  const int slots = L->Kp / 2;
+  MSWB_TILE_DISPATCH_RCG(slots, 4, (launch_sweep_b<TL, 1, true>(vi, 1, 1)));
   ctx->allreduce_sum(vi->red.p, K + 1);
-  rcg_ctl_b_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, 1);
+  rcg_ctl_b_kernel<<<1, CTL_NT, 0, ctx->stream>>>(vi->arrays, vi->ctl.p, K, 1, 1);
   MSWB_LAUNCHED();
 }
 
@@ -607,8 +560,12 @@ void fill_stat(mswb_vi *vi, const ViCtl &c, mswb_vi_stat *stat) {
 
 ViCtl poll_ctl(mswb_vi *vi) {
   ViCtl c;
-  d2h(&c, vi->ctl.p, 1, vi->ctx->stream);
-  MSWB_CUDA(cudaStreamSynchronize(vi->ctx->stream));
+  for (;;) {
+    d2h(&c, vi->ctl.p, 1, vi->ctx->stream);
+    MSWB_CUDA(cudaStreamSynchronize(vi->ctx->stream));
+    if (!c.stall || c.done) break;
+    rcg_restart_stalled(vi);
+  }
   if (vi->opts.time_kernels) {
     for (size_t i = 0; i < vi->events_used; ++i) {
       float ms = 0.f;
@@ -618,6 +575,7 @@ ViCtl poll_ctl(mswb_vi *vi) {
     }
     vi->events_used = 0;
   }
+  // (the flag travels in the all-reduced vector: every rank sees it at the same iteration and none is left in a collective)
   MSWB_REQUIRE(!c.fault, "EM pass: a class normaliser under/overflowed in the linear domain (extreme prior counts)");
   return c;
 }
@@ -648,7 +606,6 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
       MSWB_LAUNCHED();
       vi->pass_bytes = (uint64_t)lik->N * K * 56 + (uint64_t)lik->N * 8;   // sweep A 16 B + sweep B 40 B per element
     } else {
-      vi->linear = true;
       if (lik->storage == MSWB_STORE_SPARSE) {
         lik_ensure_sparse(lik);
         vi->pass_bytes = lik->nnz * 12 + (uint64_t)lik->N * 40;              // hits (group + value), ptr, P0, M_j, c_j
@@ -660,13 +617,16 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
     }
 
     // per-group vectors
-    vi->alpha0.alloc(K); vi->N_k.alloc(K); vi->dg.alloc(K); vi->dg_prev.alloc(K); vi->w.alloc(K); vi->red.alloc(K + 2);
+    vi->alpha0.alloc(K); vi->N_k.alloc(K); vi->dg.alloc(K); vi->dg_prev.alloc(K); vi->w.alloc(K); vi->red.alloc(K + RED_EXTRA);
+    MSWB_CUDA(cudaMemsetAsync(vi->red.p, 0, (K + RED_EXTRA) * sizeof(double), s));
     vi->alpha0_host.assign(alpha0, alpha0 + K);
     for (int k = 0; k < K; ++k) MSWB_REQUIRE(alpha0[k] > 0.0 && std::isfinite(alpha0[k]), "prior counts must be positive");
     h2d(vi->alpha0.p, alpha0, K, s);
     vi->max_grid = ctx->n_sms * 8;
-    vi->pstride = (int)round_up(K + 2, 2);
+    vi->pstride = (int)round_up(K + RED_EXTRA, 2);
     vi->partials.alloc((size_t)vi->max_grid * vi->pstride);
+    vi->seg.alloc((size_t)RED_SEGS * vi->pstride);
+    if (const char *e = getenv("MSWB_TAIL_MAX")) vi->tail_max = atoi(e);
     const uint64_t cap = std::min<uint64_t>(opts->max_iters, 1u << 20);
     vi->trace_bound.alloc(cap); vi->trace_gnorm.alloc(cap); vi->trace_reset.alloc(cap);
     vi->ctl.alloc(1);
@@ -701,8 +661,10 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
     for (int k = 0; k < K; ++k) { a_sum += alpha0[k]; lg_sum += std::lgamma(alpha0[k]); }
     const double bconst = (double)(std::lgamma((double)a_sum) - std::lgamma((double)(a_sum + vi->sum_counts)) - lg_sum);
 
-    vi->arrays = ViArrays{vi->alpha0.p, vi->N_k.p, vi->dg.p, vi->w.p, vi->dg_prev.p, vi->red.p, vi->trace_bound.p,
+    vi->arrays = ViArrays{vi->alpha0.p, vi->N_k.p, vi->dg.p, vi->w.p, vi->dg_prev.p, vi->red.p, vi->seg.p, vi->trace_bound.p,
                           vi->trace_gnorm.p, vi->trace_reset.p, cap};
+    // sparse pass: responsibilities are summed in 64-bit fixed point; |term| <= c_j, so 2^61 / 2^ceil(log2(sum c)) cannot overflow
+    vi->fx_scale = std::ldexp(1.0, 61 - (int)std::ceil(std::log2(std::max(1.0, vi->sum_counts))));
     vi_init_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, opts->algo, opts->tol, opts->max_iters, bconst, vi->sum_counts);
     MSWB_LAUNCHED();
     lik->last_algo = opts->algo;

@@ -6,9 +6,19 @@
 // quantities (the logsumexp / the normaliser S_j / the mean step) are reductions ALONG a row:
 // warp shuffles, plus one shared-memory hop when a row spans several warps.  Per-group quantities
 // (the expected counts N_k) accumulate DOWN the rows in registers and leave the CTA once, as a
-// per-CTA partial vector that a second tiny kernel sums in a fixed order (no atomics: results are
-// bit-reproducible and identical however many CTAs ran).  The grid is persistent (one CTA per SM, or
+// per-CTA partial vector; the partial vectors are summed in CTA order (no floating-point atomics: results are
+// bit-reproducible and identical however the CTAs were scheduled).  The grid is persistent (one CTA per SM, or
 // a small multiple) and walks the row batches with a grid stride.
+//
+// Short rows (K <= 64) use TPR = 4 / 8 / 16: a warp then works on 32/TPR row groups at once, the reductions stay
+// inside TPR-lane segments, and every lane owns one row's division and logarithm.
+//
+// Who sums the partial vectors (argument `tail` of every sweep):
+//   0  a separate kernel (finalize_ctl_kernel) — large grids x many groups, where one CTA would take too long;
+//   1  the last CTA of the sweep to finish (a ticket in the control block), nothing else — several GPUs: the
+//      all-reduce and the control kernel follow;
+//   2  the last CTA, which then also takes the control step (N_k, bound, convergence, next digamma vector) —
+//      one GPU, small problems: an EM iteration is ONE launch, an RCG iteration two.
 //
 // How the rows reach the SM (template parameter PIPE; which one a sweep uses by default was measured, vi.cu):
 //   PIPE = true   whole row batches are pulled into a ring of shared-memory stages by the TMA unit
@@ -32,14 +42,37 @@ struct ViCtl {
   double bound_const, tol, sum_counts, dg_max;
   unsigned long long iter, max_iters, resets;
   int use_old, didreset, converged, done, fault;
+  int stall;             // several GPUs: an RCG step lost ground; iterations pause until the host has enqueued the restart
+  unsigned int ticket;   // CTAs of the running sweep that have delivered their partial vector (the last one reduces them)
+  int pad_;
 };
 
+// Per-group vectors of one optimisation (all device pointers).
+struct ViArrays {
+  double *alpha0, *N_k, *dg, *w;   // [K]   dg = digamma(N_k) (EM) or digamma(N_k) - 1 (RCG)
+  double *dg_prev;                  // [K]   EM: the digamma vector the LAST pass used (posteriors on demand)
+  double *red;                      // [K + 3] reduced sums of the last sweep: per group, then the three slots below
+  double *seg;                      // [RED_SEGS x pstride] scratch of the last CTA's segmented reduction
+  double *trace_bound, *trace_gnorm;
+  unsigned char *trace_reset;
+  unsigned long long trace_cap;
+};
+// Slots of a partial / reduced vector behind the K per-group sums.
+//   RED_BOUND  data term of the bound;  RED_AUX  EM sparse: the share every group receives, RCG: the gradient norm;
+//   RED_FAULT  > 0 when a class normaliser left the representable range on ANY rank (summed by the all-reduce, so that
+//              every rank takes the same decision).
+constexpr int RED_BOUND = 0, RED_AUX = 1, RED_FAULT = 2, RED_EXTRA = 3;
+constexpr int RED_SEGS = 8;
+
+// TPR threads per row.  TPR >= 32: whole warps per row.  TPR = 4 / 8 / 16: several rows per warp (short rows).
 template <int TPR_, int KITER_, int R_> struct Tile {
   static constexpr int TPR = TPR_, KITER = KITER_, R = R_;
   static constexpr int NT = TPR < 256 ? (256 / TPR) * TPR : TPR;   // as many whole row groups as fit in 256 threads
   static constexpr int G = NT / TPR;
   static constexpr int NW = NT / 32;
-  static constexpr int WPG = TPR / 32;   // warps per row group
+  static constexpr int WPG = TPR / 32;            // warps per row group (0: the row group is a segment of a warp)
+  static constexpr int W = TPR < 32 ? TPR : 32;   // lanes of one warp that work on the same rows
+  static_assert(TPR >= 32 || (32 % TPR == 0 && R <= TPR), "sub-warp row groups: TPR divides 32 and R <= TPR");
 };
 
 // Barrier over the TPR threads of one row group: a named barrier (bar.sync id, count) when the CTA holds several groups,
@@ -131,10 +164,10 @@ template <int NSRC> struct RowPipe {
   }
 };
 
-// ---- per-CTA partial vector: fold the G row groups in group order, then one coalesced store ---------
+// ---- per-CTA partial vector: fold the row groups in a fixed order, then one coalesced store ----------
 // acc[i][v] belongs to column VEC*(t + TPR*i) + v.  comb: TPR*KITER*VEC doubles when G > 1.
 template <class TL, int VEC>
-__device__ __forceinline__ void store_partials(const double (&acc)[TL::KITER][VEC], double *comb, double *out, int K) {
+__device__ __forceinline__ void store_partials(const double (&acc_in)[TL::KITER][VEC], double *comb, double *out, int K) {
   const int t = threadIdx.x % TL::TPR, g = threadIdx.x / TL::TPR;
   if constexpr (TL::G == 1) {
 #pragma unroll
@@ -142,8 +175,36 @@ __device__ __forceinline__ void store_partials(const double (&acc)[TL::KITER][VE
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const int k = VEC * (t + TL::TPR * i) + v;
-        if (k < K) out[k] = acc[i][v];
+        if (k < K) out[k] = acc_in[i][v];
       }
+  } else if constexpr (TL::TPR < 32) {
+    // the row groups of a warp hold the same columns TPR lanes apart: butterfly over them first (fixed order), then
+    // the warps in warp order through shared memory
+    double acc[TL::KITER][VEC];
+#pragma unroll
+    for (int i = 0; i < TL::KITER; ++i)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        double a = acc_in[i][v];
+#pragma unroll
+        for (int off = 16; off >= TL::TPR; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        acc[i][v] = a;
+      }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int ww = 0; ww < TL::NW; ++ww) {
+      __syncthreads();
+      if (warp == ww && lane < TL::TPR) {
+#pragma unroll
+        for (int i = 0; i < TL::KITER; ++i)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const int c = VEC * (lane + TL::TPR * i) + v;
+            comb[c] = ww == 0 ? acc[i][v] : comb[c] + acc[i][v];
+          }
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += TL::NT) out[k] = comb[k];
   } else {
     for (int gg = 0; gg < TL::G; ++gg) {      // fixed order: bit-reproducible
       __syncthreads();
@@ -153,7 +214,7 @@ __device__ __forceinline__ void store_partials(const double (&acc)[TL::KITER][VE
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
             const int c = VEC * (t + TL::TPR * i) + v;
-            comb[c] = gg == 0 ? acc[i][v] : comb[c] + acc[i][v];
+            comb[c] = gg == 0 ? acc_in[i][v] : comb[c] + acc_in[i][v];
           }
       }
     }
@@ -175,52 +236,248 @@ struct PipeGeom { int stages, stage_rows; unsigned stage_pitch; };
 extern __shared__ __align__(128) unsigned char g_dyn_smem[];
 
 // =====================================================================================================
+// Reductions of R per-row values over the W lanes that share the rows (W = 32, or the TPR lanes of a sub-warp group).
+// A transposing butterfly: while more than one row is left a lane keeps half of the rows and hands the other half
+// to its partner (n/2 shuffles per step instead of n), then plain xor steps.  R - 1 + log2(W / R) 64-bit shuffles
+// instead of R log2(W).  On return every lane holds the total of row row_of_lane(lane), W / R lanes per row.
+// =====================================================================================================
+template <bool IS_MAX> __device__ __forceinline__ double red_op(double a, double b) { return IS_MAX ? fmax(a, b) : a + b; }
+
+template <int N, int OFF, bool IS_MAX> struct RowsRed {
+  static __device__ __forceinline__ double run(const double (&v)[N], int lane) {
+    if constexpr (OFF == 0) {
+      static_assert(N == 1, "rows per batch must not exceed the lanes that share them");
+      return v[0];
+    } else if constexpr (N > 1) {
+      const bool hi = (lane & OFF) != 0;
+      double nxt[N / 2];
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i) {
+        const double keep = hi ? v[i + N / 2] : v[i], send = hi ? v[i] : v[i + N / 2];
+        nxt[i] = red_op<IS_MAX>(keep, __shfl_xor_sync(0xffffffffu, send, OFF));
+      }
+      return RowsRed<N / 2, OFF / 2, IS_MAX>::run(nxt, lane);
+    } else {
+      const double nxt[1] = {red_op<IS_MAX>(v[0], __shfl_xor_sync(0xffffffffu, v[0], OFF))};
+      return RowsRed<1, OFF / 2, IS_MAX>::run(nxt, lane);
+    }
+  }
+};
+// the row whose total a lane holds after RowsRed<R, W/2>: the lane's transposing bits (W/2, W/4, ...), MSB first
+template <int W, int R> __device__ __forceinline__ int row_of_lane(int lane) {
+  int rid = 0;
+#pragma unroll
+  for (int n = R, off = W / 2; n > 1; n >>= 1, off >>= 1) rid = (rid << 1) | ((lane & off) ? 1 : 0);
+  return rid;
+}
+// lane (inside its W-lane segment) that canonically holds row r: its transposing bits spell r, the others are 0
+template <int W, int R> __device__ __forceinline__ int holder_lane(int r) {
+  int l = 0;
+#pragma unroll
+  for (int n = R, off = W / 2; n > 1; n >>= 1, off >>= 1) l |= (r & (n >> 1)) ? off : 0;
+  return l;
+}
+
+// Reduce R per-row values over the TPR threads of a row group (sum or max).  On return the lanes with
+// (lane % W) < R hold the group-wide result of row (lane % W); other lanes hold unspecified values.
+// scratch: 2 * NW * R doubles (used only when a row spans several warps).
+template <class TL, bool IS_MAX>
+__device__ __forceinline__ double rows_reduce(const double (&v)[TL::R], double *scratch, int &phase, int lane, int warp) {
+  constexpr int R = TL::R, W = TL::W;
+  static_assert(R == 1 || R == 2 || R == 4 || R == 8, "rows per batch must be 1, 2, 4 or 8");
+  const double k = RowsRed<R, W / 2, IS_MAX>::run(v, lane);
+  if constexpr (TL::WPG > 1) {
+    double *buf = scratch + phase * (TL::NW * R);
+    phase ^= 1;
+    if ((lane & (32 / R - 1)) == 0) buf[warp * R + row_of_lane<32, R>(lane)] = k;   // the canonical holder of every row
+    group_sync<TL>(warp / TL::WPG);
+    double tot = IS_MAX ? -INFINITY : 0.0;
+    if (lane < R) {
+      const int w0 = (warp / TL::WPG) * TL::WPG;
+#pragma unroll
+      for (int ww = 0; ww < TL::WPG; ++ww) tot = red_op<IS_MAX>(tot, buf[(w0 + ww) * R + lane]);
+    }
+    return tot;
+  } else {
+    return __shfl_sync(0xffffffffu, k, holder_lane<W, R>((lane % W) & (R - 1)), W);
+  }
+}
+
+// =====================================================================================================
+// Tails: the last CTA of a sweep sums the per-CTA partial vectors and, on one GPU, takes the control step.
+// =====================================================================================================
+// True in exactly one CTA of the launch: the one whose ticket shows that every other CTA has stored (and fenced)
+// its partial vector.  Must be reached by all threads of every CTA that did not exit early.
+__device__ __forceinline__ bool cta_is_last(ViCtl *ctl) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  const bool last = s_last != 0;
+  if (last) __threadfence();
+  return last;
+}
+
+// red[v] = sum over CTAs of partials[cta][v], v < nvals, CTAs in ascending order (whoever runs this: same bits).
+__device__ __forceinline__ void reduce_partials(const double *partials, int pstride, int n_ctas, int nvals, double *red,
+                                                int v_begin, int v_stride) {
+  for (int v = v_begin; v < nvals; v += v_stride) {
+    double a = 0.0;
+    const double *p = partials + v;
+#pragma unroll 8
+    for (int c = 0; c < n_ctas; ++c) a += __ldcg(p + (size_t)c * pstride);
+    red[v] = a;
+  }
+}
+// The same sum taken by ONE CTA (the last of a sweep).  With few columns the CTAs are cut into up to RED_SEGS
+// segments so that every thread has loads in flight: thread (segment, column) sums its segment in CTA order, the
+// segments are then added in segment order — a fixed order for a given (NT, nvals, n_ctas).
+template <int NT>
+__device__ __forceinline__ void reduce_partials_cta(const double *partials, int pstride, int n_ctas, int nvals, double *red,
+                                                    double *seg) {
+  const int nseg = min(RED_SEGS, NT / nvals);
+  if (nseg <= 1) { reduce_partials(partials, pstride, n_ctas, nvals, red, (int)threadIdx.x, NT); return; }
+  const int s = (int)threadIdx.x / nvals, v = (int)threadIdx.x % nvals;
+  const int per = (n_ctas + nseg - 1) / nseg;
+  if (s < nseg) {
+    double a = 0.0;
+    const int c0 = s * per, c1 = min(n_ctas, c0 + per);
+    const double *p = partials + v;
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) a += __ldcg(p + (size_t)c * pstride);
+    seg[(size_t)s * pstride + v] = a;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nvals) {
+    double a = 0.0;
+    for (int q = 0; q < nseg; ++q) a += seg[(size_t)q * pstride + threadIdx.x];
+    red[threadIdx.x] = a;
+  }
+}
+
+__device__ __forceinline__ void trace_push(const ViArrays &a, ViCtl *ctl, double gnorm, int reset) {
+  if (ctl->iter < a.trace_cap) {
+    a.trace_bound[ctl->iter] = ctl->bound;
+    a.trace_gnorm[ctl->iter] = gnorm;
+    a.trace_reset[ctl->iter] = (unsigned char)reset;
+  }
+}
+
+// EM: N_k, bound, convergence test, then the next digamma / weight vector.  All NT threads of one CTA.
+//   dense pass : red[k] = sum_j P(j,k) c_j / S_j (without w_k)                       N_k = alpha0 + w_k red[k]
+//   sparse pass: red[k] = sum over the hits of k of their extra responsibilities (with w_k),
+//                red[K + RED_AUX] = Z = sum_j P0_j c_j / S_j                          N_k = alpha0 + red[k] + w_k Z
+//   red[K + RED_BOUND] = sum_j c_j (log S_j + M_j).
+// (red[] is read with ld.cg: other CTAs of the same launch may have written it.)
+template <int NT>
+__device__ __forceinline__ void em_ctl_step(const ViArrays &a, ViCtl *ctl, int K, int sparse, double *scratch) {
+  double lg = 0.0, dga = 0.0;
+  const double z = __ldcg(a.red + K + RED_AUX);
+  for (int k = threadIdx.x; k < K; k += NT) {
+    const double rk = __ldcg(a.red + k);
+    const double A = sparse ? rk + a.w[k] * z : a.w[k] * rk;
+    const double nk = a.alpha0[k] + A;
+    a.N_k[k] = nk;
+    lg += lgamma(nk);
+    dga += a.dg[k] * A;
+  }
+  lg = block_sum<NT>(lg, scratch);
+  dga = block_sum<NT>(dga, scratch);
+  double mx = -INFINITY;
+  for (int k = threadIdx.x; k < K; k += NT) {
+    const double dg = digamma_series(a.N_k[k]);
+    a.dg_prev[k] = a.dg[k];
+    a.dg[k] = dg;
+    mx = fmax(mx, dg);
+  }
+  mx = block_max<NT>(mx, scratch);
+  for (int k = threadIdx.x; k < K; k += NT) a.w[k] = exp(a.dg[k] - mx);
+  if (threadIdx.x == 0) {
+    // log-normaliser of class j is log S_j + M_j + dg_max, and sum_k q (logl - gamma) = lse_j - sum_k q dg_k
+    const double data = __ldcg(a.red + K + RED_BOUND) + ctl->sum_counts * ctl->dg_max - dga;
+    const double bound = data + lg + ctl->bound_const;
+    ctl->oldbound = ctl->bound;
+    ctl->bound = bound;
+    trace_push(a, ctl, 0.0, 0);
+    ctl->iter += 1;
+    if (__ldcg(a.red + K + RED_FAULT) > 0.0) ctl->fault = 1;       // summed over ranks: the same decision everywhere
+    if (ctl->iter > 1 && fabs(bound - ctl->oldbound) < ctl->tol) ctl->converged = 1;
+    if (ctl->converged || ctl->iter >= ctl->max_iters || ctl->fault) ctl->done = 1;
+    ctl->dg_max = mx;
+  }
+}
+
+// RCG, after sweep B (stage 0) or after the restart sweep (stage 1).  All NT threads of one CTA.
+// red[k] = sum_j c_j q(j,k), red[K + RED_BOUND] = sum_jk c_j q (logl - gamma), red[K + RED_AUX] = the gradient norm
+// sweep A found (stage 0; the Fletcher-Reeves ratio sweep B used is recomputed from it and committed here).
+// stall_on_reject: several GPUs — a rejected step pauses the iterations (ctl->stall) until the host has enqueued the
+// restart; one GPU — the restart sweep sits behind every step and runs when ctl->didreset says so.
+template <int NT>
+__device__ __forceinline__ void rcg_ctl_b_step(const ViArrays &a, ViCtl *ctl, int K, int stage, int stall_on_reject,
+                                               double *scratch) {
+  __shared__ int s_accept;
+  double lg = 0.0;
+  for (int k = threadIdx.x; k < K; k += NT) lg += lgamma(a.alpha0[k] + __ldcg(a.red + k));
+  lg = block_sum<NT>(lg, scratch);
+  const double cand = __ldcg(a.red + K + RED_BOUND) + lg + ctl->bound_const;
+  if (threadIdx.x == 0) {
+    if (stage == 0) {
+      const double nn = __ldcg(a.red + K + RED_AUX);
+      ctl->beta = nn / ctl->oldnorm;
+      ctl->newnorm = nn;
+      ctl->oldnorm = nn;
+      ctl->didreset = 0;        // the flag of the PREVIOUS iteration has been consumed by sweep B
+    }
+    if (stage == 0 && cand < ctl->bound) {
+      // the conjugate direction lost ground: drop it, redo the step from the same N_k (restart sweep)
+      ctl->didreset = 1;
+      ctl->resets += 1;
+      if (stall_on_reject) ctl->stall = 1;
+      s_accept = 0;
+    } else {
+      s_accept = 1;
+      ctl->oldbound = ctl->bound;
+      ctl->bound = cand;
+      trace_push(a, ctl, ctl->newnorm, stage);
+      ctl->iter += 1;
+      ctl->stall = 0;
+      if (stage == 0 && cand - ctl->oldbound < ctl->tol) ctl->converged = 1;
+      if (ctl->converged || ctl->iter >= ctl->max_iters) ctl->done = 1;
+    }
+  }
+  __syncthreads();
+  if (!s_accept) return;
+  for (int k = threadIdx.x; k < K; k += NT) {
+    const double nk = a.alpha0[k] + __ldcg(a.red + k);
+    a.N_k[k] = nk;
+    a.dg[k] = digamma_series(nk) - 1.0;
+  }
+}
+
+// What an EM sweep does once its own partial vector is stored (sparse: 0 dense pass, 1 sparse pass).
+template <int NT>
+__device__ __forceinline__ void em_sweep_tail(int tail, int sparse, const ViArrays &a, ViCtl *ctl, const double *partials,
+                                              int pstride, int K, double *scratch) {
+  if (tail == 0) return;
+  if (!cta_is_last(ctl)) return;
+  reduce_partials_cta<NT>(partials, pstride, (int)gridDim.x, K + RED_EXTRA, a.red, a.seg);
+  if (threadIdx.x == 0) ctl->ticket = 0;
+  if (tail == 2) {
+    __syncthreads();
+    em_ctl_step<NT>(a, ctl, K, sparse, scratch);
+  }
+}
+
+// =====================================================================================================
 // EM / VB pass, linear domain.  P(j,k) = exp(logl(j,k) - M_j) is stored once; a pass is two GEMVs that
 // share one read of P:   S_j = sum_k P(j,k) w_k ,  A_k = sum_j P(j,k) c_j / S_j ,  with
 // w_k = exp(digamma(N_k) - max digamma).  Then N_k = alpha0_k + w_k A_k and the data term of the ELBO
-// is sum_j c_j (log S_j + M_j) (+ constants applied by the control kernel).  Two FMAs per element.
+// is sum_j c_j (log S_j + M_j) (+ constants applied by the control step).  Two FMAs per element.
 //
-// P, counts and rowmax are padded with zero rows to a multiple of 64 classes (ROW_PAD): a padded class
+// P, counts and rowmax are padded with zero rows to a multiple of ROW_PAD classes: a padded class
 // has c = 0 and drops out, so the sweep carries no row-bounds predicates at all.
 // =====================================================================================================
-constexpr int ROW_PAD = 64;
-
-// Sum R per-row partials over the 32 lanes with a transposing butterfly: 6 (R = 4), 6 (R = 2) or
-// 5 (R = 1) 64-bit shuffles instead of 5 R.  On return lane L holds in the result the warp total of
-// row rid(L); the lanes with (L & 7) == 0 are the canonical holders (row = holder_row(L)).
-template <int R> __device__ __forceinline__ double warp_rows_sum(const double (&s)[R], int lane, int &rid) {
-  double k;
-  if constexpr (R == 4) {
-    const bool hi = lane & 16, h8 = lane & 8;
-    double a0 = hi ? s[2] : s[0], a1 = hi ? s[3] : s[1];
-    const double b0 = hi ? s[0] : s[2], b1 = hi ? s[1] : s[3];
-    a0 += __shfl_xor_sync(0xffffffffu, b0, 16);
-    a1 += __shfl_xor_sync(0xffffffffu, b1, 16);
-    k = h8 ? a1 : a0;
-    const double snd = h8 ? a0 : a1;
-    k += __shfl_xor_sync(0xffffffffu, snd, 8);
-    rid = (hi ? 2 : 0) + (h8 ? 1 : 0);
-  } else if constexpr (R == 2) {
-    const bool hi = lane & 16;
-    k = hi ? s[1] : s[0];
-    const double snd = hi ? s[0] : s[1];
-    k += __shfl_xor_sync(0xffffffffu, snd, 16);
-    k += __shfl_xor_sync(0xffffffffu, k, 8);
-    rid = hi ? 1 : 0;
-  } else {
-    static_assert(R == 1, "R must be 1, 2 or 4");
-    k = s[0];
-    k += __shfl_xor_sync(0xffffffffu, k, 16);
-    k += __shfl_xor_sync(0xffffffffu, k, 8);
-    rid = 0;
-  }
-  k += __shfl_xor_sync(0xffffffffu, k, 4);
-  k += __shfl_xor_sync(0xffffffffu, k, 2);
-  k += __shfl_xor_sync(0xffffffffu, k, 1);
-  return k;
-}
-// lane that canonically holds row r after warp_rows_sum<R>
-template <int R> __device__ __forceinline__ int holder_lane(int r) { return R == 4 ? 16 * (r >> 1) + 8 * (r & 1) : (R == 2 ? 16 * r : 0); }
 
 // Two CTAs per SM when the two register buffers, the accumulators and the weights leave room within 128
 // registers per thread (estimate in 32-bit registers: 2 buffers x R x KITER x 4, KITER x VEC doubles, KITER x VEC weights).
@@ -236,18 +493,21 @@ template <typename ST, class TL> constexpr int em_min_blocks() {
 template <typename ST, class TL, bool PIPE>
 __global__ void __launch_bounds__(TL::NT, em_min_blocks<ST, TL>())
 em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ rowmax, const double *__restrict__ counts,
-                   const double *__restrict__ w, const ViCtl *__restrict__ ctl, double *__restrict__ partials,
-                   int pstride, unsigned long long N_pad, int K, PipeGeom geom) {
+                   ViArrays arrays, ViCtl *ctl, double *partials, int pstride, unsigned long long N_pad, int K,
+                   PipeGeom geom, int tail) {
   using VT = typename VecOf<ST>::type;
   constexpr int VEC = VecOf<ST>::VEC;
-  constexpr int R = TL::R, KITER = TL::KITER, TPR = TL::TPR, WPG = TL::WPG;
+  constexpr int R = TL::R, KITER = TL::KITER, TPR = TL::TPR, WPG = TL::WPG, W = TL::W;
   constexpr int RB = TL::G * R;                       // rows per CTA batch
+  static_assert(ROW_PAD % RB == 0, "ROW_PAD must be a multiple of the rows of one CTA batch");
   if (ctl->done) return;
   __shared__ double s_red[2 * TL::NW * R];
   __shared__ double s_comb[TL::G > 1 ? TPR * KITER * VEC : 1];
   __shared__ double s_blk[32];
+  const double *w = arrays.w;                         // (rewritten by the control step of the tail: no __restrict__)
   const int t = threadIdx.x % TPR, g = threadIdx.x / TPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tl = lane % W;                            // lane inside the segment that shares the rows
   const int nvec = ld / VEC;
 
   ST wv[KITER][VEC];
@@ -270,7 +530,14 @@ em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ 
   int fault = 0;
   int phase = 0;
 
-  // ---- one batch: pv = this thread's pieces of R rows, c_lane = count of row (row0 + lane) for lane < R
+  // Which row of the batch this lane normalises.  Rows that span warps: lanes 0..R-1 of every warp (the first warp
+  // of the group adds the bound term).  Rows inside a warp: every lane the row its transposing bits spell (W / R lanes
+  // per row compute the same division; the canonical holder adds the bound term).
+  const int my_row = WPG > 1 ? lane : row_of_lane<W, R>(lane);
+  const bool my_active = WPG > 1 ? lane < R : true;
+  const bool my_elbo = WPG > 1 ? t < 32 : tl == holder_lane<W, R>(my_row);
+
+  // ---- one batch: pv = this thread's pieces of R rows, c_lane = count of row (row0 + my_row)
   auto process = [&](const VT (&pv)[R][KITER], double c_lane, unsigned long long row0) {
     double s[R];
 #pragma unroll
@@ -290,13 +557,12 @@ em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ 
       for (int v = 1; v < VEC; ++v) tot += a[v];
       s[r] = (double)tot;
     }
-    int rid;
-    double k = warp_rows_sum<R>(s, lane, rid);
+    const double k = RowsRed<R, W / 2, false>::run(s, lane);
     double tot;
     if constexpr (WPG > 1) {
       double *buf = s_red + phase * (TL::NW * R);
       phase ^= 1;
-      if ((lane & (R == 4 ? 7 : (R == 2 ? 15 : 31))) == 0) buf[warp * R + rid] = k;
+      if ((lane & (32 / R - 1)) == 0) buf[warp * R + row_of_lane<32, R>(lane)] = k;
       group_sync<TL>(g);
       tot = 0.0;
       if (lane < R) {
@@ -305,22 +571,20 @@ em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ 
         for (int ww = 0; ww < WPG; ++ww) tot += buf[(w0 + ww) * R + lane];
       }
     } else {
-      // lane r fetches the total of row r from its holder
-      const int src = R == 4 ? 16 * ((lane >> 1) & 1) + 8 * (lane & 1) : (R == 2 ? 16 * (lane & 1) : 0);
-      tot = __shfl_sync(0xffffffffu, k, src);
+      tot = k;                                  // every lane already holds the total of row my_row
     }
-    // lanes 0..R-1: row r = lane.  One division per warp serves the whole batch.
+    // One division per row serves the whole batch.
     double inv_l = 0.0;
-    if (lane < R && c_lane > 0.0) {
+    if (my_active && c_lane > 0.0) {
       if (!(tot > 0.0) || isinf(tot)) fault = 1;
       else {
         inv_l = c_lane / tot;
-        if (t < 32) elbo += c_lane * (log(tot) + rowmax[row0 + lane]);
+        if (my_elbo) elbo += c_lane * (log(tot) + rowmax[row0 + my_row]);
       }
     }
     ST inv[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) inv[r] = (ST)__shfl_sync(0xffffffffu, inv_l, r);
+    for (int r = 0; r < R; ++r) inv[r] = (ST)__shfl_sync(0xffffffffu, inv_l, WPG > 1 ? r : holder_lane<W, R>(r), W);
     // A_k += sum_r P(r,k) c_r / S_r: the R-row partial in storage precision, the running sum in fp64
 #pragma unroll
     for (int i = 0; i < KITER; ++i) {
@@ -352,7 +616,7 @@ em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ 
 #pragma unroll
         for (int i = 0; i < KITER; ++i)
           if (inr[i]) buf[r][i] = ld_stream(p + (size_t)r * nvec + i * TPR);
-      c_lane = lane < R ? counts[row0 + lane] : 0.0;
+      c_lane = my_active ? counts[row0 + my_row] : 0.0;
     };
     VT bufA[R][KITER], bufB[R][KITER];
 #pragma unroll
@@ -401,89 +665,36 @@ em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ 
           for (int i = 0; i < KITER; ++i)
             pv[r][i] = inr[i] ? reinterpret_cast<const VT *>(sp + (size_t)(lrow0 + r) * pipe.row_bytes)[t + TPR * i] : zero;
         const unsigned long long row0 = stage_row0 + lrow0;
-        process(pv, lane < R ? counts[row0 + lane] : 0.0, row0);
+        process(pv, my_active ? counts[row0 + my_row] : 0.0, row0);
       }
     });
   }
   double *out = partials + (unsigned long long)blockIdx.x * pstride;
   store_partials<TL, VEC>(acc, s_comb, out, K);
   elbo = block_sum<TL::NT>(elbo, s_blk);
-  if (threadIdx.x == 0) { out[K] = elbo; out[K + 1] = 0.0; }
-  if (fault) atomicExch(const_cast<int *>(&ctl->fault), 1);
+  const int any_fault = __syncthreads_or(fault);
+  if (threadIdx.x == 0) { out[K + RED_BOUND] = elbo; out[K + RED_AUX] = 0.0; out[K + RED_FAULT] = any_fault ? 1.0 : 0.0; }
+  em_sweep_tail<TL::NT>(tail, 0, arrays, ctl, partials, pstride, K, s_blk);
 }
 
 // =====================================================================================================
-// Log-domain sweeps (fp64): the RCG optimiser, the restart step, and the log-domain EM pass.
+// Log-domain sweeps (fp64): the RCG optimiser and its restart step.
 // =====================================================================================================
-
-// Reduce R per-row values over the TPR threads of a row group (sum or max).  On return lanes 0..R-1 of every
-// warp of the group hold the group-wide result of row `lane`; other lanes hold unspecified values.
-// Transposing butterfly inside the warp (6 / 6 / 5 64-bit shuffles for R = 4 / 2 / 1), then one
-// shared-memory hop when the row spans several warps.  scratch: 2 * NW * R doubles.
-template <bool IS_MAX> __device__ __forceinline__ double red_op(double a, double b) { return IS_MAX ? fmax(a, b) : a + b; }
-
-template <class TL, bool IS_MAX>
-__device__ __forceinline__ double rows_reduce(const double (&v)[TL::R], double *scratch, int &phase, int lane, int warp) {
-  constexpr int R = TL::R;
-  static_assert(R == 1 || R == 2 || R == 4, "rows per batch must be 1, 2 or 4");
-  double k;
-  int rid;
-  if constexpr (R == 4) {
-    const bool hi = lane & 16, h8 = lane & 8;
-    double a0 = hi ? v[2] : v[0], a1 = hi ? v[3] : v[1];
-    const double b0 = hi ? v[0] : v[2], b1 = hi ? v[1] : v[3];
-    a0 = red_op<IS_MAX>(a0, __shfl_xor_sync(0xffffffffu, b0, 16));
-    a1 = red_op<IS_MAX>(a1, __shfl_xor_sync(0xffffffffu, b1, 16));
-    k = h8 ? a1 : a0;
-    const double snd = h8 ? a0 : a1;
-    k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, snd, 8));
-    rid = (hi ? 2 : 0) + (h8 ? 1 : 0);
-  } else if constexpr (R == 2) {
-    const bool hi = lane & 16;
-    k = hi ? v[1] : v[0];
-    const double snd = hi ? v[0] : v[1];
-    k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, snd, 16));
-    k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 8));
-    rid = hi ? 1 : 0;
-  } else {
-    k = v[0];
-    k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 16));
-    k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 8));
-    rid = 0;
-  }
-  k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 4));
-  k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 2));
-  k = red_op<IS_MAX>(k, __shfl_xor_sync(0xffffffffu, k, 1));
-  if constexpr (TL::WPG > 1) {
-    double *buf = scratch + phase * (TL::NW * R);
-    phase ^= 1;
-    if ((lane & (R == 4 ? 7 : (R == 2 ? 15 : 31))) == 0) buf[warp * R + rid] = k;
-    group_sync<TL>(warp / TL::WPG);
-    double tot = IS_MAX ? -INFINITY : 0.0;
-    if (lane < R) {
-      const int w0 = (warp / TL::WPG) * TL::WPG;
-#pragma unroll
-      for (int ww = 0; ww < TL::WPG; ++ww) tot = red_op<IS_MAX>(tot, buf[(w0 + ww) * R + lane]);
-    }
-    return tot;
-  } else {
-    const int src = R == 4 ? 16 * ((lane >> 1) & 1) + 8 * (lane & 1) : (R == 2 ? 16 * (lane & 1) : 0);
-    return __shfl_sync(0xffffffffu, k, src);
-  }
-}
 
 // Sweep A of an RCG iteration ("mixt_negnatgrad"): d = logl + (digamma(N_k) - 1) - gamma,
 // newnorm = sum_jk q (d - <d>_j) d  with q = exp(gamma), <d>_j = sum_k q d.  Nothing is written: d is
-// recomputed by sweep B, which saves 16 B/element of traffic over storing it.
+// recomputed by sweep B, which saves 16 B/element of traffic over storing it.  The last CTA to finish sums
+// the per-CTA norms into red[K + RED_AUX] (one value per CTA: always cheap).
 template <class TL, bool PIPE>
 __global__ void __launch_bounds__(TL::NT, TL::NT > 256 ? 1 : (TL::R * TL::KITER <= 4 ? 3 : (TL::R * TL::KITER <= 8 ? 2 : 1)))
 rcg_sweep_a_kernel(const double *__restrict__ logl, const double *__restrict__ gamma, int ld,
-                   const double *__restrict__ dgm1, const ViCtl *__restrict__ ctl, double *__restrict__ partials,
+                   ViArrays arrays, ViCtl *ctl, double *partials,
                    int pstride, unsigned long long N, int K, PipeGeom geom) {
-  constexpr int R = TL::R, KITER = TL::KITER, TPR = TL::TPR;
-  if (ctl->done) return;
+  constexpr int R = TL::R, KITER = TL::KITER, TPR = TL::TPR, W = TL::W;
+  if (ctl->done || ctl->stall) return;
   __shared__ double s_red[2 * TL::NW * R];
   __shared__ double s_blk[32];
+  const double *dgm1 = arrays.dg;
   const int t = threadIdx.x % TPR, g = threadIdx.x / TPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = ld / 2;
@@ -506,24 +717,49 @@ rcg_sweep_a_kernel(const double *__restrict__ logl, const double *__restrict__ g
   auto body = [&](auto &&load, unsigned long long row0) {   // load(src, r, idx): src 0 = logl, 1 = gamma
     double d[R][KITER][2], q[R][KITER][2];
     double s[R];
-    if (warp_cols_ok && row0 + R <= N) {
-      // fast path (warp-uniform): every row and column this warp touches is real — no predicates
+    // Three flavours (no shuffles inside: the row groups of a warp may take different ones at the ragged end):
+    // every row and column real — no predicates; rows real, columns ragged (K not a multiple of the tile width) —
+    // per-thread column flags only; ragged rows — everything predicated.
+    if (row0 + R <= N) {
+      if (warp_cols_ok) {
 #pragma unroll
-      for (int r = 0; r < R; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int i = 0; i < KITER; ++i) { unpack(load(0, r, t + TPR * i), d[r][i]); unpack(load(1, r, t + TPR * i), q[r][i]); }
+          for (int i = 0; i < KITER; ++i) { unpack(load(0, r, t + TPR * i), d[r][i]); unpack(load(1, r, t + TPR * i), q[r][i]); }
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        s[r] = 0.0;
+        for (int r = 0; r < R; ++r) {
+          s[r] = 0.0;
 #pragma unroll
-        for (int i = 0; i < KITER; ++i)
+          for (int i = 0; i < KITER; ++i)
 #pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            const double gam = q[r][i][v];
-            d[r][i][v] = d[r][i][v] + dk[i][v] - gam;
-            q[r][i][v] = exp_nonpos(gam);
-            s[r] = fma(d[r][i][v], q[r][i][v], s[r]);
+            for (int v = 0; v < 2; ++v) {
+              const double gam = q[r][i][v];
+              d[r][i][v] = d[r][i][v] + dk[i][v] - gam;
+              q[r][i][v] = exp_nonpos(gam);
+              s[r] = fma(d[r][i][v], q[r][i][v], s[r]);
+            }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int i = 0; i < KITER; ++i) {
+            if (t + TPR * i < nvec) { unpack(load(0, r, t + TPR * i), d[r][i]); unpack(load(1, r, t + TPR * i), q[r][i]); }
+            else { d[r][i][0] = d[r][i][1] = 0.0; q[r][i][0] = q[r][i][1] = 0.0; }
           }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          s[r] = 0.0;
+#pragma unroll
+          for (int i = 0; i < KITER; ++i)
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              const double gam = q[r][i][v];
+              d[r][i][v] = ok[i][v] ? d[r][i][v] + dk[i][v] - gam : 0.0;
+              q[r][i][v] = ok[i][v] ? exp_nonpos(gam) : 0.0;
+              s[r] = fma(d[r][i][v], q[r][i][v], s[r]);
+            }
+        }
       }
     } else {
 #pragma unroll
@@ -553,7 +789,7 @@ rcg_sweep_a_kernel(const double *__restrict__ logl, const double *__restrict__ g
     const double tot = rows_reduce<TL, false>(s, s_red, phase, lane, warp);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const double sr = __shfl_sync(0xffffffffu, tot, r);
+      const double sr = __shfl_sync(0xffffffffu, tot, r, W);
 #pragma unroll
       for (int i = 0; i < KITER; ++i)
 #pragma unroll
@@ -591,29 +827,40 @@ rcg_sweep_a_kernel(const double *__restrict__ logl, const double *__restrict__ g
     });
   }
   nn = block_sum<TL::NT>(nn, s_blk);
-  if (threadIdx.x == 0) partials[(unsigned long long)blockIdx.x * pstride + K + 1] = nn;
+  if (threadIdx.x == 0) partials[(unsigned long long)blockIdx.x * pstride + K + RED_AUX] = nn;
+  if (cta_is_last(ctl)) {
+    double a = 0.0;
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += TL::NT) a += __ldcg(partials + (size_t)c * pstride + K + RED_AUX);
+    a = block_sum<TL::NT>(a, s_blk);
+    if (threadIdx.x == 0) { arrays.red[K + RED_AUX] = a; ctl->ticket = 0; }
+  }
 }
 
 // Sweep B of an RCG iteration: step = d (+ beta * oldstep), gamma += step, renormalise every class,
 // store gamma and step, accumulate N_k - alpha0 = sum_j c_j q and the data term of the ELBO.
-// MODE 0: RCG step.  MODE 1: plain step from the current digamma vector, gamma = normalise(logl + dg)
-// (the RCG restart, and the log-domain EM pass); WRITE says whether gamma is stored.
+// MODE 0: RCG step; the Fletcher-Reeves ratio beta = newnorm / oldnorm comes from the (all-reduced) norm of sweep A
+// in red[K + RED_AUX], recomputed by every CTA (the control step after the sweep commits it).
+// MODE 1: plain step from the current digamma vector, gamma = normalise(logl + dg) (the RCG restart).
 template <class TL, int MODE, bool WRITE, bool PIPE>
 __global__ void __launch_bounds__(TL::NT, TL::R * TL::KITER <= 4 && TL::NT <= 256 ? 2 : 1)
 rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, double *__restrict__ step, int ld,
-                   const double *__restrict__ dgv, const double *__restrict__ counts, const ViCtl *__restrict__ ctl,
-                   double *__restrict__ partials, int pstride, unsigned long long N, int K, int only_if_reset,
-                   PipeGeom geom) {
-  constexpr int R = TL::R, KITER = TL::KITER, TPR = TL::TPR;
+                   ViArrays arrays, const double *__restrict__ counts, ViCtl *ctl,
+                   double *partials, int pstride, unsigned long long N, int K, int only_if_reset,
+                   PipeGeom geom, int tail) {
+  constexpr int R = TL::R, KITER = TL::KITER, TPR = TL::TPR, W = TL::W;
   if (ctl->done) return;
-  if (only_if_reset && !ctl->didreset) return;
+  if (only_if_reset ? !ctl->didreset : ctl->stall != 0) return;
   __shared__ double s_red[2 * TL::NW * R];
   __shared__ double s_comb[TL::G > 1 ? TPR * KITER * 2 : 1];
   __shared__ double s_blk[32];
+  const double *dgv = arrays.dg;
   const int t = threadIdx.x % TPR, g = threadIdx.x / TPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool use_old = MODE == 0 && ctl->use_old != 0;
-  const double beta_eff = use_old ? ctl->beta : 0.0;   // step = d + beta * oldstep; no direction memory -> beta 0
+  const int tl = lane % W;
+  // the direction memory is empty before the first accepted step (the reference starts it at zero) and after a restart
+  const double beta = MODE == 0 ? arrays.red[K + RED_AUX] / ctl->oldnorm : 0.0;
+  const bool use_old = MODE == 0 && !ctl->didreset && beta > 0.0 && ctl->iter > 0;
+  const double beta_eff = use_old ? beta : 0.0;   // step = d + beta * oldstep; no direction memory -> beta 0
   const int nvec = ld / 2;
   const double NEG_INF = -INFINITY;
   double dk[KITER][2];
@@ -634,25 +881,26 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
   double bound = 0.0;
   int phase = 0;
 
-  // One batch = three element-wise phases separated by two row reductions.  The phases exist in two
-  // compile-time flavours: FULL (every row and column this WARP touches is real: no predicates, the loads of a
-  // batch issue back to back) and the predicated one for ragged edges.  The choice is warp-uniform and the
-  // reductions (shuffles with a full mask, __syncthreads) sit outside the flavoured code, in common control flow.
+  // One batch = three element-wise phases separated by two row reductions.  The phases exist in three
+  // compile-time flavours: every row and column this thread touches is real (no predicates, the loads of a batch issue
+  // back to back); rows real but columns ragged (K not a multiple of the tile width: per-thread column flags only); and
+  // the fully predicated one for the last rows.  The reductions (shuffles with a full mask, barriers) sit outside the
+  // flavoured code, in common control flow.
   const bool warp_cols_ok = __all_sync(0xffffffffu, cols_ok) != 0;
   auto body = [&](auto &&load, unsigned long long row0) {   // load(src, r, idx): 0 = logl, 1 = gamma, 2 = old step
-    const bool full = warp_cols_ok && row0 + R <= N;        // uniform over the warp (a warp never spans two row groups)
+    const bool rows_ok = row0 + R <= N;
     double l[R][KITER][2], gn[R][KITER][2], m[R];
     double e[R][KITER][2], sum[R], lsum[R], cinv[R];
 
-    // FULL is a literal at both call sites; the lambda is inlined and specialised for it
-    auto phase1 = [&](const bool FULL) {
+    // ROWS / COLS are literals at the call sites; the lambdas are inlined and specialised for them
+    auto phase1 = [&](const bool ROWS, const bool COLS) {
       double st[R][KITER][2];
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int i = 0; i < KITER; ++i) {
           const int idx = t + TPR * i;
-          const bool in = FULL || (row0 + r < N && idx < nvec);
+          const bool in = (ROWS || row0 + r < N) && (COLS || idx < nvec);
           if (in) unpack(load(0, r, idx), l[r][i]); else l[r][i][0] = l[r][i][1] = 0.0;
           if (MODE == 0) { if (in) unpack(load(1, r, idx), gn[r][i]); else gn[r][i][0] = gn[r][i][1] = 0.0; }
         }
@@ -662,7 +910,7 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
 #pragma unroll
           for (int i = 0; i < KITER; ++i) {
             const int idx = t + TPR * i;
-            const bool in = FULL || (row0 + r < N && idx < nvec);
+            const bool in = (ROWS || row0 + r < N) && (COLS || idx < nvec);
             if (in) unpack(load(2, r, idx), st[r][i]); else st[r][i][0] = st[r][i][1] = 0.0;
           }
       } else {
@@ -682,7 +930,7 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
           const int idx = t + TPR * i;
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
-            const bool on = FULL || (row < N && ok[i][v]);
+            const bool on = (ROWS || row < N) && (COLS || ok[i][v]);
             double g2;
             if (MODE == 0) {
               const double d = l[r][i][v] + dk[i][v] - gn[r][i][v];
@@ -695,25 +943,25 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
             gn[r][i][v] = on ? g2 : NEG_INF;
             m[r] = fmax(m[r], gn[r][i][v]);
           }
-          if (MODE == 0 && (FULL || (row < N && idx < nvec))) st_stream(sp + idx, make_double2(st[r][i][0], st[r][i][1]));
+          if (MODE == 0 && (ROWS || row < N) && (COLS || idx < nvec)) st_stream(sp + idx, make_double2(st[r][i][0], st[r][i][1]));
         }
       }
     };
-    auto phase3 = [&](const bool FULL) {
+    auto phase3 = [&](const bool ROWS, const bool COLS) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const unsigned long long row = row0 + r;
-        if (!FULL && row >= N) continue;
+        if (!ROWS && row >= N) continue;
         double2 *gp = reinterpret_cast<double2 *>(gamma) + row * (unsigned long long)nvec;
 #pragma unroll
         for (int i = 0; i < KITER; ++i) {
           const int idx = t + TPR * i;
-          if (!FULL && idx >= nvec) continue;
+          if (!COLS && idx >= nvec) continue;
           double gout[2];
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
             const double g2 = gn[r][i][v] - lsum[r];     // normalised log-responsibility
-            gout[v] = (FULL || ok[i][v]) ? g2 : 0.0;
+            gout[v] = (COLS || ok[i][v]) ? g2 : 0.0;
             const double cq = cinv[r] * e[r][i][v];      // c_j q(j,k); 0 for unobserved classes and padding
             acc[i][v] += cq;
             if (cq > 0.0) bound = fma(cq, l[r][i][v] - g2, bound);
@@ -723,11 +971,11 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
       }
     };
 
-    if (full) phase1(true); else phase1(false);
+    if (rows_ok) { if (warp_cols_ok) phase1(true, true); else phase1(true, false); } else phase1(false, false);
     const double mt = rows_reduce<TL, true>(m, s_red, phase, lane, warp);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      double mm = __shfl_sync(0xffffffffu, mt, r);
+      double mm = __shfl_sync(0xffffffffu, mt, r, W);
       mm = mm == NEG_INF ? 0.0 : mm;                     // a row past the end: keep the arithmetic finite
       sum[r] = 0.0;
 #pragma unroll
@@ -740,18 +988,18 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
         }
     }
     const double tot = rows_reduce<TL, false>(sum, s_red, phase, lane, warp);
-    // lanes 0..R-1: one log, one division and one count load per warp serve the whole batch
+    // lanes 0..R-1 of the segment: one log, one division and one count load per row serve the whole batch
     double lsum_l = 0.0, cinv_l = 0.0;
-    if (lane < R && row0 + lane < N) {
+    if (tl < R && row0 + tl < N) {
       lsum_l = log(tot);
-      cinv_l = counts[row0 + lane] / tot;
+      cinv_l = counts[row0 + tl] / tot;
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      lsum[r] = __shfl_sync(0xffffffffu, lsum_l, r);
-      cinv[r] = __shfl_sync(0xffffffffu, cinv_l, r);
+      lsum[r] = __shfl_sync(0xffffffffu, lsum_l, r, W);
+      cinv[r] = __shfl_sync(0xffffffffu, cinv_l, r, W);
     }
-    if (full) phase3(true); else phase3(false);
+    if (rows_ok) { if (warp_cols_ok) phase3(true, true); else phase3(true, false); } else phase3(false, false);
   };
 
   if constexpr (!PIPE) {
@@ -791,82 +1039,208 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
   double *out = partials + (unsigned long long)blockIdx.x * pstride;
   store_partials<TL, 2>(acc, s_comb, out, K);
   bound = block_sum<TL::NT>(bound, s_blk);
-  if (threadIdx.x == 0) out[K] = bound;
+  if (threadIdx.x == 0) out[K + RED_BOUND] = bound;
+  // Only the K per-group sums and the bound term are reduced here: slot RED_AUX of red[] holds the norm of sweep A,
+  // which the control step still needs.
+  if (tail != 0 && cta_is_last(ctl)) {
+    reduce_partials_cta<TL::NT>(partials, pstride, (int)gridDim.x, K + 1, arrays.red, arrays.seg);
+    if (threadIdx.x == 0) ctl->ticket = 0;
+    if (tail == 2) {
+      __syncthreads();
+      rcg_ctl_b_step<TL::NT>(arrays, ctl, K, MODE == 0 ? 0 : 1, 0, s_blk);
+    }
+  }
 }
 
 // =====================================================================================================
 // EM / VB pass over the SPARSE storage: class j is P0_j on every group except its hits, where it is P0_j + dP.
-//   S_j = P0_j W + sum_hits dP w_g          (W = sum_k w_k)
-//   A_k = Z + sum_{hits of k} dP c_j / S_j  (Z = sum_j P0_j c_j / S_j, the part every group receives)
-// One thread per class, the weight vector and the per-group accumulators in shared memory (fp64 atomics: the
-// only place on the path where the summation order, hence the last bits, can vary from run to run).
+//   S_j = P0_j W + sum_hits dP w_g                 (W = sum_k w_k)
+//   N_k - alpha0_k = w_k Z + sum_{hits of k} q     (Z = sum_j P0_j c_j / S_j, the part every group receives;
+//                                                   q = dP w_g c_j / S_j, the hit's extra responsibility)
+// One WARP per chunk of 32 consecutive classes.  The chunk's hits are one contiguous range of the hit arrays:
+// they are read with coalesced loads (hit-parallel), multiplied by the weight of their group and parked in shared
+// memory; lane l then adds up the hits of class l in list order (class-parallel) and takes the division and the
+// logarithm of its class; the scatter into the per-group accumulators is hit-parallel again.
+// The accumulators are 64-bit FIXED-POINT sums in shared memory, updated with two native 32-bit shared atomics
+// (low word, then high word + carry): |q| <= c_j, so with the scale 2^61 / 2^ceil(log2(sum_j c_j)) nothing can
+// overflow, integer addition is associative — the pass is bit-reproducible whatever order the atomics land in —
+// and no compare-and-swap loop is involved (sm_100 has no native 64-bit shared-memory add, integer or floating).
 // =====================================================================================================
-__global__ void __launch_bounds__(256)
+constexpr int SP_NT = 256;            // threads per CTA
+constexpr int SP_CHUNK = 32;          // classes per warp chunk
+constexpr int SP_STAGE = 224;         // hits a warp parks in shared memory at a time (a chunk averages ~4 per class)
+constexpr int SP_PF = 4;              // slabs of 32 hits of the NEXT chunk kept in flight in registers
+constexpr uint32_t SP_GRP_MASK = 0x00ffffffu;   // nz_grp: group in the low 24 bits, (class index & 31) in the top 8
+
+__device__ __forceinline__ void fx_atomic_add(unsigned *acc2 /* [lo, hi] */, long long x) {
+  const unsigned lo = (unsigned)(unsigned long long)x, hi = (unsigned)((unsigned long long)x >> 32);
+  const unsigned old = atomicAdd(&acc2[0], lo);
+  const unsigned carry = (old + lo) < old ? 1u : 0u;       // unsigned wrap-around of the low word
+  if (hi + carry != 0u) atomicAdd(&acc2[1], hi + carry);
+}
+
+// A warp walks a CONTIGUOUS run of chunks, so the hits of its next chunk start where those of the current one end:
+// while the arithmetic of chunk i runs, the per-class values of chunk i + 1 and the first SP_PF x 32 hits behind the
+// current range are already in flight (the pass is bound by load latency, not by instructions).
+__global__ void __launch_bounds__(SP_NT, 3)
 em_sparse_pass_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_dP,
                       const double *__restrict__ P0, const double *__restrict__ rowmax, const double *__restrict__ counts,
-                      const double *__restrict__ w, const ViCtl *__restrict__ ctl, double *__restrict__ partials, int pstride,
-                      unsigned long long N, int K) {
+                      ViArrays arrays, ViCtl *ctl, double *partials, int pstride,
+                      unsigned long long N, unsigned long long nnz, int K, double fx_scale, int tail) {
   if (ctl->done) return;
-  extern __shared__ double s_dyn[];
-  double *s_w = s_dyn, *s_acc = s_dyn + K;
+  extern __shared__ __align__(16) unsigned char s_dyn_sp[];
+  double *s_w = reinterpret_cast<double *>(s_dyn_sp);                         // [K]
+  unsigned *s_acc = reinterpret_cast<unsigned *>(s_w + K);                    // [K][2] fixed-point accumulators
+  double *s_val = reinterpret_cast<double *>(s_acc + 2 * (size_t)K);          // [warps][SP_STAGE] dP * w of the parked hits
+  double *s_r = s_val + (SP_NT / 32) * SP_STAGE;                              // [warps][32] c_j / S_j of the chunk
+  uint32_t *s_key = reinterpret_cast<uint32_t *>(s_r + (SP_NT / 32) * 32);    // [warps][SP_STAGE] packed (class, group)
   __shared__ double s_blk[32];
+  const double *w = arrays.w;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double wsum = 0.0;
-  for (int k = threadIdx.x; k < K; k += 256) { const double x = w[k]; s_w[k] = x; s_acc[k] = 0.0; wsum += x; }
-  wsum = block_sum<256>(wsum, s_blk);        // same order in every CTA and on every rank
+  for (int k = threadIdx.x; k < K; k += SP_NT) { const double x = w[k]; s_w[k] = x; s_acc[2 * k] = 0u; s_acc[2 * k + 1] = 0u; wsum += x; }
+  wsum = block_sum<SP_NT>(wsum, s_blk);        // same order in every CTA and on every rank
   __syncthreads();
+  double *val = s_val + warp * SP_STAGE;
+  uint32_t *key = s_key + warp * SP_STAGE;
+  double *rr = s_r + warp * 32;
   double z = 0.0, elbo = 0.0;
   int fault = 0;
-  // The pass is bound by load latency, not by bytes: everything a class needs is requested before anything is used
-  // (its five per-class values together, then its first HEAD hits together), and the hits stay in registers for the
-  // scatter.  Terms are added in hit order whatever the chunking, so the sums do not depend on HEAD.
-  constexpr int HEAD = 8;
-  for (unsigned long long j = blockIdx.x * 256ull + threadIdx.x; j < N; j += (unsigned long long)gridDim.x * 256ull) {
-    const double c = counts[j];
-    const unsigned long long a = nz_ptr[j], b = nz_ptr[j + 1];
-    const double p0 = P0[j], m = rowmax[j];
-    if (!(c > 0.0)) continue;
-    const unsigned long long n = b - a;
-    double dp[HEAD];
-    uint32_t gr[HEAD];
+  const unsigned long long n_chunks = (N + SP_CHUNK - 1) / SP_CHUNK;
+  const unsigned long long warps_total = (unsigned long long)gridDim.x * (SP_NT / 32);
+  const unsigned long long per = (n_chunks + warps_total - 1) / warps_total;
+  const unsigned long long ch_begin = min(n_chunks, ((unsigned long long)blockIdx.x * (SP_NT / 32) + warp) * per);
+  const unsigned long long ch_end = min(n_chunks, ch_begin + per);
+  const unsigned long long last_hit = nnz ? nnz - 1 : 0;
+
+  struct ClassData { unsigned long long a, b; double c, p0, m; };
+  auto load_class = [&](unsigned long long ch) {
+    // everything the classes of a chunk need, requested together (coalesced: consecutive lanes, consecutive classes)
+    const unsigned long long j = ch * SP_CHUNK + lane;
+    const bool have = j < N;
+    ClassData d;
+    d.a = nz_ptr[have ? j : N]; d.b = nz_ptr[have ? j + 1 : N];
+    d.c = have ? counts[j] : 0.0; d.p0 = have ? P0[j] : 0.0; d.m = have ? rowmax[j] : 0.0;
+    return d;
+  };
+  uint32_t pg[SP_PF];
+  double pd[SP_PF];
+  auto load_hits = [&](unsigned long long base) {          // (clamped: reads past the end of the arrays never happen)
 #pragma unroll
-    for (int u = 0; u < HEAD; ++u) {
-      const bool on = (unsigned long long)u < n;
-      dp[u] = on ? nz_dP[a + u] : 0.0;
-      gr[u] = on ? nz_grp[a + u] : 0u;
+    for (int k = 0; k < SP_PF; ++k) {
+      const unsigned long long e = min(base + (unsigned long long)(32 * k + lane), last_hit);
+      pg[k] = nz_grp[e];
+      pd[k] = nz_dP[e];
     }
-    double s = p0 * wsum;
+  };
+  auto normalise = [&](const ClassData &d, double s) {     // lane l: class l of the chunk
+    double r = 0.0;
+    if (d.c > 0.0) {
+      if (!(s > 0.0) || isinf(s)) fault = 1;
+      else {
+        r = d.c / s;
+        z = fma(r, d.p0, z);
+        elbo = fma(d.c, log(s) + d.m, elbo);
+      }
+    }
+    __syncwarp();
+    rr[lane] = r;
+    __syncwarp();
+  };
+  auto scatter = [&](int n_here) {                          // hit-parallel
+    for (int x = lane; x < n_here; x += 32) {
+      const uint32_t kg = key[x];
+      const double q = rr[kg >> 24] * val[x];
+      if (q != 0.0) fx_atomic_add(&s_acc[2 * (kg & SP_GRP_MASK)], __double2ll_rn(q * fx_scale));
+    }
+  };
+
+  if (ch_begin < ch_end) {
+    ClassData nxt = load_class(ch_begin);
+    load_hits(__shfl_sync(0xffffffffu, nxt.a, 0));           // (the one exposed round trip of the warp)
+    for (unsigned long long ch = ch_begin; ch < ch_end; ++ch) {
+      const ClassData cur = nxt;
+      const unsigned long long h0 = __shfl_sync(0xffffffffu, cur.a, 0), h1 = __shfl_sync(0xffffffffu, cur.b, 31);
+      if (ch + 1 < ch_end) nxt = load_class(ch + 1);
+      double s = cur.p0 * wsum;
+      if (h1 - h0 <= SP_STAGE) {
+        const int n_here = (int)(h1 - h0);
+        __syncwarp();
+        // park the chunk's hits: the first SP_PF slabs arrived in registers, the rest comes straight from memory
 #pragma unroll
-    for (int u = 0; u < HEAD; ++u) s = fma(dp[u], s_w[gr[u]], s);          // a padded slot adds dp = 0: s unchanged
-    for (unsigned long long e = a + HEAD; e < b; ++e) s = fma(nz_dP[e], s_w[nz_grp[e]], s);
-    if (!(s > 0.0) || isinf(s)) { fault = 1; continue; }
-    const double r = c / s;
-    z = fma(r, p0, z);
-    elbo = fma(c, log(s) + m, elbo);
-#pragma unroll
-    for (int u = 0; u < HEAD; ++u)
-      if ((unsigned long long)u < n) atomicAdd(&s_acc[gr[u]], r * dp[u]);
-    for (unsigned long long e = a + HEAD; e < b; ++e) atomicAdd(&s_acc[nz_grp[e]], r * nz_dP[e]);
+        for (int k = 0; k < SP_PF; ++k) {
+          const int x = 32 * k + lane;
+          if (x < n_here) { key[x] = pg[k]; val[x] = pd[k] * s_w[pg[k] & SP_GRP_MASK]; }
+        }
+        for (int x = 32 * SP_PF + lane; x < n_here; x += 32) {
+          const uint32_t kg = nz_grp[h0 + x];
+          key[x] = kg;
+          val[x] = nz_dP[h0 + x] * s_w[kg & SP_GRP_MASK];
+        }
+        load_hits(h1);
+        __syncwarp();
+        // class-parallel: lane l adds the parked hits of class l in list order
+        for (int x = (int)(cur.a - h0), xe = (int)(cur.b - h0); x < xe; ++x) s += val[x];
+        normalise(cur, s);
+        scatter(n_here);
+      } else {
+        // a chunk with more hits than a stage holds: pieces, two rounds (the normalisers first, then the scatter)
+        for (int round = 0; round < 2; ++round) {
+          for (unsigned long long q0 = h0; q0 < h1; q0 += SP_STAGE) {
+            const int n_here = (int)min((unsigned long long)SP_STAGE, h1 - q0);
+            __syncwarp();
+            for (int x = lane; x < n_here; x += 32) {
+              const uint32_t kg = nz_grp[q0 + x];
+              key[x] = kg;
+              val[x] = nz_dP[q0 + x] * s_w[kg & SP_GRP_MASK];
+            }
+            __syncwarp();
+            if (round == 0) {
+              const unsigned long long lo = max(cur.a, q0), hi = min(cur.b, q0 + (unsigned long long)n_here);
+              for (unsigned long long x = lo; x < hi; ++x) s += val[x - q0];
+            } else {
+              scatter(n_here);
+            }
+          }
+          if (round == 0) normalise(cur, s);
+        }
+        load_hits(h1);
+      }
+    }
   }
   __syncthreads();
   double *out = partials + (unsigned long long)blockIdx.x * pstride;
-  for (int k = threadIdx.x; k < K; k += 256) out[k] = s_acc[k];
-  z = block_sum<256>(z, s_blk);
-  elbo = block_sum<256>(elbo, s_blk);
-  if (threadIdx.x == 0) { out[K] = elbo; out[K + 1] = z; }
-  if (fault) atomicExch(const_cast<int *>(&ctl->fault), 1);
+  const double fx_inv = 1.0 / fx_scale;
+  for (int k = threadIdx.x; k < K; k += SP_NT) {
+    const long long v = (long long)(((unsigned long long)s_acc[2 * k + 1] << 32) | (unsigned long long)s_acc[2 * k]);
+    out[k] = (double)v * fx_inv;
+  }
+  z = block_sum<SP_NT>(z, s_blk);
+  elbo = block_sum<SP_NT>(elbo, s_blk);
+  const int any_fault = __syncthreads_or(fault);
+  if (threadIdx.x == 0) { out[K + RED_BOUND] = elbo; out[K + RED_AUX] = z; out[K + RED_FAULT] = any_fault ? 1.0 : 0.0; }
+  em_sweep_tail<SP_NT>(tail, 1, arrays, ctl, partials, pstride, K, s_blk);
+}
+inline size_t em_sparse_smem_bytes(int K) {
+  return (size_t)K * 16 + (size_t)(SP_NT / 32) * SP_STAGE * (8 + 4) + (size_t)(SP_NT / 32) * 32 * 8;
 }
 
-// ---- small kernels --------------------------------------------------------------------------------
-// red[v] = sum over CTAs of partials[cta][v], fixed order.  v < nvals.
-__global__ void finalize_partials_kernel(const double *__restrict__ partials, int pstride, int n_ctas, int nvals,
-                                         double *__restrict__ red, const ViCtl *__restrict__ ctl, int only_if_reset) {
-  if (ctl->done) return;
-  if (only_if_reset && !ctl->didreset) return;
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nvals) return;
-  double a = 0.0;
-  for (int c = 0; c < n_ctas; ++c) a += partials[(size_t)c * pstride + v];
-  red[v] = a;
+// ---- separate reduction (+ control) kernel: large grids x many groups ---------------------------------
+// red[v] = sum over CTAs of partials[cta][v], fixed order; v < nvals.  ctl_mode: -1 none (several GPUs: the all-reduce
+// and a control kernel follow), else the last CTA takes the control step (0 EM dense, 1 EM sparse, 2 RCG stage 0).
+constexpr int FIN_NT = 128;
+__global__ void __launch_bounds__(FIN_NT)
+finalize_ctl_kernel(const double *partials, int pstride, int n_ctas, int nvals, ViArrays arrays, ViCtl *ctl, int K,
+                    int ctl_mode, int ignore_stall) {
+  if (ctl->done || (ctl->stall && !ignore_stall)) return;
+  __shared__ double s_blk[32];
+  reduce_partials(partials, pstride, n_ctas, nvals, arrays.red, (int)(blockIdx.x * FIN_NT + threadIdx.x), (int)(gridDim.x * FIN_NT));
+  if (ctl_mode < 0) return;
+  if (!cta_is_last(ctl)) return;
+  if (threadIdx.x == 0) ctl->ticket = 0;
+  __syncthreads();
+  if (ctl_mode <= 1) em_ctl_step<FIN_NT>(arrays, ctl, K, ctl_mode, s_blk);
+  else rcg_ctl_b_step<FIN_NT>(arrays, ctl, K, 0, 0, s_blk);
 }
 
 } // namespace mswb

@@ -12,8 +12,10 @@
 #include "msweep_b200.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -283,6 +285,66 @@ int main(int argc, char *argv[]) {
     }
   }
 
+  // Sharded mode: every GPU builds only the classes of its own hash range (mswb_ec_build_partitioned).  The host routes
+  // each aligned read by the reference's pattern hash (include/mSWEEP_alignment.hpp:150-155): rank r owns the r-th of
+  // `world` equal ranges of the 64-bit hash space, so the ranks' tables, concatenated, are the global table in the
+  // reference's order (ascending hash) and no class straddles two GPUs.  Unaligned reads belong to no class and stay
+  // on the host (they only count in #num_reads).  part_ids[g][local row] = the read's id in the input.
+  std::vector<b200::ReadTable> parts(world > 1 ? n_gpus : 0);
+  std::vector<std::vector<uint32_t>> part_ids(world > 1 ? n_gpus : 0);
+  double t_route = 0;
+  if (world > 1) {
+    Timer tr;
+    const uint64_t R = reads.n_reads;
+    std::vector<uint8_t> owner(R);
+    std::vector<std::vector<uint64_t>> cnt(n_threads, std::vector<uint64_t>(2 * (size_t)n_gpus, 0));   // [thread][gpu]: reads, hits
+#pragma omp parallel for num_threads(n_threads) schedule(static, 1)
+    for (int tid = 0; tid < n_threads; ++tid) {      // one contiguous chunk of reads per (nominal) thread
+      const int nth = n_threads;
+      const uint64_t lo = R * tid / nth, hi = R * (tid + 1) / nth;
+      for (uint64_t r = lo; r < hi; ++r) {
+        const uint64_t a = reads.row_ptr[r], b = reads.row_ptr[r + 1];
+        if (a == b) { owner[r] = 255; continue; }
+        const uint64_t h = mswb_pattern_hash(reads.targets.data() + a, b - a);
+        const int g = (int)(((unsigned __int128)h * (unsigned)n_gpus) >> 64);
+        owner[r] = (uint8_t)g;
+        cnt[tid][2 * g] += 1;
+        cnt[tid][2 * g + 1] += b - a;
+      }
+    }
+    // exclusive offsets per (thread, gpu) so that reads keep their input order inside every partition
+    std::vector<std::vector<uint64_t>> off(n_threads, std::vector<uint64_t>(2 * (size_t)n_gpus, 0));
+    for (int g = 0; g < n_gpus; ++g) {
+      uint64_t nr = 0, nh = 0;
+      for (int t = 0; t < n_threads; ++t) { off[t][2 * g] = nr; off[t][2 * g + 1] = nh; nr += cnt[t][2 * g]; nh += cnt[t][2 * g + 1]; }
+      parts[g].n_reads = nr; parts[g].n_targets = reads.n_targets;
+      parts[g].row_ptr.assign(nr + 1, 0);
+      parts[g].targets.resize(nh);
+      part_ids[g].resize(nr);
+      parts[g].row_ptr[nr] = nh;
+    }
+#pragma omp parallel for num_threads(n_threads) schedule(static, 1)
+    for (int tid = 0; tid < n_threads; ++tid) {
+      const int nth = n_threads;
+      std::vector<uint64_t> o = off[tid];
+      const uint64_t lo = R * tid / nth, hi = R * (tid + 1) / nth;
+      for (uint64_t r = lo; r < hi; ++r) {
+        const int g = owner[r];
+        if (g == 255) continue;
+        const uint64_t a = reads.row_ptr[r], b = reads.row_ptr[r + 1];
+        parts[g].row_ptr[o[2 * g]] = o[2 * g + 1];
+        part_ids[g][o[2 * g]] = (uint32_t)r;
+        std::copy(reads.targets.begin() + a, reads.targets.begin() + b, parts[g].targets.begin() + o[2 * g + 1]);
+        o[2 * g] += 1;
+        o[2 * g + 1] += b - a;
+      }
+    }
+    t_route = tr.lap();
+  }
+  // A failure on one GPU must not leave the others waiting in a collective: the failing worker aborts every
+  // communicator (mswb_ctx_abort), the peers' pending collectives end with an error, and main() reports the FIRST failure.
+  std::atomic<int> first_failed{-1};
+
   std::vector<std::vector<std::vector<double>>> results_by_gpu(n_gpus);   // [gpu][0 = plain, 1.. = replicates][group]
   const bool want_probs = args.has("write-probs") || args.has("print-probs");
   const bool bin_reads = args.has("bin-reads");
@@ -291,6 +353,7 @@ int main(int argc, char *argv[]) {
   std::vector<std::string> errors(n_gpus);
   std::vector<int> failed_stage(n_gpus, 0);   // 1 = EC/likelihood, 2 = estimation, 3 = bootstrap, 4 = binning
   std::vector<bool> mask;
+  std::vector<uint64_t> ecs_by_gpu(n_gpus, 0), aligned_by_gpu(n_gpus, 0);
   uint64_t n_ecs = 0, n_aligned = 0, n_reads = 0;
   double t_ec = 0, t_lik = 0, t_vi = 0, t_boot = 0;
   b200::ViReport report;
@@ -302,9 +365,11 @@ int main(int argc, char *argv[]) {
       b200::Context &ctx = *ctx_holder;
       Timer tm;
       if (gpu == 0) log("Building equivalence classes");
-      b200::Alignment aln(ctx, reads);
-      if (gpu == 0) { n_ecs = aln.n_ecs(); n_aligned = aln.n_aligned(); n_reads = aln.n_reads(); t_ec = tm.lap();
-                      log("  found " + std::to_string(n_ecs) + " unique alignments"); log("Computing the likelihood matrix"); }
+      b200::Alignment aln(ctx, world > 1 ? parts[gpu] : reads, world > 1);
+      ecs_by_gpu[gpu] = aln.n_ecs(); aligned_by_gpu[gpu] = aln.n_aligned();
+      if (gpu == 0) { t_ec = tm.lap(); log("Computing the likelihood matrix"); }
+      if (const char *inj = std::getenv("MSWB_TEST_FAIL_GPU"))   // fault injection for the abort path (tests only)
+        if (std::atoi(inj) == gpu) throw std::runtime_error("injected failure on GPU " + std::to_string(gpu));
       b200::Likelihood ll(ctx, aln, grouping.group_of_target, grouping.sizes, q, e_disp, min_hits, zi, storage);
       const std::vector<bool> my_mask = ll.groups_considered();
       if (gpu == 0) { mask = my_mask; t_lik = tm.lap(); }
@@ -361,6 +426,8 @@ int main(int argc, char *argv[]) {
         for (size_t k = 0; k < est_names.size(); ++k)
           if (targets.count(est_names[k]) && !(args.has("min-abundance") && res[0][k] < min_abundance)) thr[k] = std::log(res[0][k]);
         bins_by_gpu[gpu] = ll.assign(aln, thr);
+        if (world > 1)   // the partition's rows are local: back to the read ids of the input
+          for (auto &bin : bins_by_gpu[gpu]) for (auto &id : bin) id = part_ids[gpu][id];
         failed_stage[gpu] = 2;
       }
       if (bootstrap) {
@@ -374,6 +441,9 @@ int main(int argc, char *argv[]) {
       failed_stage[gpu] = 0;
     } catch (const std::exception &e) {
       errors[gpu] = e.what();
+      int none = -1;
+      if (first_failed.compare_exchange_strong(none, gpu) && world > 1)
+        for (int g = 0; g < n_gpus; ++g) mswb_ctx_abort(group[g]);
     }
   };
   for (auto &x : warmups) if (x.joinable()) x.join();
@@ -384,7 +454,8 @@ int main(int argc, char *argv[]) {
     worker(0);
     for (auto &t : threads) t.join();
   }
-  for (int g = 0; g < n_gpus; ++g) {
+  for (int i = 0; i < n_gpus; ++i) {
+    const int g = first_failed.load() >= 0 ? (first_failed.load() + i) % n_gpus : i;   // the original failure first
     if (!failed_stage[g]) continue;
     const char *what = failed_stage[g] == 1 ? "Building the log-likelihood array failed:\n  "
                      : failed_stage[g] == 2 ? "Estimating relative abundances failed:\n  "
@@ -392,6 +463,10 @@ int main(int argc, char *argv[]) {
     std::cerr << what << errors[g] << "\nexiting\n";
     return 1;
   }
+  n_reads = reads.n_reads;
+  if (world > 1) for (int g = 0; g < n_gpus; ++g) { n_ecs += ecs_by_gpu[g]; n_aligned += aligned_by_gpu[g]; }
+  else { n_ecs = ecs_by_gpu[0]; n_aligned = aligned_by_gpu[0]; }
+  log("  found " + std::to_string(n_ecs) + " unique alignments");
   if (args.has("no-fit-model")) { log("Skipping relative abundance estimation (--no-fit-model toggled)"); return 0; }
   if (min_hits > 0)
     std::cerr << "WARNING: --min-hits > 0 is an experimental option that has not been thoroughly tested and is subject to change.\n" << std::endl;
@@ -475,7 +550,7 @@ int main(int argc, char *argv[]) {
   const double t_gpu_total = timer.lap();
   if (timings)
     std::cerr << "{\"grouping_s\": " << t_grouping << ", \"parse_s\": " << t_parse << ", \"cuda_init_wait_s\": " << t_warm
-              << ", \"gpu_stage_total_s\": " << t_gpu_total << ", \"ec_build_s\": " << t_ec
+              << ", \"route_s\": " << t_route << ", \"gpu_stage_total_s\": " << t_gpu_total << ", \"ec_build_s\": " << t_ec
               << ", \"likelihood_s\": " << t_lik << ", \"optimiser_s\": " << t_vi << ", \"bootstrap_s\": " << t_boot
               << ", \"write_s\": " << timer.lap() << ", \"n_ecs\": " << n_ecs << ", \"iters\": " << report.iters
               << ", \"bound\": " << report.bound << ", \"converged\": " << (report.converged ? "true" : "false") << "}" << std::endl;

@@ -185,6 +185,28 @@ inline std::vector<double> rcg_optl(const Context &ctx, Likelihood &ll, const st
   return theta;
 }
 
+// Signature-compatible form of the rcgpar entry points the reference calls at src/mSWEEP.cpp:194-202:
+//   seamat::DenseMatrix<double> rcgpar::rcg_optl_omp(const seamat::Matrix<double>& logl, const std::vector<double>&
+//       log_times_observed, const std::vector<double>& alpha0, const double& tol, uint16_t max_iters, std::ostream& log)
+// with the matrix types flattened to what they hold: `logl` is the K x N group-major log-likelihood
+// (seamat::DenseMatrix row-major storage), the return value the K x N matrix of LOG-posteriors (gamma_Z) the reference
+// moves into Sample::ec_probabilities (include/Sample.hpp:66).  algo: MSWB_ALGO_RCG for rcg_optl_omp / rcg_optl_torch,
+// MSWB_ALGO_EM for em_torch (storage MSWB_STORE_F32 = its "float" precision).  For matrices a host can hold; the
+// device-resident path above is the one that scales.  mixture_components(result, log_times_observed) is `theta_out`.
+inline std::vector<double> rcg_optl_dense(const Context &ctx, const std::vector<double> &logl, uint32_t n_groups, uint64_t n_ecs,
+                                          const std::vector<double> &log_times_observed, const std::vector<double> &alpha0,
+                                          double tol, uint64_t max_iters, std::ostream &log, int algo = MSWB_ALGO_RCG,
+                                          int storage = MSWB_STORE_F64, std::vector<double> *theta_out = nullptr) {
+  if (logl.size() != (size_t)n_groups * n_ecs) throw std::runtime_error("logl must hold n_groups x n_ecs values");
+  if (log_times_observed.size() != n_ecs) throw std::runtime_error("log_times_observed must have one value per equivalence class");
+  Likelihood ll(ctx, logl.data(), n_groups, n_ecs, log_times_observed.data(), storage);
+  ViOptions o;
+  o.tol = tol; o.max_iters = max_iters; o.algo = algo;
+  std::vector<double> theta = rcg_optl(ctx, ll, nullptr, alpha0, o, log.good() ? &log : nullptr);   // a never-opened ofstream = quiet (src/mSWEEP.cpp:190)
+  if (theta_out) *theta_out = std::move(theta);
+  return ll.posteriors(0, n_ecs);
+}
+
 // The digamma series mSWEEP carries for RATE (src/Sample.cpp:87-97): recurrence up to 7, then the expansion in 1/(x - 1/2).
 inline double digamma(double x) {
   double r = 0.0;

@@ -134,7 +134,7 @@ def generate(n_reads: int, n_targets: int, n_groups: int, *, n_present: int = 5,
 
 def generate_ec_patterns(n_patterns: int, n_groups: int, group_size: int, *, n_present: int = 50, n_related: int = 3,
                          q_hit: float = 0.65, q_related: float = 0.15, seed: int = 20231019,
-                         chunk: int = 1 << 20, dup_factor: float = 0.0, n_pool: int = 0) -> Workload:
+                         chunk: int = 1 << 20, dup_factor: float = 0.0, n_pool: int = 0, workers: int | None = None) -> Workload:
     """Bench-scale generator (config 3): every read gets its own freshly drawn pattern, block grouping
     (targets of lineage g are g*S .. g*S+S-1) so rows come out sorted without a sort.  With
     dup_factor > 0 a fraction of reads repeat the previous read's pattern (EC counts > 1).  With n_pool > 0 the
@@ -156,30 +156,42 @@ def generate_ec_patterns(n_patterns: int, n_groups: int, group_size: int, *, n_p
         others = np.setdiff1d(np.arange(K), present)
         extra = rng.choice(others, size=max(0, min(n_pool, K) - len(present)), replace=False)
         pool = np.sort(np.concatenate([present, extra]))
-    ptr_parts, tgt_parts, base = [np.zeros(1, np.uint64)], [], 0
     thr_src, thr_rel = int(q_hit * 256), int(q_related * 256)
-    for c0 in range(0, n_patterns, chunk):
-        n = min(chunk, n_patterns - c0)
-        s = present[rng.choice(len(present), size=n, p=theta)]
+    n_chunks = (n_patterns + chunk - 1) // chunk
+
+    def one_chunk(ci: int):
+        # every chunk draws from its own Philox stream (jumped 2^128 draws apart): chunks can be generated in any
+        # order, on any number of threads, with the same result
+        crng = np.random.Generator(np.random.Philox(seed).jumped(ci + 1))
+        n = min(chunk, n_patterns - ci * chunk)
+        s = present[crng.choice(len(present), size=n, p=theta)]
         if pool is None:
-            rel = (s[:, None] + rng.integers(1, K, size=(n, n_related))) % K
+            rel = (s[:, None] + crng.integers(1, K, size=(n, n_related))) % K
         else:
-            rel = pool[rng.integers(0, len(pool), size=(n, n_related))]
+            rel = pool[crng.integers(0, len(pool), size=(n, n_related))]
         lin = np.sort(np.concatenate([s[:, None], rel], axis=1), axis=1)              # ascending lineages
         is_src = lin == s[:, None]
         thr = np.where(is_src, thr_src, thr_rel).astype(np.uint8)
-        hit = rng.integers(0, 256, size=(n, L, S), dtype=np.uint8) < thr[:, :, None]
+        hit = crng.integers(0, 256, size=(n, L, S), dtype=np.uint8) < thr[:, :, None]
         dup = np.zeros((n, L), bool)
         dup[:, 1:] = lin[:, 1:] == lin[:, :-1]
         hit &= ~dup[:, :, None]
         rows, li, si = np.nonzero(hit)                                                 # row-major => sorted
         tg = (lin[rows, li] * S + si).astype(np.uint32)
-        lens = np.bincount(rows, minlength=n)
-        ptr_parts.append((base + np.cumsum(lens)).astype(np.uint64))
-        base += int(lens.sum())
-        tgt_parts.append(tg)
-    row_ptr = np.concatenate(ptr_parts)
-    targets = np.concatenate(tgt_parts)
+        return np.bincount(rows, minlength=n).astype(np.uint64), tg
+
+    if workers is None:
+        workers = min(n_chunks, os.cpu_count() or 1)
+    if workers > 1 and n_chunks > 1:
+        from concurrent.futures import ThreadPoolExecutor        # numpy releases the GIL in the heavy calls
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            parts = list(ex.map(one_chunk, range(n_chunks)))
+    else:
+        parts = [one_chunk(ci) for ci in range(n_chunks)]
+    row_ptr = np.zeros(n_patterns + 1, np.uint64)
+    np.cumsum(np.concatenate([p[0] for p in parts]), out=row_ptr[1:])
+    targets = np.concatenate([p[1] for p in parts])
+    del parts
     wl = Workload(n_patterns, T, K, row_ptr, targets, got, sizes, names, truth)
     if dup_factor > 0:
         wl = _duplicate_reads(wl, dup_factor, rng)
@@ -205,29 +217,85 @@ def write_grouping(path: str, wl: Workload) -> None:
             f.write(wl.group_names[int(g)] + "\n")
 
 
-def write_themisto(prefix: str, wl: Workload, *, paired: bool = True, seed: int = 7, shuffle_frac: float = 0.01):
+def _format_tokens(vals: np.ndarray, sep: np.ndarray) -> np.ndarray:
+    """ASCII bytes of `vals` in decimal, token i followed by the byte sep[i] (vectorised; no Python loop per token)."""
+    v = vals.astype(np.int64)
+    nd = np.ones(len(v), np.int64)
+    p10 = 10
+    while True:
+        m = v >= p10
+        if not m.any():
+            break
+        nd += m
+        p10 *= 10
+    end = np.cumsum(nd + 1)
+    buf = np.empty(int(end[-1]) if len(end) else 0, np.uint8)
+    buf[end - 1] = sep
+    d = 0
+    while True:
+        m = nd > d
+        if not m.any():
+            break
+        buf[end[m] - 2 - d] = 48 + v[m] % 10
+        v //= 10
+        d += 1
+    return buf
+
+
+def write_themisto(prefix: str, wl: Workload, *, paired: bool = True, seed: int = 7, shuffle_frac: float = 0.01,
+                   rows_per_block: int = 1 << 16):
     """Writes Themisto plaintext ("<read_id> <t0> <t1> ...").  Paired: strand k = merged pattern plus
-    strand-private extra hits, so that the default intersection merge recovers `wl` exactly.
+    strand-private extra hits (odd targets only on strand 1, even only on strand 2, inserted at a random place:
+    Themisto does not sort the targets inside a line), so that the default intersection merge recovers `wl` exactly.
     A small fraction of lines is emitted out of order (Themisto's multi-threaded output is unordered;
-    include/mSWEEP_alignment.hpp:60-64 indexes by the id column, not the line number)."""
+    include/mSWEEP_alignment.hpp:60-64 indexes by the id column, not the line number).  Vectorised: 1e6 reads x 2
+    strands (600 MB of text) take seconds, not a minute."""
     rng = np.random.Generator(np.random.Philox(seed))
-    R = wl.n_reads
+    R, T = wl.n_reads, wl.n_targets
     paths = [f"{prefix}_1.aln", f"{prefix}_2.aln"] if paired else [f"{prefix}.aln"]
     rp = wl.row_ptr.astype(np.int64)
+    lens = np.diff(rp)
+    keys = np.repeat(np.arange(R, dtype=np.int64), lens) * T + wl.targets.astype(np.int64)     # ascending (rows are sorted)
     for k, p in enumerate(paths):
         order = np.arange(R)
         n_sw = int(R * shuffle_frac) // 2 * 2
         if n_sw:
             pick = rng.choice(R, size=n_sw, replace=False)
             order[pick] = order[pick[::-1]]
-        with open(p, "w") as f:
-            for r in order:
-                t = wl.targets[rp[r]:rp[r + 1]]
-                if paired and len(t) and rng.random() < 0.3:
-                    # strand-private hit: odd targets only on strand 1, even only on strand 2
-                    extra = int(rng.integers(0, wl.n_targets // 2)) * 2 + (1 - k)
-                    if extra < wl.n_targets and extra not in t:
-                        pos = int(rng.integers(0, len(t) + 1))
-                        t = np.insert(t, pos, extra)     # Themisto does not sort targets inside a line
-                f.write(" ".join([str(int(r))] + [str(int(x)) for x in t]) + "\n")
+        # strand-private extra hit for ~30 % of the aligned reads
+        extra = np.full(R, -1, np.int64)
+        if paired and T >= 2:
+            cand = (lens > 0) & (rng.random(R) < 0.3)
+            e = rng.integers(0, T // 2, size=R) * 2 + (1 - k)
+            ok = cand & (e < T)
+            idx = np.flatnonzero(ok)
+            pos = np.searchsorted(keys, idx * T + e[idx])
+            present = (pos < len(keys)) & (keys[np.minimum(pos, len(keys) - 1)] == idx * T + e[idx])
+            extra[idx[~present]] = e[idx[~present]]
+        ins_pos = (rng.random(R) * (lens + 1)).astype(np.int64)                                 # where the extra hit goes
+        def block(b0: int) -> bytes:
+            rows = order[b0:b0 + rows_per_block]
+            n = len(rows)
+            has = extra[rows] >= 0
+            ln = lens[rows] + has                       # targets on the line
+            tok_per = ln + 1                            # + the read id
+            tend = np.cumsum(tok_per)
+            tstart = tend - tok_per
+            vals = np.empty(int(tend[-1]), np.int64)
+            sep = np.full(len(vals), 32, np.uint8)
+            sep[tend - 1] = 10
+            vals[tstart] = rows
+            # original targets: slot = their index in the row, shifted by one behind the insertion point
+            rep = np.repeat(np.arange(n), lens[rows])
+            within = np.arange(int(lens[rows].sum())) - np.repeat(np.cumsum(lens[rows]) - lens[rows], lens[rows])
+            shift = (has[rep] & (within >= ins_pos[rows][rep])).astype(np.int64)
+            vals[tstart[rep] + 1 + within + shift] = wl.targets[rp[rows][rep] + within]
+            hi = np.flatnonzero(has)
+            vals[tstart[hi] + 1 + ins_pos[rows][hi]] = extra[rows][hi]
+            return _format_tokens(vals, sep).tobytes()
+
+        from concurrent.futures import ThreadPoolExecutor        # numpy releases the GIL in the heavy calls
+        with open(p, "wb") as f, ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            for chunk_bytes in ex.map(block, range(0, R, rows_per_block)):
+                f.write(chunk_bytes)
     return paths

@@ -256,7 +256,9 @@ def test_equal_patterns_far_apart_merge(oracle, mswb, ctx):
     _ec_equal(mswb.Alignment(ctx, len(rows), 500, ptr, tg).export(), oracle.ec_build_csr(len(rows), 500, ptr, tg))
 
 
-@pytest.mark.parametrize("K,N", [(1, 37), (2, 1), (3, 1000), (33, 513), (65, 2049), (100, 333), (129, 700), (190, 450), (257, 300),
+@pytest.mark.parametrize("K,N", [(1, 37), (2, 1), (3, 1000), (4, 3000), (5, 777), (8, 5000), (9, 300), (13, 2500), (16, 4097), (17, 999), (25, 1300), (31, 640), (32, 2048),
+                                 (50, 3001), (64, 1025),
+                                 (33, 513), (65, 2049), (100, 333), (129, 700), (190, 450), (257, 300),
                                  (330, 257), (400, 129), (460, 131), (560, 90), (600, 200), (900, 110), (1100, 150), (1300, 100), (1500, 60), (1600, 70), (1900, 65),
                                  (2100, 64), (2600, 40), (3100, 33), (3700, 20), (5000, 12), (9000, 9)])
 def test_dense_entry_all_tile_shapes(oracle, mswb, ctx, K, N):
@@ -305,6 +307,88 @@ def test_tma_stage_ring_variant(oracle, mswb, ctx, algo, K, env, value):
     for got in (default, other):
         assert np.max(np.abs(got.theta - ref.theta)) < THETA_TOL and abs(got.bound - ref.bound) <= ELBO_RTOL * abs(ref.bound)
     assert np.max(np.abs(other.theta - default.theta)) < 1e-13
+
+
+@pytest.mark.parametrize("K,N", [(3, 900), (7, 4000), (12, 1500), (30, 2600), (50, 3100), (100, 700), (128, 515)])
+def test_short_rows_fp32_storage(oracle, mswb, ctx, K, N):
+    """The sub-warp tile shapes of the fp32-stored EM sweep (rows of 1..32 float4 pieces) against the fp64 oracle at a fixed
+    iteration count; fp32 STORAGE tolerance: theta 2e-6 absolute, ELBO 1e-6 relative (stated separately from fp64)."""
+    rng = np.random.default_rng(K * 7 + N)
+    logl = rng.normal(-5.0, 2.0, size=(K, N))
+    logl[rng.integers(0, K, size=N), np.arange(N)] = rng.normal(-0.5, 0.2, size=N)
+    lc = np.log(rng.integers(1, 50, size=N).astype(np.float64))
+    ref = oracle.vi_run("em", logl, lc, tol=0.0, max_iters=20)
+    got = mswb.Likelihood.from_dense(ctx, logl, lc, storage=mswb.STORE_F32).vi_run(mswb.ALGO_EM, tol=0.0, max_iters=20)
+    assert got.iters == ref.iters == 20
+    assert np.max(np.abs(got.theta - ref.theta)) < 2e-6
+    assert abs(got.bound - ref.bound) <= 1e-6 * abs(ref.bound)
+
+
+@pytest.mark.parametrize("algo", ["rcg", "em"])
+@pytest.mark.parametrize("K,N", [(50, 30000), (100, 20000)])
+def test_reduction_tail_variants(oracle, mswb, ctx, algo, K, N):
+    """The per-CTA partial vectors are summed either by the last CTA of the sweep (which then also takes the control
+    step: one launch per EM iteration) or by finalize_ctl_kernel; MSWB_TAIL_MAX=0 forces the latter.  Both must follow
+    the oracle, and each other to summation-order noise."""
+    rng = np.random.default_rng(K + N)
+    logl = rng.normal(-6.0, 2.0, size=(K, N))
+    logl[rng.integers(0, K, size=N), np.arange(N)] = -0.3
+    lc = np.log(rng.integers(1, 30, size=N).astype(np.float64))
+    ref = oracle.vi_run(algo, logl, lc, tol=1e-7, max_iters=15)
+    lik = mswb.Likelihood.from_dense(ctx, logl, lc)
+    code = mswb.ALGO_RCG if algo == "rcg" else mswb.ALGO_EM
+    fused = lik.vi_run(code, tol=1e-7, max_iters=15)
+
+    def launches_per_iteration():
+        sess = lik.vi_begin(code, tol=-1e300 if algo == "rcg" else 0.0, max_iters=1000)
+        sess.step(2)
+        l0 = mswb.launch_count()
+        sess.step(10)
+        n = mswb.launch_count() - l0
+        sess.finish()
+        return n / 10.0
+
+    per_iter_fused = launches_per_iteration()
+    os.environ["MSWB_TAIL_MAX"] = "0"
+    try:
+        split = lik.vi_run(code, tol=1e-7, max_iters=15)
+        per_iter_split = launches_per_iteration()
+    finally:
+        del os.environ["MSWB_TAIL_MAX"]
+    assert fused.iters == split.iters == ref.iters
+    for got in (fused, split):
+        assert np.max(np.abs(got.theta - ref.theta)) < THETA_TOL and abs(got.bound - ref.bound) <= ELBO_RTOL * abs(ref.bound)
+    assert np.max(np.abs(fused.theta - split.theta)) < 1e-13
+    # launch budget per iteration on one GPU: EM 1 (fused) / 2, RCG 3 / 4 (sweep A, sweep B [, reduction], restart sweep)
+    assert per_iter_fused == (1.0 if algo == "em" else 3.0), per_iter_fused
+    assert per_iter_split == (2.0 if algo == "em" else 4.0), per_iter_split
+
+
+def test_sparse_pass_is_bit_reproducible(mswb, ctx):
+    """The sparse EM pass scatters into fixed-point accumulators (integer adds commute): two runs give identical bits."""
+    wl = synth.generate_ec_patterns(200_000, 300, 12, n_present=20, seed=9)
+    aln = mswb.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=mswb.STORE_SPARSE)
+    runs = [lik.vi_run(mswb.ALGO_EM, tol=0.0, max_iters=40) for _ in range(3)]
+    for r in runs[1:]:
+        assert np.array_equal(r.theta, runs[0].theta) and r.bound == runs[0].bound
+    dense = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes).vi_run(mswb.ALGO_EM, tol=0.0, max_iters=40)
+    assert np.max(np.abs(dense.theta - runs[0].theta)) < 1e-11
+    assert abs(dense.bound - runs[0].bound) <= 1e-12 * abs(dense.bound)
+
+
+def test_group_sizes_must_match_the_indicators(mswb, ctx):
+    """The hit count of a class indexes the group's row of the lookup table: sizes that disagree with the indicators
+    (a C-ABI caller's mistake; the reference's Grouping derives both from one file) are refused."""
+    wl = synth.generate(2000, 60, 6, n_present=2, n_templates=20, seed=4)
+    aln = mswb.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    bad = wl.group_sizes.copy()
+    bad[2] -= 1
+    with pytest.raises(mswb.MswbError, match="group_sizes"):
+        mswb.Likelihood.build(ctx, aln, wl.group_of_target, bad)
+    bad[2] = 0
+    with pytest.raises(mswb.MswbError, match="group_sizes"):
+        mswb.Likelihood.build(ctx, aln, wl.group_of_target, bad)
 
 
 def test_bootstrap_counts_bit_exact(oracle, mswb, ctx):
