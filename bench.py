@@ -417,16 +417,25 @@ def extra_c2_c5(a, torch, M, dist, ctx, stream, rank, world, want_c2, want_c5, p
             # the share of this rank when B replicates are spread over 8 GPUs — with N < 8 the job is weak-scaled (N/8 of config 5)
             n_rep_job = B if world >= 8 else int(np.ceil(B / 8)) * world
             res = {}
-            for name, algo in (("rcg", M.ALGO_RCG), ("em", M.ALGO_EM)):
+            sparse = M.Likelihood.build(solo, aln, wl.group_of_target, wl.group_sizes, storage=M.STORE_SPARSE)
+            for name, algo, L in (("rcg", M.ALGO_RCG, lik), ("em_batched", M.ALGO_EM, lik), ("em_sparse", M.ALGO_EM, sparse)):
                 dist.barrier()
                 t0 = time.perf_counter()
-                thetas, iters = lik.bootstrap_run(n_rep_job, seed=11, algo=algo, replica_rank=rank, replica_world=world)
+                thetas, iters = L.bootstrap_run(n_rep_job, seed=11, algo=algo, replica_rank=rank, replica_world=world)
                 solo.sync()
                 sec = dist.reduce_max(time.perf_counter() - t0)
                 mine = [i for i in range(n_rep_job) if i % world == rank]
                 res[name] = {"replicates_in_job": n_rep_job, "replicates_on_rank0": len(mine), "seconds": round(sec, 3),
                              "replicates_per_s": n_rep_job / sec, "mean_iters": float(np.mean([iters[i] for i in mine])),
                              "theta_sum_min": float(np.min(thetas[mine].sum(axis=1))), "theta_sum_max": float(np.max(thetas[mine].sum(axis=1)))}
+                if name == "rcg":
+                    th_rcg = thetas[mine]
+                else:
+                    res[name]["max_abs_theta_diff_vs_rcg_replicates"] = float(np.max(np.abs(thetas[mine] - th_rcg)))
+            sparse.close()
+            res["how"] = {"rcg": "one replicate after the other, each a cold-start RCG run (the reference's default algorithm)",
+                          "em_batched": "dense fp64: all count vectors of the rank resampled first, then ONE sweep of the matrix per iteration serves every replicate still running (em_lin_batch_kernel)",
+                          "em_sparse": "lossless sparse storage: one replicate after the other, each pass reads ~90 B per class instead of 8 KB"}
             out["c5"] = {"config": f"5: --iters {B} bootstrap on 1e7 reads x 1,000 lineages, replicates spread over 8 GPUs "
                                    f"(this run: {n_rep_job} replicates on {world} GPU(s), replicas only, exact std::mt19937_64 resampling)",
                          **shape, **res}

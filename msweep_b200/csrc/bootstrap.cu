@@ -76,6 +76,11 @@ __global__ void u32_to_double_kernel(const unsigned *in, double *out, size_t n) 
 // declared in vi.cu: a run whose class counts already sit on the device
 int mswb_vi_run_dev_counts(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const double *counts_dev,
                            double sum_counts, const mswb_vi_opts *opts, double *theta, mswb_vi_stat *stat);
+// ... and the batched form: B count vectors, one sweep of the likelihood per iteration for all of them (vi.cu)
+bool mswb_vi_batch_supported(const mswb_lik *lik, const mswb_vi_opts *opts);
+int mswb_vi_run_batch_dev_counts(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const double *counts_dev,
+                                 uint64_t counts_stride, int B, double sum_counts, const mswb_vi_opts *opts, double *thetas,
+                                 mswb_vi_stat *stats);
 
 namespace {
 
@@ -188,6 +193,37 @@ int mswb_bootstrap_run(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const
     DevBuf<unsigned> hist;
     DevBuf<double> counts;
     hist.alloc(rs.N);
+    // EM on a dense likelihood: the replicates of this rank run as device batches — all their count vectors are
+    // resampled first, then one sweep of the matrix per iteration serves every replicate still running (vi.cu).
+    // Groups of at most 64 replicates and 4 GB of counts at a time.
+    if (mswb_vi_batch_supported(lik, opts)) {
+      std::vector<uint64_t> mine;
+      for (uint64_t r = 0; r < n_replicates; ++r) if ((int)(r % (uint64_t)replica_world) == replica_rank) mine.push_back(r);
+      const uint64_t group_max = std::max<uint64_t>(1, std::min<uint64_t>(64, ((uint64_t)4 << 30) / (lik->N_pad * sizeof(double))));
+      uint64_t next_rep = 0;      // next replicate of the sequence whose draws have not been consumed yet
+      for (size_t g0 = 0; g0 < mine.size(); g0 += group_max) {
+        const size_t nb = std::min<size_t>(group_max, mine.size() - g0);
+        counts.alloc(nb * lik->N_pad);
+        MSWB_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes(), ctx->stream));
+        for (size_t b = 0; b < nb; ++b) {
+          const uint64_t r = mine[g0 + b];
+          for (; next_rep < r; ++next_rep) rs.skip();          // another GPU's replicates
+          rs.next(r, hist.p);
+          ++next_rep;
+          u32_to_double_kernel<<<ctx->n_sms * 2, 256, 0, ctx->stream>>>(hist.p, counts.p + b * lik->N_pad, rs.N);
+          MSWB_LAUNCHED();
+        }
+        std::vector<double> th(nb * lik->K);
+        std::vector<mswb_vi_stat> st(nb);
+        if (mswb_vi_run_batch_dev_counts(ctx, lik, alpha0, counts.p, lik->N_pad, (int)nb, (double)rs.draws, opts, th.data(), st.data()))
+          throw Error(std::string("bootstrap replicates ") + std::to_string(mine[g0]) + ".." + std::to_string(mine[g0 + nb - 1]) + ": " + mswb_last_error());
+        for (size_t b = 0; b < nb; ++b) {
+          std::copy(th.begin() + b * lik->K, th.begin() + (b + 1) * lik->K, thetas + mine[g0 + b] * lik->K);
+          if (stats) stats[mine[g0 + b]] = st[b];
+        }
+      }
+      return;
+    }
     counts.alloc(lik->N_pad);
     MSWB_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes(), ctx->stream));
     for (uint64_t r = 0; r < n_replicates; ++r) {

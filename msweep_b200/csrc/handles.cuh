@@ -62,7 +62,11 @@ struct mswb_lik {
   mswb::DevBuf<uint32_t> nz_grp;   // [nnz] row position (kept-group index) of the hit
   mswb::DevBuf<double> nz_dP;      // [nnz] exp(logl - M_j) - P0[j]
   mswb::DevBuf<double> P0;         // [N_pad] exp(log(zero_inflation) - M_j)
+  mswb::DevBuf<double> nz_logl;    // [nnz] log-likelihood of the hit (sparse RCG works in the log domain)
   uint64_t nnz = 0;
+  // sparse RCG state (vi_sparse_rcg.cuh): gamma = a_k + b_j off the hits, explicit on them; the same for the direction
+  mswb::DevBuf<double> sp_b, sp_v; // [N] class part of gamma / of the search direction
+  mswb::DevBuf<double> sp_g, sp_t; // [nnz] gamma / search direction of the hits
 
   // optimiser state that outlives a run (posterior export)
   mswb::DevBuf<double> gamma;    // [N x Kp] RCG log-responsibilities

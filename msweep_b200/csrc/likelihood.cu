@@ -149,8 +149,8 @@ sparse_fill_kernel(const uint64_t *__restrict__ pat_ptr, const uint32_t *__restr
                    const uint32_t *__restrict__ group_of_target, const int *__restrict__ pos_of_group,
                    const uint64_t *__restrict__ lut_off, const double *__restrict__ lut, unsigned long long N,
                    int K_all, int active_warps, double l0, const uint64_t *__restrict__ nz_ptr,
-                   uint32_t *__restrict__ nz_grp, double *__restrict__ nz_dP, double *__restrict__ P0,
-                   double *__restrict__ rowmax) {
+                   uint32_t *__restrict__ nz_grp, double *__restrict__ nz_dP, double *__restrict__ nz_logl,
+                   double *__restrict__ P0, double *__restrict__ rowmax) {
   extern __shared__ unsigned s_rows[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp >= active_warps) return;
@@ -178,38 +178,41 @@ sparse_fill_kernel(const uint64_t *__restrict__ pat_ptr, const uint32_t *__restr
       const unsigned long long p = p0i + lane;
       bool mine = false;
       uint32_t pos_u = 0;
-      double v = 0.0;
+      double v = 0.0, lv = 0.0;
       if (p < b) {
         const uint32_t g = group_of_target[pat_targets[p]];
         const unsigned c = atomicExch(&row[g], 0u);
         const int pos = pos_of_group[g];
         // the sparse pass wants (class index inside its 32-class chunk, group) in one word: top 8 bits, low 24 bits
-        if (c > 0u && pos >= 0) { mine = true; pos_u = (uint32_t)pos | ((uint32_t)(j & 31u) << 24); v = exp(lut[lut_off[pos] + c] - m) - p0; }
+        if (c > 0u && pos >= 0) { mine = true; pos_u = (uint32_t)pos | ((uint32_t)(j & 31u) << 24); lv = lut[lut_off[pos] + c]; v = exp(lv - m) - p0; }
       }
       const unsigned ballot = __ballot_sync(0xffffffffu, mine);
       if (mine) {
         const unsigned slot = emitted + __popc(ballot & ((1u << lane) - 1u));
         nz_grp[base + slot] = pos_u;
         nz_dP[base + slot] = v;
+        nz_logl[base + slot] = lv;
       }
       emitted += __popc(ballot);
     }
     __syncwarp();
     // ... then order them by group (distinct within a row): every entry finds its rank and moves there
     if (n_row <= 32) {
-      uint32_t gi = 0; double vi = 0.0; unsigned rank = 0;
+      uint32_t gi = 0; double vi = 0.0, li = 0.0; unsigned rank = 0;
       if ((unsigned)lane < n_row) {
-        gi = nz_grp[base + lane]; vi = nz_dP[base + lane];
+        gi = nz_grp[base + lane]; vi = nz_dP[base + lane]; li = nz_logl[base + lane];
         for (unsigned q = 0; q < n_row; ++q) rank += nz_grp[base + q] < gi ? 1u : 0u;
       }
       __syncwarp();                                        // everything is read before anything is overwritten
-      if ((unsigned)lane < n_row) { nz_grp[base + rank] = gi; nz_dP[base + rank] = vi; }
+      if ((unsigned)lane < n_row) { nz_grp[base + rank] = gi; nz_dP[base + rank] = vi; nz_logl[base + rank] = li; }
     } else if (lane == 0) {                                // a class hitting more than 32 groups: insertion sort, rare
       for (unsigned x = 1; x < n_row; ++x) {
-        const uint32_t g = nz_grp[base + x]; const double v = nz_dP[base + x];
+        const uint32_t g = nz_grp[base + x]; const double v = nz_dP[base + x], l = nz_logl[base + x];
         unsigned y = x;
-        while (y > 0 && nz_grp[base + y - 1] > g) { nz_grp[base + y] = nz_grp[base + y - 1]; nz_dP[base + y] = nz_dP[base + y - 1]; --y; }
-        nz_grp[base + y] = g; nz_dP[base + y] = v;
+        while (y > 0 && nz_grp[base + y - 1] > g) {
+          nz_grp[base + y] = nz_grp[base + y - 1]; nz_dP[base + y] = nz_dP[base + y - 1]; nz_logl[base + y] = nz_logl[base + y - 1]; --y;
+        }
+        nz_grp[base + y] = g; nz_dP[base + y] = v; nz_logl[base + y] = l;
       }
     }
     __syncwarp();
@@ -404,6 +407,7 @@ void lik_ensure_sparse(mswb_lik *L) {
   L->nnz = nnz;
   L->nz_grp.alloc(nnz);
   L->nz_dP.alloc(nnz);
+  L->nz_logl.alloc(nnz);
   L->P0.alloc(L->N_pad);
   L->rowmax.alloc(L->N_pad);
   MSWB_CUDA(cudaMemsetAsync(L->P0.p, 0, L->P0.bytes(), s));
@@ -411,7 +415,7 @@ void lik_ensure_sparse(mswb_lik *L) {
   prepare_fill_kernel(sparse_fill_kernel, smem);
   sparse_fill_kernel<<<grid, LIK_NT, smem, s>>>(L->pat_ptr.p, L->pat_targets.p, L->group_of_target.p, L->pos_dev.p, L->lut_off.p,
                                                 L->lut.p, L->N, (int)L->K_all, aw, L->l0, L->nz_ptr.p, L->nz_grp.p, L->nz_dP.p,
-                                                L->P0.p, L->rowmax.p);
+                                                L->nz_logl.p, L->P0.p, L->rowmax.p);
   MSWB_LAUNCHED();
 }
 

@@ -3,6 +3,7 @@
 // reference at src/mSWEEP.cpp:192-203, 419-423, 507-516.
 #include "handles.cuh"
 #include "vi_kernels.cuh"
+#include "vi_sparse_rcg.cuh"
 
 #include <cmath>
 #include <cstring>
@@ -39,6 +40,33 @@ __global__ void vi_init_kernel(ViArrays a, ViCtl *ctl, int K, int algo, double t
   if (threadIdx.x == 0) {
     ctl->bound = algo == MSWB_ALGO_RCG ? -100000.0 : 0.0;
     ctl->oldbound = ctl->bound;
+    ctl->oldnorm = 1.0; ctl->newnorm = 0.0; ctl->beta = 0.0;
+    ctl->bound_const = bound_const; ctl->tol = tol; ctl->sum_counts = sum_counts; ctl->dg_max = mx;
+    ctl->iter = 0; ctl->max_iters = max_iters; ctl->resets = 0;
+    ctl->use_old = 0; ctl->didreset = 0; ctl->converged = 0; ctl->fault = 0;
+    ctl->stall = 0; ctl->ticket = 0u; ctl->pad_ = 0;
+    ctl->done = max_iters == 0 ? 1 : 0;
+  }
+}
+
+// One CTA per bootstrap replicate: the same start as vi_init_kernel (EM), on the replicate's own vectors.
+__global__ void __launch_bounds__(CTL_NT) vi_init_batch_kernel(ViArrays base, ViCtl *ctls, int K, int pstride, double tol,
+                                                               unsigned long long max_iters, double bound_const, double sum_counts) {
+  __shared__ double scratch[32];
+  const ViArrays a = arrays_of_replicate(base, (int)blockIdx.x, K, pstride);
+  ViCtl *ctl = ctls + blockIdx.x;
+  double mx = -INFINITY;
+  for (int k = threadIdx.x; k < K; k += CTL_NT) {
+    const double nk = a.alpha0[k] + sum_counts / (double)K;
+    a.N_k[k] = nk;
+    const double dg = digamma_series(nk);
+    a.dg[k] = dg;
+    mx = fmax(mx, dg);
+  }
+  mx = block_max<CTL_NT>(mx, scratch);
+  for (int k = threadIdx.x; k < K; k += CTL_NT) a.w[k] = exp(a.dg[k] - mx);
+  if (threadIdx.x == 0) {
+    ctl->bound = 0.0; ctl->oldbound = 0.0;
     ctl->oldnorm = 1.0; ctl->newnorm = 0.0; ctl->beta = 0.0;
     ctl->bound_const = bound_const; ctl->tol = tol; ctl->sum_counts = sum_counts; ctl->dg_max = mx;
     ctl->iter = 0; ctl->max_iters = max_iters; ctl->resets = 0;
@@ -169,6 +197,8 @@ struct mswb_vi {
   std::vector<double> alpha0_host;
   ViArrays arrays{};
   int pstride = 0, grid = 0, max_grid = 0;
+  DevBuf<double> rs_a, rs_u, rs_a_new, rs_u_new, rs_ec, rs_mom;   // sparse RCG: group vectors (vi_sparse_rcg.cuh)
+  RcgsGroup rs{};
   int tail_max = 16384;          // partial values (grid x columns) the last CTA of a sweep may reduce on its own
   double fx_scale = 1.0;         // fixed-point scale of the sparse pass (vi_kernels.cuh)
   uint64_t enqueued = 0;
@@ -346,6 +376,7 @@ int grid_cap(const mswb_vi *vi, int nvals) {
   const mswb_lik *L = vi->lik;
   const bool small = (uint64_t)L->N * L->K * 8 <= ((uint64_t)64 << 20);
   if (!small) return vi->max_grid;
+  if (const char *e = getenv("MSWB_SMALL_GRID")) return std::max(1, atoi(e));
   return std::max(1, std::min(vi->max_grid, std::max(vi->ctx->n_sms, vi->tail_max / nvals)));
 }
 
@@ -387,7 +418,7 @@ template <typename ST, class TL> int launch_em(mswb_vi *vi, const ST *P, int ld)
   if constexpr (TL::TPR == 256) {
     if (want_em_pipe()) geom = pipe_geometry((size_t)ld * sizeof(ST), TL::G * TL::R, 1, TL::TPR);
     if (geom.stages) {
-      auto kern = em_lin_pass_kernel<ST, TL, true>;
+      auto kern = em_lin_pass_kernel<ST, TL, true, true>;
       const size_t smem = pipe_smem_bytes(geom, 1);
       vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N_pad, (uint64_t)geom.stage_rows), cap);
       const int tail = tail_mode(vi, vi->grid, nvals);
@@ -398,11 +429,16 @@ template <typename ST, class TL> int launch_em(mswb_vi *vi, const ST *P, int ld)
     }
   }
   if (em_chunked(L)) geom.stage_rows = 1;
-  auto kern = em_lin_pass_kernel<ST, TL, false>;
+  auto kern = em_lin_pass_kernel<ST, TL, false, false>;      // the hot-loop-only instantiation (see the kernel)
   vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, L->N_pad / (TL::G * TL::R), cap);
   const int tail = tail_mode(vi, vi->grid, nvals);
-  kern<<<vi->grid, TL::NT, 0, s>>>(P, ld, L->rowmax.p, vi->counts, vi->arrays, vi->ctl.p, vi->partials.p, vi->pstride, L->N_pad, vi->K,
-                                   geom, tail);
+  if (tail == 0) {
+    kern<<<vi->grid, TL::NT, 0, s>>>(P, ld, L->rowmax.p, vi->counts, vi->arrays, vi->ctl.p, vi->partials.p, vi->pstride, L->N_pad, vi->K,
+                                     geom, 0);
+  } else {
+    em_lin_pass_kernel<ST, TL, false, true><<<vi->grid, TL::NT, 0, s>>>(P, ld, L->rowmax.p, vi->counts, vi->arrays, vi->ctl.p, vi->partials.p,
+                                                                        vi->pstride, L->N_pad, vi->K, geom, tail);
+  }
   MSWB_LAUNCHED();
   return tail;
 }
@@ -442,21 +478,33 @@ template <class TL, int MODE, bool WRITE> int launch_sweep_b(mswb_vi *vi, int on
   if constexpr ((TL::TPR >= 64 || (TL::TPR == 32 && TL::KITER == 2)) && TL::NT <= 512) {
     if (want_rcg_pipe()) geom = pipe_geometry((size_t)ld * 8, TL::G * TL::R, 3, TL::TPR, TL::NT <= 256 ? RCG_RING_BYTES : SMEM_BUDGET, TL::NT <= 256 ? RCG_STAGE_BYTES : 2 * RCG_STAGE_BYTES);
     if (geom.stages) {
-      auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, true>;
+      auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, true, MODE == 1>;     // the restart sweep always carries the tail
       const size_t smem = pipe_smem_bytes(geom, 3);
       vi->grid = persistent_grid(vi->ctx, kern, TL::NT, smem, ceil_div(L->N, (uint64_t)geom.stage_rows), cap);
       const int tail = force_tail >= 0 ? force_tail : tail_mode(vi, vi->grid, nvals);
-      kern<<<vi->grid, TL::NT, smem, s>>>(L->logl.p, gam, stp, ld, vi->arrays, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N,
-                                          vi->K, only_if_reset, geom, tail);
+      if (MODE == 1 || tail == 0) {
+        kern<<<vi->grid, TL::NT, smem, s>>>(L->logl.p, gam, stp, ld, vi->arrays, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N,
+                                            vi->K, only_if_reset, geom, tail);
+      } else {
+        auto kern_t = rcg_sweep_b_kernel<TL, MODE, WRITE, true, true>;
+        if (smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(kern_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern_t<<<vi->grid, TL::NT, smem, s>>>(L->logl.p, gam, stp, ld, vi->arrays, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N,
+                                              vi->K, only_if_reset, geom, tail);
+      }
       MSWB_LAUNCHED();
       return tail;
     }
   }
-  auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, false>;
+  auto kern = rcg_sweep_b_kernel<TL, MODE, WRITE, false, MODE == 1>;
   vi->grid = persistent_grid(vi->ctx, kern, TL::NT, 0, ceil_div(L->N, (uint64_t)TL::G * TL::R), cap);
   const int tail = force_tail >= 0 ? force_tail : tail_mode(vi, vi->grid, nvals);
-  kern<<<vi->grid, TL::NT, 0, s>>>(L->logl.p, gam, stp, ld, vi->arrays, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N, vi->K,
-                                   only_if_reset, geom, tail);
+  if (MODE == 1 || tail == 0) {
+    kern<<<vi->grid, TL::NT, 0, s>>>(L->logl.p, gam, stp, ld, vi->arrays, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N, vi->K,
+                                     only_if_reset, geom, tail);
+  } else {
+    rcg_sweep_b_kernel<TL, MODE, WRITE, false, true><<<vi->grid, TL::NT, 0, s>>>(L->logl.p, gam, stp, ld, vi->arrays, vi->counts, vi->ctl.p,
+                                                                                 vi->partials.p, vi->pstride, L->N, vi->K, only_if_reset, geom, tail);
+  }
   MSWB_LAUNCHED();
   return tail;
 }
@@ -475,10 +523,12 @@ void em_iteration(mswb_vi *vi) {
   if (sparse) {
     const size_t smem = em_sparse_smem_bytes(K);
     MSWB_REQUIRE(smem <= 200 * 1024, "too many groups for the sparse EM pass (weights and accumulators live in shared memory)");
-    vi->grid = persistent_grid(ctx, em_sparse_pass_kernel, SP_NT, smem, ceil_div(L->N, (uint64_t)SP_NT), grid_cap(vi, nvals));
+    vi->grid = persistent_grid(ctx, em_sparse_pass_kernel<false>, SP_NT, smem, ceil_div(L->N, (uint64_t)SP_NT), grid_cap(vi, nvals));
     tail = tail_mode(vi, vi->grid, nvals);
-    em_sparse_pass_kernel<<<vi->grid, SP_NT, smem, s>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_dP.p, L->P0.p, L->rowmax.p, vi->counts,
-                                                       vi->arrays, vi->ctl.p, vi->partials.p, vi->pstride, L->N, L->nnz, K, vi->fx_scale, tail);
+    auto kern = tail ? em_sparse_pass_kernel<true> : em_sparse_pass_kernel<false>;
+    if (tail && smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<vi->grid, SP_NT, smem, s>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_dP.p, L->P0.p, L->rowmax.p, vi->counts,
+                                      vi->arrays, vi->ctl.p, vi->partials.p, vi->pstride, L->N, L->nnz, K, vi->fx_scale, tail);
     MSWB_LAUNCHED();
   } else if (L->storage == MSWB_STORE_F32) {
     MSWB_TILE_DISPATCH(L->Kp32 / 4, 8, true, tail = launch_em<float, TL>(vi, L->P32.p, (int)L->Kp32));
@@ -533,12 +583,91 @@ void rcg_iteration(mswb_vi *vi) {
   MSWB_LAUNCHED();
 }
 
+// One RCG iteration on the sparse storage (vi_sparse_rcg.cuh): sweep A, [all-reduce(1)], the K-sized preparation of the
+// step, sweep B (its last CTA — or rcgs_finalize_kernel — reduces and, on one GPU, takes the control step), then on one
+// GPU the restart pair (preparation + sweep), which exits at once unless the step was rejected.
+template <int MODE> int launch_rcgs_sweep_b(mswb_vi *vi, int force_tail) {
+  mswb_lik *L = vi->lik;
+  const int K = vi->K;
+  const size_t smem = rcgs_sweep_b_smem(K);
+  MSWB_REQUIRE(smem <= SMEM_BUDGET, "too many groups for the sparse RCG sweep (group vectors and accumulators live in shared memory)");
+  auto kern0 = rcgs_sweep_b_kernel<MODE, false>;
+  auto kern1 = rcgs_sweep_b_kernel<MODE, true>;
+  vi->grid = persistent_grid(vi->ctx, kern1, RS_NT, smem, ceil_div(L->N, (uint64_t)RS_NT), grid_cap(vi, K + 2));
+  const int tail = force_tail >= 0 ? force_tail : tail_mode(vi, vi->grid, K + 2);
+  if (tail == 0) {
+    if (smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern0<<<vi->grid, RS_NT, smem, vi->ctx->stream>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_logl.p, vi->counts, L->sp_b.p, L->sp_v.p, L->sp_g.p, L->sp_t.p,
+                                                       vi->arrays, vi->rs, vi->ctl.p, vi->partials.p, vi->pstride, L->N, K, L->l0, vi->fx_scale, 0);
+  } else {
+    kern1<<<vi->grid, RS_NT, smem, vi->ctx->stream>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_logl.p, vi->counts, L->sp_b.p, L->sp_v.p, L->sp_g.p, L->sp_t.p,
+                                                       vi->arrays, vi->rs, vi->ctl.p, vi->partials.p, vi->pstride, L->N, K, L->l0, vi->fx_scale, tail);
+  }
+  MSWB_LAUNCHED();
+  return tail;
+}
+
+void rcgs_iteration(mswb_vi *vi) {
+  mswb_lik *L = vi->lik;
+  mswb_ctx *ctx = vi->ctx;
+  cudaStream_t s = ctx->stream;
+  const int K = vi->K;
+  {
+    PassTimer timer(vi);
+    const size_t smem = rcgs_sweep_a_smem(K);
+    MSWB_REQUIRE(smem <= SMEM_BUDGET, "too many groups for the sparse RCG sweep");
+    const int ga = persistent_grid(ctx, rcgs_sweep_a_kernel, RS_NT, smem, ceil_div(L->N, (uint64_t)RS_NT), grid_cap(vi, K + 2));
+    rcgs_sweep_a_kernel<<<ga, RS_NT, smem, s>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_logl.p, L->sp_b.p, L->sp_g.p, vi->arrays, vi->rs, vi->ctl.p,
+                                               vi->partials.p, vi->pstride, L->N, K, L->l0);
+    MSWB_LAUNCHED();
+    timer.stop();
+  }
+  ctx->allreduce_sum(vi->red.p + K + RS_NORM, 1);
+  rcgs_prep_kernel<<<1, RCGS_PREP_NT, 0, s>>>(vi->arrays, vi->rs, vi->ctl.p, K, 0);
+  MSWB_LAUNCHED();
+  int tail;
+  {
+    PassTimer timer(vi);
+    tail = launch_rcgs_sweep_b<0>(vi, -1);
+    timer.stop();
+  }
+  if (ctx->world == 1) {
+    if (tail == 0) {
+      rcgs_finalize_kernel<<<(K + 2 + FIN_NT - 1) / FIN_NT, FIN_NT, 0, s>>>(vi->partials.p, vi->pstride, vi->grid, vi->arrays, vi->rs, vi->ctl.p, K, 0, 0);
+      MSWB_LAUNCHED();
+    }
+    rcgs_prep_kernel<<<1, RCGS_PREP_NT, 0, s>>>(vi->arrays, vi->rs, vi->ctl.p, K, 1);
+    MSWB_LAUNCHED();
+    launch_rcgs_sweep_b<1>(vi, 2);
+    return;
+  }
+  if (tail == 0) {
+    rcgs_finalize_kernel<<<(K + 2 + FIN_NT - 1) / FIN_NT, FIN_NT, 0, s>>>(vi->partials.p, vi->pstride, vi->grid, vi->arrays, vi->rs, vi->ctl.p, K, -1, 0);
+    MSWB_LAUNCHED();
+  }
+  ctx->allreduce_sum(vi->red.p, K + 2);
+  rcgs_ctl_b_kernel<<<1, 256, 0, s>>>(vi->arrays, vi->rs, vi->ctl.p, K, 0, 1);
+  MSWB_LAUNCHED();
+}
+
+void rcgs_restart_stalled(mswb_vi *vi) {
+  mswb_ctx *ctx = vi->ctx;
+  const int K = vi->K;
+  rcgs_prep_kernel<<<1, RCGS_PREP_NT, 0, ctx->stream>>>(vi->arrays, vi->rs, vi->ctl.p, K, 1);
+  MSWB_LAUNCHED();
+  launch_rcgs_sweep_b<1>(vi, 1);
+  ctx->allreduce_sum(vi->red.p, K + 2);
+  rcgs_ctl_b_kernel<<<1, 256, 0, ctx->stream>>>(vi->arrays, vi->rs, vi->ctl.p, K, 1, 1);
+  MSWB_LAUNCHED();
+}
+
 // Several GPUs: the restart of a stalled optimisation (every rank stalls at the same iteration: the decision is taken
 // on all-reduced values).
 void rcg_restart_stalled(mswb_vi *vi) {
   mswb_lik *L = vi->lik;
   mswb_ctx *ctx = vi->ctx;
   const int K = vi->K;
+  if (L->storage == MSWB_STORE_SPARSE) { rcgs_restart_stalled(vi); return; }
   const int slots = L->Kp / 2;
   MSWB_TILE_DISPATCH_RCG(slots, 4, (launch_sweep_b<TL, 1, true>(vi, 1, 1)));
   ctx->allreduce_sum(vi->red.p, K + 1);
@@ -596,8 +725,18 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
     const int K = vi->K = (int)lik->K;
     cudaStream_t s = ctx->stream;
 
-    if (opts->algo == MSWB_ALGO_RCG) {
-      MSWB_REQUIRE(lik->storage == MSWB_STORE_F64, "RCG needs the fp64 log-likelihood (build the likelihood with MSWB_STORE_F64)");
+    if (opts->algo == MSWB_ALGO_RCG && lik->storage == MSWB_STORE_SPARSE) {
+      // RCG on the sparse storage: separable state off the hits (vi_sparse_rcg.cuh)
+      lik_ensure_sparse(lik);
+      lik->sp_b.ensure(lik->N); lik->sp_v.ensure(lik->N); lik->sp_g.ensure(lik->nnz); lik->sp_t.ensure(lik->nnz);
+      const double g0 = std::log(1.0 / (double)K);
+      fill_kernel<<<ctx->n_sms * 4, 256, 0, s>>>(lik->sp_b.p, lik->N, g0); MSWB_LAUNCHED();
+      fill_kernel<<<ctx->n_sms * 4, 256, 0, s>>>(lik->sp_g.p, lik->nnz, g0); MSWB_LAUNCHED();
+      MSWB_CUDA(cudaMemsetAsync(lik->sp_v.p, 0, lik->sp_v.bytes(), s));
+      MSWB_CUDA(cudaMemsetAsync(lik->sp_t.p, 0, lik->sp_t.bytes(), s));
+      vi->pass_bytes = lik->nnz * 64 + (uint64_t)lik->N * 64;   // sweep A 20 B per hit + 16 B per class, sweep B 44 + 48
+    } else if (opts->algo == MSWB_ALGO_RCG) {
+      MSWB_REQUIRE(lik->storage == MSWB_STORE_F64, "RCG needs the fp64 log-likelihood (build the likelihood with MSWB_STORE_F64 or MSWB_STORE_SPARSE)");
       lik_ensure_logl(lik);
       const size_t n = (size_t)lik->N * lik->Kp;
       lik->gamma.ensure(n);
@@ -667,6 +806,13 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
     vi->fx_scale = std::ldexp(1.0, 61 - (int)std::ceil(std::log2(std::max(1.0, vi->sum_counts))));
     vi_init_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, opts->algo, opts->tol, opts->max_iters, bconst, vi->sum_counts);
     MSWB_LAUNCHED();
+    if (opts->algo == MSWB_ALGO_RCG && lik->storage == MSWB_STORE_SPARSE) {
+      vi->rs_a.alloc(K); vi->rs_u.alloc(K); vi->rs_a_new.alloc(K); vi->rs_u_new.alloc(K); vi->rs_ec.alloc(K); vi->rs_mom.alloc(RCGS_MOM);
+      MSWB_CUDA(cudaMemsetAsync(vi->rs_mom.p, 0, RCGS_MOM * sizeof(double), s));
+      vi->rs = RcgsGroup{vi->rs_a.p, vi->rs_u.p, vi->rs_a_new.p, vi->rs_u_new.p, vi->rs_ec.p, vi->rs_mom.p};
+      rcgs_init_groups_kernel<<<1, 256, 0, s>>>(vi->arrays, vi->rs, K);
+      MSWB_LAUNCHED();
+    }
     lik->last_algo = opts->algo;
     *out = vi.release();
   });
@@ -684,7 +830,8 @@ int mswb_vi_step(mswb_vi *vi, uint64_t n_iters) {
     MSWB_REQUIRE(vi, "vi is NULL");
     MSWB_CUDA(cudaSetDevice(vi->ctx->device));
     for (uint64_t i = 0; i < n_iters; ++i) {
-      if (vi->opts.algo == MSWB_ALGO_RCG) rcg_iteration(vi); else em_iteration(vi);
+      if (vi->opts.algo == MSWB_ALGO_RCG) { if (vi->lik->storage == MSWB_STORE_SPARSE) rcgs_iteration(vi); else rcg_iteration(vi); }
+      else em_iteration(vi);
     }
     vi->enqueued += n_iters;
   });
@@ -784,6 +931,150 @@ int mswb_vi_posteriors(mswb_ctx *ctx, mswb_lik *lik, uint64_t ec_begin, uint64_t
 }
 
 } // extern "C"
+
+// =====================================================================================================
+// Batched EM over bootstrap replicates (bootstrap.cu): B count vectors resident on the device, ONE sweep of the
+// likelihood per iteration serves every replicate that is still running.
+// =====================================================================================================
+namespace {
+
+// Replicates per CTA (BT) and rows per batch (R) by row shape: the accumulators (BT x KITER x VEC doubles per thread)
+// have to stay in registers.
+template <typename ST, int KITER> struct BatchShape {
+  static constexpr int VEC = 16 / (int)sizeof(ST);
+  static constexpr int BT = KITER * VEC >= 16 ? 2 : 4;
+  static constexpr int R = KITER <= 2 ? 2 : 1;
+};
+#define MSWB_BATCH_CASE(ST, TPRV, KITERV, ...) { using TL = Tile<TPRV, KITERV, BatchShape<ST, KITERV>::R>; constexpr int BT = BatchShape<ST, KITERV>::BT; __VA_ARGS__; }
+#define MSWB_BATCH_BY_TPR(ST, tpr, KITERV, ...)                                              \
+  switch (tpr) {                                                                             \
+    case 32: MSWB_BATCH_CASE(ST, 32, KITERV, __VA_ARGS__) break;                             \
+    case 64: MSWB_BATCH_CASE(ST, 64, KITERV, __VA_ARGS__) break;                             \
+    case 96: MSWB_BATCH_CASE(ST, 96, KITERV, __VA_ARGS__) break;                             \
+    case 128: MSWB_BATCH_CASE(ST, 128, KITERV, __VA_ARGS__) break;                           \
+    case 160: MSWB_BATCH_CASE(ST, 160, KITERV, __VA_ARGS__) break;                           \
+    case 192: MSWB_BATCH_CASE(ST, 192, KITERV, __VA_ARGS__) break;                           \
+    case 224: MSWB_BATCH_CASE(ST, 224, KITERV, __VA_ARGS__) break;                           \
+    default: MSWB_BATCH_CASE(ST, 256, KITERV, __VA_ARGS__) break;                            \
+  }
+// rows of up to 1024 pieces (K <= 2048 in fp64, 4096 in fp32); wider rows run the replicates one by one
+#define MSWB_BATCH_DISPATCH(ST, slots, ...)                                                  \
+  do {                                                                                       \
+    const int _s = (int)(slots);                                                             \
+    if (_s <= 32) MSWB_BATCH_CASE(ST, 32, 1, __VA_ARGS__)                                    \
+    else if (_s <= 512) { const int _t = (int)round_up(ceil_div(_s, 2), 32); MSWB_BATCH_BY_TPR(ST, _t, 2, __VA_ARGS__) }     \
+    else { const int _t = (int)round_up(ceil_div(_s, 4), 32); MSWB_BATCH_BY_TPR(ST, _t, 4, __VA_ARGS__) }                    \
+  } while (0)
+
+struct BatchRun {
+  mswb_ctx *ctx; mswb_lik *lik; int K, pstride, B;
+  const double *counts; uint64_t counts_stride;
+  ViArrays base; ViCtl *ctls; int *active; double *partials; size_t partials_cap;
+  int grid_x = 0;
+};
+
+template <typename ST, class TL, int BT> void launch_batch_pass(BatchRun &r, const ST *P, int ld, int n_active) {
+  mswb_lik *L = r.lik;
+  auto kern = em_lin_batch_kernel<ST, TL, BT>;
+  const size_t smem = (size_t)BT * ld * sizeof(ST);
+  MSWB_REQUIRE(smem <= SMEM_BUDGET, "too many groups for the batched pass");
+  const int n_slices = (n_active + BT - 1) / BT;
+  const uint64_t n_batches = L->N_pad / (TL::G * TL::R);
+  // all slices resident at once, CTAs of different slices walking the same rows together (the second read hits L2)
+  const int resident = persistent_grid(r.ctx, kern, TL::NT, smem, ~0ull, 1 << 30);
+  int gx = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_batches, (uint64_t)std::max(1, resident / n_slices)));
+  MSWB_REQUIRE((size_t)n_slices * BT * gx * r.pstride <= r.partials_cap, "batched pass: partial buffer too small");
+  r.grid_x = gx;
+  kern<<<dim3(gx, n_slices), TL::NT, smem, r.ctx->stream>>>(P, ld, L->rowmax.p, r.counts, r.counts_stride, r.base, r.active, n_active,
+                                                              r.partials, r.pstride, L->N_pad, r.K);
+  MSWB_LAUNCHED();
+}
+
+} // namespace
+
+// internal (bootstrap.cu).  counts_dev: B x counts_stride doubles (zero beyond the classes), every replicate with the same
+// total `sum_counts`.  Returns false when the likelihood's shape has no batched kernel (the caller runs them one by one).
+bool mswb_vi_batch_supported(const mswb_lik *lik, const mswb_vi_opts *opts) {
+  if (opts->algo != MSWB_ALGO_EM) return false;
+  if (const char *e = getenv("MSWB_BOOT_BATCH")) if (e[0] == '0') return false;
+  if (lik->storage == MSWB_STORE_F64) return lik->Kp / 2 <= 1024 && lik->ctx->world == 1;
+  if (lik->storage == MSWB_STORE_F32) return round_up(lik->K, 4) / 4 <= 1024 && lik->ctx->world == 1;
+  return false;
+}
+
+int mswb_vi_run_batch_dev_counts(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const double *counts_dev,
+                                 uint64_t counts_stride, int B, double sum_counts, const mswb_vi_opts *opts, double *thetas,
+                                 mswb_vi_stat *stats) {
+  return guarded([&] {
+    MSWB_REQUIRE(ctx && lik && alpha0 && counts_dev && opts && thetas && B >= 1, "bad arguments");
+    MSWB_REQUIRE(mswb_vi_batch_supported(lik, opts), "no batched pass for this likelihood");
+    MSWB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    lik_ensure_linear(lik);
+    const int K = (int)lik->K, nvals = K + RED_EXTRA;
+    for (int k = 0; k < K; ++k) MSWB_REQUIRE(alpha0[k] > 0.0 && std::isfinite(alpha0[k]), "prior counts must be positive");
+    BatchRun r{};
+    r.ctx = ctx; r.lik = lik; r.K = K; r.B = B; r.counts = counts_dev; r.counts_stride = counts_stride;
+    r.pstride = (int)round_up(nvals, 2);
+    DevBuf<double> d_alpha0, d_Nk, d_dg, d_dgp, d_w, d_red, d_seg, d_partials;
+    DevBuf<ViCtl> d_ctl;
+    DevBuf<int> d_active;
+    d_alpha0.alloc(K); d_Nk.alloc((size_t)B * K); d_dg.alloc((size_t)B * K); d_dgp.alloc((size_t)B * K); d_w.alloc((size_t)B * K);
+    d_red.alloc((size_t)B * nvals); d_seg.alloc((size_t)B * RED_SEGS * r.pstride); d_ctl.alloc(B); d_active.alloc(B);
+    r.partials_cap = (size_t)(ctx->n_sms * 8 + 8 * B) * r.pstride;
+    d_partials.alloc(r.partials_cap);
+    h2d(d_alpha0.p, alpha0, K, s);
+    r.base = ViArrays{d_alpha0.p, d_Nk.p, d_dg.p, d_w.p, d_dgp.p, d_red.p, d_seg.p, nullptr, nullptr, nullptr, 0};
+    r.ctls = d_ctl.p; r.active = d_active.p; r.partials = d_partials.p;
+    long double a_sum = 0.0L, lg_sum = 0.0L;
+    for (int k = 0; k < K; ++k) { a_sum += alpha0[k]; lg_sum += std::lgamma(alpha0[k]); }
+    const double bconst = (double)(std::lgamma((double)a_sum) - std::lgamma((double)(a_sum + sum_counts)) - lg_sum);
+    vi_init_batch_kernel<<<B, CTL_NT, 0, s>>>(r.base, r.ctls, K, r.pstride, opts->tol, opts->max_iters, bconst, sum_counts);
+    MSWB_LAUNCHED();
+
+    std::vector<int> active(B);
+    for (int b = 0; b < B; ++b) active[b] = b;
+    std::vector<ViCtl> ctl_h(B);
+    const uint64_t every = opts->poll_every ? opts->poll_every : 16;
+    uint64_t passes = 0;
+    while (!active.empty() && opts->max_iters > 0) {
+      const int n_active = (int)active.size();
+      h2d(d_active.p, active.data(), active.size(), s);
+      for (uint64_t it = 0; it < every; ++it) {
+        if (lik->storage == MSWB_STORE_F32) {
+          MSWB_BATCH_DISPATCH(float, lik->Kp32 / 4, (launch_batch_pass<float, TL, BT>(r, lik->P32.p, (int)lik->Kp32, n_active)));
+        } else {
+          MSWB_BATCH_DISPATCH(double, lik->Kp / 2, (launch_batch_pass<double, TL, BT>(r, lik->P64.p, (int)lik->Kp, n_active)));
+        }
+        finalize_ctl_batch_kernel<<<dim3((nvals + 127) / 128, n_active), 128, 0, s>>>(r.partials, r.pstride, r.grid_x, nvals, r.base, r.ctls, K,
+                                                                                      r.active);
+        MSWB_LAUNCHED();
+        ++passes;
+      }
+      d2h(ctl_h.data(), d_ctl.p, B, s);
+      MSWB_CUDA(cudaStreamSynchronize(s));     // (also keeps `active` alive until the copy above has been consumed)
+      std::vector<int> still;
+      for (int b : active) {
+        MSWB_REQUIRE(!ctl_h[b].fault, "EM pass: a class normaliser under/overflowed in the linear domain (extreme prior counts)");
+        if (!ctl_h[b].done) still.push_back(b);
+      }
+      active.swap(still);
+    }
+    std::vector<double> nk((size_t)B * K);
+    d2h(nk.data(), d_Nk.p, nk.size(), s);
+    d2h(ctl_h.data(), d_ctl.p, B, s);
+    MSWB_CUDA(cudaStreamSynchronize(s));
+    for (int b = 0; b < B; ++b) {
+      for (int k = 0; k < K; ++k) thetas[(size_t)b * K + k] = (nk[(size_t)b * K + k] - alpha0[k]) / sum_counts;
+      if (stats) {
+        stats[b] = mswb_vi_stat{};
+        stats[b].bound = ctl_h[b].bound; stats[b].iters = ctl_h[b].iter; stats[b].converged = ctl_h[b].converged;
+        stats[b].pass_launches = passes;
+      }
+    }
+    lik->last_algo = -1;     // the posteriors of a batch are not kept: mswb_vi_posteriors needs a plain run
+  });
+}
 
 // internal (bootstrap.cu): class counts already resident on the device
 int mswb_vi_run_dev_counts(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const double *counts_dev,

@@ -330,29 +330,21 @@ __device__ __forceinline__ void reduce_partials(const double *partials, int pstr
     red[v] = a;
   }
 }
-// The same sum taken by ONE CTA (the last of a sweep).  With few columns the CTAs are cut into up to RED_SEGS
-// segments so that every thread has loads in flight: thread (segment, column) sums its segment in CTA order, the
-// segments are then added in segment order — a fixed order for a given (NT, nvals, n_ctas).
+// The same sum taken by ONE CTA (the last of a sweep): a warp per column, its lanes stride over the CTAs (every load
+// independent of the others: one round trip to L2 instead of a chain), then a shuffle sum — a fixed order for a
+// given (NT, n_ctas), so run-to-run reproducible; it differs from the column-serial order of reduce_partials only
+// in the last bits.
 template <int NT>
 __device__ __forceinline__ void reduce_partials_cta(const double *partials, int pstride, int n_ctas, int nvals, double *red,
-                                                    double *seg) {
-  const int nseg = min(RED_SEGS, NT / nvals);
-  if (nseg <= 1) { reduce_partials(partials, pstride, n_ctas, nvals, red, (int)threadIdx.x, NT); return; }
-  const int s = (int)threadIdx.x / nvals, v = (int)threadIdx.x % nvals;
-  const int per = (n_ctas + nseg - 1) / nseg;
-  if (s < nseg) {
+                                                    double * /*seg: unused scratch*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int v = warp; v < nvals; v += NT / 32) {
     double a = 0.0;
-    const int c0 = s * per, c1 = min(n_ctas, c0 + per);
     const double *p = partials + v;
-#pragma unroll 8
-    for (int c = c0; c < c1; ++c) a += __ldcg(p + (size_t)c * pstride);
-    seg[(size_t)s * pstride + v] = a;
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < nvals) {
-    double a = 0.0;
-    for (int q = 0; q < nseg; ++q) a += seg[(size_t)q * pstride + threadIdx.x];
-    red[threadIdx.x] = a;
+#pragma unroll 4
+    for (int c = lane; c < n_ctas; c += 32) a += __ldcg(p + (size_t)c * pstride);
+    a = warp_sum(a);
+    if (lane == 0) red[v] = a;
   }
 }
 
@@ -490,7 +482,10 @@ template <typename ST, class TL> constexpr int em_min_blocks() {
   return TL::NT <= 192 && (TL::KITER <= 4 || sizeof(ST) == 8) ? 2 : 1;
 }
 
-template <typename ST, class TL, bool PIPE>
+// TAIL: whether the last-CTA reduction / control step is compiled in.  Its code (lgamma, digamma, block reductions)
+// perturbs the scheduling of the streaming loads of the hot loop enough to cost 12 % on matrices of tens of GB, so the
+// large problems — which use finalize_ctl_kernel anyway — run the TAIL = false instantiation.
+template <typename ST, class TL, bool PIPE, bool TAIL>
 __global__ void __launch_bounds__(TL::NT, em_min_blocks<ST, TL>())
 em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ rowmax, const double *__restrict__ counts,
                    ViArrays arrays, ViCtl *ctl, double *partials, int pstride, unsigned long long N_pad, int K,
@@ -674,7 +669,184 @@ em_lin_pass_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ 
   elbo = block_sum<TL::NT>(elbo, s_blk);
   const int any_fault = __syncthreads_or(fault);
   if (threadIdx.x == 0) { out[K + RED_BOUND] = elbo; out[K + RED_AUX] = 0.0; out[K + RED_FAULT] = any_fault ? 1.0 : 0.0; }
-  em_sweep_tail<TL::NT>(tail, 0, arrays, ctl, partials, pstride, K, s_blk);
+  if constexpr (TAIL) em_sweep_tail<TL::NT>(tail, 0, arrays, ctl, partials, pstride, K, s_blk);
+}
+
+// =====================================================================================================
+// The same pass for a BATCH of bootstrap replicates (src/mSWEEP.cpp:496-518: the same likelihood, B resampled count
+// vectors, B cold-start estimations).  The matrix is the expensive thing to read and it does not depend on the
+// replicate: a CTA streams a row batch ONCE and serves BT replicates from it — S_jb = sum_k P_jk w_kb,
+// A_kb += P_jk c_jb / S_jb — i.e. bytes per replicate-iteration fall BT-fold (fp64 FMA throughput then sets the price:
+// 2 BT FMAs per element).  Slices of BT replicates sit on gridDim.y; CTAs of different slices walk the same rows at the
+// same time, so the second slice's reads are served by L2.  Every replicate has its own weights, counts, control block
+// and convergence; a replicate that has converged drops out of the `active` list at the host's next poll.
+// Per-replicate vectors live at base + replicate * K (red: K + RED_EXTRA); traces are not kept.
+// =====================================================================================================
+__device__ __forceinline__ ViArrays arrays_of_replicate(const ViArrays &base, int rep, int K, int pstride) {
+  ViArrays a = base;
+  a.N_k += (size_t)rep * K; a.dg += (size_t)rep * K; a.w += (size_t)rep * K; a.dg_prev += (size_t)rep * K;
+  a.red += (size_t)rep * (K + RED_EXTRA);
+  a.seg += (size_t)rep * RED_SEGS * pstride;
+  a.trace_cap = 0;
+  return a;
+}
+
+template <typename ST, class TL, int BT>
+__global__ void __launch_bounds__(TL::NT, (TL::NT <= 256 && BT * TL::R * TL::KITER <= 16) ? 2 : 1)
+em_lin_batch_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ rowmax, const double *__restrict__ counts,
+                    unsigned long long counts_stride, ViArrays base, const int *__restrict__ active, int n_active,
+                    double *partials, int pstride, unsigned long long N_pad, int K) {
+  using VT = typename VecOf<ST>::type;
+  constexpr int VEC = VecOf<ST>::VEC;
+  constexpr int R = TL::R, KITER = TL::KITER, TPR = TL::TPR, WPG = TL::WPG;
+  constexpr int NP = R * BT;                          // (row, replicate) pairs of one batch: one normaliser each
+  constexpr int RB = TL::G * R;
+  static_assert(TPR >= 32 && NP <= 32, "the batched pass uses whole-warp rows and at most 32 (row, replicate) pairs per batch");
+  static_assert(ROW_PAD % RB == 0, "ROW_PAD must be a multiple of the rows of one CTA batch");
+  ST *sW = reinterpret_cast<ST *>(g_dyn_smem);        // [BT][ld] weights of the slice's replicates
+  __shared__ double s_red[2 * TL::NW * NP];
+  __shared__ double s_comb[TL::G > 1 ? TPR * KITER * VEC : 1];
+  __shared__ double s_blk[32];
+  const int slice = blockIdx.y, b0 = slice * BT, nb = min(BT, n_active - b0);
+  const int t = threadIdx.x % TPR, g = threadIdx.x / TPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = ld / VEC;
+  for (int idx = threadIdx.x; idx < BT * ld; idx += TL::NT) {
+    const int b = idx / ld, k = idx - b * ld;
+    sW[idx] = (b < nb && k < K) ? (ST)base.w[(size_t)active[b0 + b] * K + k] : (ST)0;
+  }
+  __syncthreads();
+
+  bool inr[KITER];
+#pragma unroll
+  for (int i = 0; i < KITER; ++i) inr[i] = t + TPR * i < nvec;
+  double acc[BT][KITER][VEC];
+#pragma unroll
+  for (int b = 0; b < BT; ++b)
+#pragma unroll
+    for (int i = 0; i < KITER; ++i)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[b][i][v] = 0.0;
+  double elbo = 0.0;
+  int fault = 0, phase = 0;
+
+  // the (row, replicate) pair this lane normalises: pair p = r * BT + b
+  const int my_pair = WPG > 1 ? lane : row_of_lane<32, NP>(lane);
+  const bool pair_on = WPG > 1 ? lane < NP : true;
+  const int my_r = (my_pair % NP) / BT, my_b = (my_pair % NP) % BT;
+  const bool my_elbo = WPG > 1 ? t < 32 : lane == holder_lane<32, NP>(my_pair);
+  const double *my_counts = (pair_on && my_b < nb) ? counts + (size_t)active[b0 + my_b] * counts_stride : nullptr;
+
+  const unsigned long long n_batches = N_pad / RB;
+  const VT *pbase = reinterpret_cast<const VT *>(P) + t;
+  const VT zero = VT{};
+  for (unsigned long long bt = blockIdx.x; bt < n_batches; bt += gridDim.x) {
+    const unsigned long long row0 = bt * RB + (unsigned long long)g * R;
+    const VT *p = pbase + row0 * (unsigned long long)nvec;
+    VT pv[R][KITER];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < KITER; ++i) pv[r][i] = inr[i] ? ld_stream(p + (size_t)r * nvec + i * TPR) : zero;
+    const double c_lane = my_counts ? my_counts[row0 + my_r] : 0.0;
+    double s[NP];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      VT wv[KITER];
+#pragma unroll
+      for (int i = 0; i < KITER; ++i) wv[i] = inr[i] ? reinterpret_cast<const VT *>(sW + (size_t)b * ld)[t + TPR * i] : zero;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        ST a[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) a[v] = (ST)0;
+#pragma unroll
+        for (int i = 0; i < KITER; ++i) {
+          ST e[VEC], ww[VEC];
+          unpack(pv[r][i], e);
+          unpack(wv[i], ww);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) a[v] = fma(e[v], ww[v], a[v]);
+        }
+        ST tot = a[0];
+#pragma unroll
+        for (int v = 1; v < VEC; ++v) tot += a[v];
+        s[r * BT + b] = (double)tot;
+      }
+    }
+    const double k = RowsRed<NP, 16, false>::run(s, lane);
+    double tot;
+    if constexpr (WPG > 1) {
+      double *buf = s_red + phase * (TL::NW * NP);
+      phase ^= 1;
+      if ((lane & (32 / NP - 1)) == 0) buf[warp * NP + row_of_lane<32, NP>(lane)] = k;
+      group_sync<TL>(g);
+      tot = 0.0;
+      if (lane < NP) {
+        const int w0 = (warp / WPG) * WPG;
+#pragma unroll
+        for (int ww = 0; ww < WPG; ++ww) tot += buf[(w0 + ww) * NP + lane];
+      }
+    } else {
+      tot = k;
+    }
+    double inv_l = 0.0;
+    if (c_lane > 0.0) {
+      if (!(tot > 0.0) || isinf(tot)) fault = 1;
+      else {
+        inv_l = c_lane / tot;
+        if (my_elbo) elbo += c_lane * (log(tot) + rowmax[row0 + my_r]);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      ST inv[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) inv[r] = (ST)__shfl_sync(0xffffffffu, inv_l, WPG > 1 ? r * BT + b : holder_lane<32, NP>(r * BT + b));
+#pragma unroll
+      for (int i = 0; i < KITER; ++i) {
+        ST a[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) a[v] = (ST)0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          ST e[VEC];
+          unpack(pv[r][i], e);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) a[v] = fma(e[v], inv[r], a[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[b][i][v] += (double)a[v];
+      }
+    }
+  }
+  // one partial vector per (replicate slot, CTA): partials[(slot * gridDim.x + cta) * pstride + ...]
+#pragma unroll
+  for (int b = 0; b < BT; ++b) {
+    double *out = partials + ((size_t)(b0 + b) * gridDim.x + blockIdx.x) * pstride;
+    if (b < nb) store_partials<TL, VEC>(acc[b], s_comb, out, K);       // (nb is uniform over the CTA)
+    const double eb = block_sum<TL::NT>((pair_on && my_b == b) ? elbo : 0.0, s_blk);
+    const int fb = __syncthreads_or((fault && my_b == b) ? 1 : 0);
+    if (b < nb && threadIdx.x == 0) { out[K + RED_BOUND] = eb; out[K + RED_AUX] = 0.0; out[K + RED_FAULT] = fb ? 1.0 : 0.0; }
+  }
+}
+
+// Reduction + control step of the batched pass: gridDim.y = active replicates, the last CTA of a replicate's row
+// of CTAs takes its control step.
+__global__ void __launch_bounds__(128)
+finalize_ctl_batch_kernel(const double *partials, int pstride, int n_ctas, int nvals, ViArrays base, ViCtl *ctls, int K,
+                          const int *__restrict__ active) {
+  const int slot = blockIdx.y, rep = active[slot];
+  ViCtl *ctl = ctls + rep;
+  if (ctl->done) return;
+  __shared__ double s_blk[32];
+  const ViArrays a = arrays_of_replicate(base, rep, K, pstride);
+  reduce_partials(partials + (size_t)slot * n_ctas * pstride, pstride, n_ctas, nvals, a.red, (int)(blockIdx.x * 128 + threadIdx.x),
+                  (int)(gridDim.x * 128));
+  if (!cta_is_last(ctl)) return;
+  if (threadIdx.x == 0) ctl->ticket = 0;
+  __syncthreads();
+  em_ctl_step<128>(a, ctl, K, 0, s_blk);
 }
 
 // =====================================================================================================
@@ -841,7 +1013,7 @@ rcg_sweep_a_kernel(const double *__restrict__ logl, const double *__restrict__ g
 // MODE 0: RCG step; the Fletcher-Reeves ratio beta = newnorm / oldnorm comes from the (all-reduced) norm of sweep A
 // in red[K + RED_AUX], recomputed by every CTA (the control step after the sweep commits it).
 // MODE 1: plain step from the current digamma vector, gamma = normalise(logl + dg) (the RCG restart).
-template <class TL, int MODE, bool WRITE, bool PIPE>
+template <class TL, int MODE, bool WRITE, bool PIPE, bool TAIL>
 __global__ void __launch_bounds__(TL::NT, TL::R * TL::KITER <= 4 && TL::NT <= 256 ? 2 : 1)
 rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, double *__restrict__ step, int ld,
                    ViArrays arrays, const double *__restrict__ counts, ViCtl *ctl,
@@ -1042,12 +1214,14 @@ rcg_sweep_b_kernel(const double *__restrict__ logl, double *__restrict__ gamma, 
   if (threadIdx.x == 0) out[K + RED_BOUND] = bound;
   // Only the K per-group sums and the bound term are reduced here: slot RED_AUX of red[] holds the norm of sweep A,
   // which the control step still needs.
-  if (tail != 0 && cta_is_last(ctl)) {
-    reduce_partials_cta<TL::NT>(partials, pstride, (int)gridDim.x, K + 1, arrays.red, arrays.seg);
-    if (threadIdx.x == 0) ctl->ticket = 0;
-    if (tail == 2) {
-      __syncthreads();
-      rcg_ctl_b_step<TL::NT>(arrays, ctl, K, MODE == 0 ? 0 : 1, 0, s_blk);
+  if constexpr (TAIL) {
+    if (tail != 0 && cta_is_last(ctl)) {
+      reduce_partials_cta<TL::NT>(partials, pstride, (int)gridDim.x, K + 1, arrays.red, arrays.seg);
+      if (threadIdx.x == 0) ctl->ticket = 0;
+      if (tail == 2) {
+        __syncthreads();
+        rcg_ctl_b_step<TL::NT>(arrays, ctl, K, MODE == 0 ? 0 : 1, 0, s_blk);
+      }
     }
   }
 }
@@ -1082,6 +1256,7 @@ __device__ __forceinline__ void fx_atomic_add(unsigned *acc2 /* [lo, hi] */, lon
 // A warp walks a CONTIGUOUS run of chunks, so the hits of its next chunk start where those of the current one end:
 // while the arithmetic of chunk i runs, the per-class values of chunk i + 1 and the first SP_PF x 32 hits behind the
 // current range are already in flight (the pass is bound by load latency, not by instructions).
+template <bool TAIL>
 __global__ void __launch_bounds__(SP_NT, 3)
 em_sparse_pass_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_dP,
                       const double *__restrict__ P0, const double *__restrict__ rowmax, const double *__restrict__ counts,
@@ -1219,7 +1394,7 @@ em_sparse_pass_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__res
   elbo = block_sum<SP_NT>(elbo, s_blk);
   const int any_fault = __syncthreads_or(fault);
   if (threadIdx.x == 0) { out[K + RED_BOUND] = elbo; out[K + RED_AUX] = z; out[K + RED_FAULT] = any_fault ? 1.0 : 0.0; }
-  em_sweep_tail<SP_NT>(tail, 1, arrays, ctl, partials, pstride, K, s_blk);
+  if constexpr (TAIL) em_sweep_tail<SP_NT>(tail, 1, arrays, ctl, partials, pstride, K, s_blk);
 }
 inline size_t em_sparse_smem_bytes(int K) {
   return (size_t)K * 16 + (size_t)(SP_NT / 32) * SP_STAGE * (8 + 4) + (size_t)(SP_NT / 32) * 32 * 8;

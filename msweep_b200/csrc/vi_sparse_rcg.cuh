@@ -1,0 +1,410 @@
+// vi_sparse_rcg.cuh — the RCG optimiser (rcgpar::rcg_optl_*) on the SPARSE likelihood storage.
+//
+// LL_WOR21 gives every group a class does NOT hit the same value l0 = log(zero_inflation) (include/Likelihood.hpp:96,
+// 176-185).  RCG starts from the uniform gamma = log(1/K), and every update it applies to an entry (j, k) is
+//     d_jk = logl_jk + (digamma(N_k) - 1) - gamma_jk,   step = d + beta * oldstep,   gamma += step - m_j.
+// On the non-hit entries logl is the constant l0, so by induction gamma and the search direction stay SEPARABLE there:
+//     gamma_jk = a_k + b_j ,   step_jk = u_k + v_j        for every group k that class j does not hit,
+// exactly (not an approximation): d_jk = (psi_k - a_k) + (l0 - b_j), and sums of separable terms are separable.
+// The dense K x N state of RCG — 32 bytes per (class, group) pair, the reason RCG could not run on config 3 at all —
+// collapses to two K-vectors (a, u), two N-vectors (b, v) and explicit (gamma, step) values for the hits only.  Every
+// row reduction the sweeps need splits into a closed form over the non-hit groups, built from global moments of the
+// group vectors minus the class's few hit groups, plus an explicit sum over its hits:
+//     sum_k exp(gamma_jk)             = exp(b_j) (M0 - sum_H E_k) + sum_hits exp(g_e),           E_k = exp(a_k), M0 = sum_k E_k
+//     sum_k q (d - <d>)  d            = S2_j - S1_j^2  with the direction centred per class (no cancellation at the optimum)
+//     N_k - alpha0_k                  = E_k (B - sum_{j hits k} c_j exp(b_j)) + sum_{j hits k} c_j q_jk,  B = sum_j c_j exp(b_j)
+//     sum_k c_j q (logl - gamma)      = c_j exp(b_j) ((l0 - b_j)(M0 - sum_H E) - (Ma - sum_H E a)) + hits,  Ma = sum_k E_k a_k
+// The iteration is the dense one, step for step (same Fletcher-Reeves ratio, same restart rule, same stopping rule): the
+// trajectory differs from the dense sweeps only by summation order.  Bytes per iteration: ~150 per class + ~50 per hit,
+// against 56 K per class.
+//
+// Kernels: rcgs_prep_kernel (one CTA: the K-sized group vectors and moments of the step about to be taken),
+// rcgs_sweep_a_kernel (gradient norm), rcgs_sweep_b_kernel<MODE> (step / restart, renormalise, N_k, bound), and the control
+// step.  One warp per chunk of 32 classes, hits read hit-parallel (coalesced) and parked in shared memory, class sums
+// class-parallel in list order, per-group sums in the fixed-point accumulators of the sparse EM pass (bit-reproducible).
+#pragma once
+#include "vi_kernels.cuh"
+
+namespace mswb {
+
+// Per-group vectors and global moments of sparse RCG (device pointers; identical on every rank).
+struct RcgsGroup {
+  double *a, *u;          // [K] group part of gamma (max-normalised: max_k a_k = 0) and of the search direction
+  double *a_new, *u_new;  // [K] the same for the step being taken; committed by the control step when it is accepted
+  double *ec;             // [K] e_k - ebar with e_k = psi_k - a_k   (sweep A)
+  double *mom;            // [RCGS_MOM] see below
+};
+// mom[]: moments of the committed state (sweep A) and of the candidate (sweep B)
+constexpr int RM_M0 = 0, RM_EBAR = 1, RM_M2C = 2, RM_M0N = 3, RM_MAN = 4, RM_SHIFT = 5, RM_BETA = 6, RCGS_MOM = 8;
+// slots of the reduced vector behind the K per-group sums (the norm sits last so that the all-reduce after sweep B,
+// K + 2 values, leaves it alone)
+constexpr int RS_BOUND = 0, RS_MASS = 1, RS_NORM = 2;
+
+// Moments for sweep A from the committed (a, psi): E_k = exp(a_k), M0, ebar = sum E e / M0, ec = e - ebar, M2c = sum E ec^2.
+template <int NT>
+__device__ __forceinline__ void rcgs_prep_a(const ViArrays &va, const RcgsGroup &g, int K, double *scratch) {
+  double m0 = 0.0, m1 = 0.0;
+  for (int k = threadIdx.x; k < K; k += NT) {
+    const double E = exp(g.a[k]), e = va.dg[k] - g.a[k];
+    m0 += E; m1 = fma(E, e, m1);
+  }
+  m0 = block_sum<NT>(m0, scratch);
+  m1 = block_sum<NT>(m1, scratch);
+  const double ebar = m1 / m0;
+  double m2 = 0.0;
+  for (int k = threadIdx.x; k < K; k += NT) {
+    const double E = exp(g.a[k]), ec = va.dg[k] - g.a[k] - ebar;
+    g.ec[k] = ec;
+    m2 = fma(E * ec, ec, m2);
+  }
+  m2 = block_sum<NT>(m2, scratch);
+  if (threadIdx.x == 0) { g.mom[RM_M0] = m0; g.mom[RM_EBAR] = ebar; g.mom[RM_M2C] = m2; }
+}
+
+// The group part of the step about to be taken.  mode 0: u' = e + beta u, a' = a + u'.  mode 1 (restart): a' = psi, u' = 0.
+// a' is shifted to max 0 (the shift goes into the class offsets); M0' = sum exp(a'), Ma' = sum exp(a') a'.
+constexpr int RCGS_PREP_NT = 256;
+__global__ void __launch_bounds__(RCGS_PREP_NT) rcgs_prep_kernel(ViArrays va, RcgsGroup g, ViCtl *ctl, int K, int mode) {
+  if (ctl->done) return;
+  if (mode == 0 ? ctl->stall != 0 : !ctl->didreset) return;
+  __shared__ double scratch[32];
+  double beta_eff = 0.0;
+  if (mode == 0) {
+    const double beta = va.red[K + RS_NORM] / ctl->oldnorm;
+    // the direction memory is empty before the first accepted step and after a restart
+    beta_eff = (!ctl->didreset && beta > 0.0 && ctl->iter > 0) ? beta : 0.0;
+  }
+  double mx = -INFINITY;
+  for (int k = threadIdx.x; k < K; k += RCGS_PREP_NT) {
+    double an, un;
+    if (mode == 0) { un = fma(beta_eff, g.u[k], va.dg[k] - g.a[k]); an = g.a[k] + un; }
+    else { un = 0.0; an = va.dg[k]; }
+    g.u_new[k] = un;
+    g.a_new[k] = an;
+    mx = fmax(mx, an);
+  }
+  mx = block_max<RCGS_PREP_NT>(mx, scratch);
+  double m0 = 0.0, ma = 0.0;
+  for (int k = threadIdx.x; k < K; k += RCGS_PREP_NT) {
+    const double an = g.a_new[k] - mx, E = exp(an);
+    g.a_new[k] = an;
+    m0 += E; ma = fma(E, an, ma);
+  }
+  m0 = block_sum<RCGS_PREP_NT>(m0, scratch);
+  ma = block_sum<RCGS_PREP_NT>(ma, scratch);
+  if (threadIdx.x == 0) { g.mom[RM_M0N] = m0; g.mom[RM_MAN] = ma; g.mom[RM_SHIFT] = mx; g.mom[RM_BETA] = beta_eff; }
+}
+
+// ---- warp-level plumbing shared by the two sweeps ------------------------------------------------------------------
+constexpr int RS_NT = 256;
+constexpr int RS_STAGE = 224;      // hits a warp parks at a time
+
+// Sweep A: newnorm = sum_j (S2_j - S1_j^2), the direction centred per class by c_j = (l0 - b_j) + ebar so that every term
+// vanishes at the optimum (no cancellation between large sums):
+//   delta_e = (logl_e + psi_k - g_e) - c_j   on the hits,   ec_k = e_k - ebar on the non-hit groups (sum_k E_k ec_k = 0)
+//   S1_j = sum_hits (q_e delta_e - exp(b_j) E_k ec_k)
+//   S2_j = exp(b_j) M2c + sum_hits (q_e delta_e^2 - exp(b_j) E_k ec_k^2)
+__global__ void __launch_bounds__(RS_NT, 3)
+rcgs_sweep_a_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
+                    const double *__restrict__ sp_b, const double *__restrict__ sp_g, ViArrays va, RcgsGroup grp, ViCtl *ctl,
+                    double *partials, int pstride, unsigned long long N, int K, double l0) {
+  if (ctl->done || ctl->stall) return;
+  extern __shared__ __align__(16) unsigned char s_dyn_rs[];
+  double *s_E = reinterpret_cast<double *>(s_dyn_rs);            // [K] exp(a_k)
+  double *s_ec = s_E + K;                                         // [K]
+  double *s_psi = s_ec + K;                                       // [K]
+  double *s_x1 = s_psi + K;                                       // [warps][RS_STAGE]
+  double *s_x2 = s_x1 + (RS_NT / 32) * RS_STAGE;                  // [warps][RS_STAGE]
+  double *s_cls = s_x2 + (RS_NT / 32) * RS_STAGE;                 // [warps][2][32]: exp(b_j), centre c_j
+  __shared__ double s_blk[32];
+  for (int k = threadIdx.x; k < K; k += RS_NT) { s_E[k] = exp(grp.a[k]); s_ec[k] = grp.ec[k]; s_psi[k] = va.dg[k]; }
+  const double ebar = grp.mom[RM_EBAR], m2c = grp.mom[RM_M2C];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *x1 = s_x1 + warp * RS_STAGE, *x2 = s_x2 + warp * RS_STAGE;
+  double *cls_w = s_cls + warp * 64, *cls_c = cls_w + 32;
+  double nn = 0.0;
+  const unsigned long long n_chunks = (N + 31) / 32;
+  const unsigned long long warps_total = (unsigned long long)gridDim.x * (RS_NT / 32);
+  const unsigned long long per = (n_chunks + warps_total - 1) / warps_total;
+  const unsigned long long ch_begin = min(n_chunks, ((unsigned long long)blockIdx.x * (RS_NT / 32) + warp) * per);
+  const unsigned long long ch_end = min(n_chunks, ch_begin + per);
+  for (unsigned long long ch = ch_begin; ch < ch_end; ++ch) {
+    const unsigned long long j = ch * 32 + lane;
+    const bool have = j < N;
+    const unsigned long long a = nz_ptr[have ? j : N], b = nz_ptr[have ? j + 1 : N];
+    const double bj = have ? sp_b[j] : 0.0;
+    const double wj = have ? exp(bj) : 0.0;
+    const unsigned long long h0 = __shfl_sync(0xffffffffu, a, 0), h1 = __shfl_sync(0xffffffffu, b, 31);
+    __syncwarp();
+    cls_w[lane] = wj;
+    cls_c[lane] = (l0 - bj) + ebar;
+    __syncwarp();
+    double s1 = 0.0, s2 = wj * m2c;
+    for (unsigned long long q0 = h0; q0 < h1; q0 += RS_STAGE) {
+      const int n_here = (int)min((unsigned long long)RS_STAGE, h1 - q0);
+      __syncwarp();
+      for (int x = lane; x < n_here; x += 32) {                  // hit-parallel, coalesced
+        const uint32_t kg = nz_grp[q0 + x];
+        const int k = (int)(kg & SP_GRP_MASK), c = (int)(kg >> 24);
+        const double g = sp_g[q0 + x];
+        const double delta = (nz_logl[q0 + x] + s_psi[k] - g) - cls_c[c];
+        const double q = exp_nonpos(fmin(g, 0.0));
+        const double Ew = cls_w[c] * s_E[k], ec = s_ec[k];
+        x1[x] = fma(q, delta, -Ew * ec);
+        x2[x] = fma(q * delta, delta, -Ew * ec * ec);
+      }
+      __syncwarp();
+      const unsigned long long lo = max(a, q0), hi = min(b, q0 + (unsigned long long)n_here);
+      for (unsigned long long x = lo; x < hi; ++x) { s1 += x1[x - q0]; s2 += x2[x - q0]; }   // class-parallel, list order
+    }
+    if (have) nn += s2 - s1 * s1;
+  }
+  nn = block_sum<RS_NT>(nn, s_blk);
+  if (threadIdx.x == 0) partials[(unsigned long long)blockIdx.x * pstride + K + RS_NORM] = nn;
+  if (cta_is_last(ctl)) {
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += RS_NT) acc += __ldcg(partials + (size_t)c * pstride + K + RS_NORM);
+    acc = block_sum<RS_NT>(acc, s_blk);
+    if (threadIdx.x == 0) { va.red[K + RS_NORM] = acc; ctl->ticket = 0; }
+  }
+}
+inline size_t rcgs_sweep_a_smem(int K) { return (size_t)K * 24 + (size_t)(RS_NT / 32) * RS_STAGE * 16 + (size_t)(RS_NT / 32) * 64 * 8; }
+
+// Control step after sweep B (stage 0) / the restart sweep (stage 1); all NT threads of one CTA.
+//   red[k] = sum over the hits of k of c_j (q_jk - exp(b_j) E'_k),  red[K + RS_MASS] = B = sum_j c_j exp(b_j),
+//   red[K + RS_BOUND] = data term of the bound, red[K + RS_NORM] = the gradient norm of sweep A.
+// Accepting commits the candidate group vectors and prepares the moments of the next sweep A.
+template <int NT>
+__device__ __forceinline__ void rcgs_ctl_b_step(const ViArrays &va, const RcgsGroup &g, ViCtl *ctl, int K, int stage,
+                                                int stall_on_reject, double *scratch) {
+  __shared__ int s_accept;
+  const double mass = __ldcg(va.red + K + RS_MASS);
+  double lg = 0.0;
+  for (int k = threadIdx.x; k < K; k += NT) lg += lgamma(va.alpha0[k] + fma(exp(g.a_new[k]), mass, __ldcg(va.red + k)));
+  lg = block_sum<NT>(lg, scratch);
+  const double cand = __ldcg(va.red + K + RS_BOUND) + lg + ctl->bound_const;
+  if (threadIdx.x == 0) {
+    if (stage == 0) {
+      const double nn = __ldcg(va.red + K + RS_NORM);
+      ctl->beta = nn / ctl->oldnorm;
+      ctl->newnorm = nn;
+      ctl->oldnorm = nn;
+      ctl->didreset = 0;
+    }
+    if (stage == 0 && cand < ctl->bound) {
+      ctl->didreset = 1;
+      ctl->resets += 1;
+      if (stall_on_reject) ctl->stall = 1;
+      s_accept = 0;
+    } else {
+      s_accept = 1;
+      ctl->oldbound = ctl->bound;
+      ctl->bound = cand;
+      trace_push(va, ctl, ctl->newnorm, stage);
+      ctl->iter += 1;
+      ctl->stall = 0;
+      if (stage == 0 && cand - ctl->oldbound < ctl->tol) ctl->converged = 1;
+      if (ctl->converged || ctl->iter >= ctl->max_iters) ctl->done = 1;
+    }
+  }
+  __syncthreads();
+  if (!s_accept) return;
+  for (int k = threadIdx.x; k < K; k += NT) {
+    const double nk = va.alpha0[k] + fma(exp(g.a_new[k]), mass, __ldcg(va.red + k));
+    va.N_k[k] = nk;
+    va.dg[k] = digamma_series(nk) - 1.0;
+    g.a[k] = g.a_new[k];
+    g.u[k] = g.u_new[k];
+  }
+  __syncthreads();
+  rcgs_prep_a<NT>(va, g, K, scratch);
+}
+
+__global__ void __launch_bounds__(256) rcgs_ctl_b_kernel(ViArrays va, RcgsGroup g, ViCtl *ctl, int K, int stage, int stall_on_reject) {
+  if (ctl->done) return;
+  if (stage == 0 ? ctl->stall != 0 : !ctl->didreset) return;
+  __shared__ double scratch[32];
+  rcgs_ctl_b_step<256>(va, g, ctl, K, stage, stall_on_reject, scratch);
+}
+
+// Sweep B.  MODE 0: the RCG step; MODE 1: the restart, gamma = normalise(logl + psi) (class part b = l0 + shift, hits
+// logl_e + psi_k), no direction memory.  Per class j with the candidate group vectors (a', E' = exp(a'), M0', Ma', shift):
+//   v_j' = (l0 - b_j) + beta v_j,  bb = b_j + v_j' + shift      (non-hit gamma before normalisation: a'_k + bb)
+//   t_e' = (logl_e + psi_k - g_e) + beta t_e,  gg_e = g_e + t_e'
+//   m_j  = log( exp(bb) (M0' - sum_H E'_k) + sum_hits exp(gg_e) ),   b_j' = bb - m_j,  g_e' = gg_e - m_j
+// Three rounds over the chunk's hits: (0) new step out, gamma parked, class maximum and hit-group moments; (1) the
+// normaliser; (2) normalised gamma out, N_k scatter, bound.  A chunk that fits one stage is parked once.
+// tail: 0 none (rcgs_finalize_kernel follows), 1 the last CTA reduces the partial vectors, 2 ... and takes the control step.
+template <int MODE, bool TAIL>
+__global__ void __launch_bounds__(RS_NT, 2)
+rcgs_sweep_b_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
+                    const double *__restrict__ counts, double *__restrict__ sp_b, double *__restrict__ sp_v,
+                    double *__restrict__ sp_g, double *__restrict__ sp_t, ViArrays va, RcgsGroup grp, ViCtl *ctl,
+                    double *partials, int pstride, unsigned long long N, int K, double l0, double fx_scale, int tail) {
+  if (ctl->done) return;
+  if (MODE == 1 ? !ctl->didreset : ctl->stall != 0) return;
+  extern __shared__ __align__(16) unsigned char s_dyn_rs[];
+  double *s_an = reinterpret_cast<double *>(s_dyn_rs);            // [K] a'_k
+  double *s_En = s_an + K;                                         // [K] exp(a'_k)
+  double *s_psi = s_En + K;                                        // [K]
+  unsigned *s_acc = reinterpret_cast<unsigned *>(s_psi + K);       // [K][2] fixed-point accumulators
+  double *s_gg = reinterpret_cast<double *>(s_acc + 2 * (size_t)K);   // [warps][RS_STAGE] gamma of the parked hits (before normalisation)
+  double *s_ll = s_gg + (RS_NT / 32) * RS_STAGE;                   // [warps][RS_STAGE] logl of the parked hits
+  double *s_cls = s_ll + (RS_NT / 32) * RS_STAGE;                  // [warps][3][32]: per class of the chunk
+  uint32_t *s_key = reinterpret_cast<uint32_t *>(s_cls + (RS_NT / 32) * 96);   // [warps][RS_STAGE]
+  __shared__ double s_blk[32];
+  for (int k = threadIdx.x; k < K; k += RS_NT) {
+    const double an = grp.a_new[k];
+    s_an[k] = an; s_En[k] = exp(an); s_psi[k] = va.dg[k];
+    s_acc[2 * k] = 0u; s_acc[2 * k + 1] = 0u;
+  }
+  const double m0n = grp.mom[RM_M0N], man = grp.mom[RM_MAN], shift = grp.mom[RM_SHIFT];
+  const double beta = MODE == 0 ? grp.mom[RM_BETA] : 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *gg = s_gg + warp * RS_STAGE, *ll = s_ll + warp * RS_STAGE;
+  uint32_t *key = s_key + warp * RS_STAGE;
+  double *cls_m = s_cls + warp * 96, *cls_cw = cls_m + 32, *cls_c = cls_m + 64;   // m_j, c_j exp(b_j'), c_j
+  double bound = 0.0, mass = 0.0;
+  const unsigned long long n_chunks = (N + 31) / 32;
+  const unsigned long long warps_total = (unsigned long long)gridDim.x * (RS_NT / 32);
+  const unsigned long long per = (n_chunks + warps_total - 1) / warps_total;
+  const unsigned long long ch_begin = min(n_chunks, ((unsigned long long)blockIdx.x * (RS_NT / 32) + warp) * per);
+  const unsigned long long ch_end = min(n_chunks, ch_begin + per);
+  for (unsigned long long ch = ch_begin; ch < ch_end; ++ch) {
+    const unsigned long long j = ch * 32 + lane;
+    const bool have = j < N;
+    const unsigned long long a = nz_ptr[have ? j : N], b = nz_ptr[have ? j + 1 : N];
+    const double c = have ? counts[j] : 0.0;
+    double bj = 0.0, vj = 0.0;
+    if (MODE == 0 && have) { bj = sp_b[j]; vj = sp_v[j]; }
+    const unsigned long long h0 = __shfl_sync(0xffffffffu, a, 0), h1 = __shfl_sync(0xffffffffu, b, 31);
+    const double vn = MODE == 0 ? fma(beta, vj, l0 - bj) : 0.0;       // class part of the step
+    const double bb = MODE == 0 ? bj + vn + shift : l0 + shift;        // class part of gamma before normalisation
+    const bool one_piece = h1 - h0 <= RS_STAGE;
+    double mx = bb, sumE = 0.0, sumEa = 0.0, ssum = 0.0;
+    for (int round = 0; round < 3; ++round) {
+      for (unsigned long long q0 = h0; q0 < h1; q0 += RS_STAGE) {
+        const int n_here = (int)min((unsigned long long)RS_STAGE, h1 - q0);
+        if (round == 0 || !one_piece) {
+          __syncwarp();
+          for (int x = lane; x < n_here; x += 32) {               // hit-parallel, coalesced
+            const uint32_t kg = nz_grp[q0 + x];
+            const int k = (int)(kg & SP_GRP_MASK);
+            const double lg = nz_logl[q0 + x];
+            double g2;
+            if (MODE == 0) {
+              const double g = sp_g[q0 + x];
+              double tn;
+              if (round == 0) { tn = fma(beta, sp_t[q0 + x], lg + s_psi[k] - g); sp_t[q0 + x] = tn; }   // the new direction leaves at once
+              else tn = sp_t[q0 + x];                             // (a chunk in several pieces: the step is already the new one)
+              g2 = g + tn;
+            } else {
+              g2 = lg + s_psi[k];
+            }
+            key[x] = kg; gg[x] = g2; ll[x] = lg;
+          }
+          __syncwarp();
+        }
+        if (round == 0) {                                         // class-parallel, list order
+          const unsigned long long lo = max(a, q0), hi = min(b, q0 + (unsigned long long)n_here);
+          for (unsigned long long x = lo; x < hi; ++x) {
+            mx = fmax(mx, gg[x - q0]);
+            const int k = (int)(key[x - q0] & SP_GRP_MASK);
+            sumE += s_En[k];
+            sumEa = fma(s_En[k], s_an[k], sumEa);
+          }
+        } else if (round == 1) {
+          const unsigned long long lo = max(a, q0), hi = min(b, q0 + (unsigned long long)n_here);
+          for (unsigned long long x = lo; x < hi; ++x) ssum += exp_nonpos(gg[x - q0] - mx);
+        } else {
+          for (int x = lane; x < n_here; x += 32) {               // hit-parallel: normalised gamma out, N_k scatter, bound
+            const uint32_t kg = key[x];
+            const int k = (int)(kg & SP_GRP_MASK), cl = (int)(kg >> 24);
+            const double gnew = gg[x] - cls_m[cl];
+            sp_g[q0 + x] = gnew;
+            const double cj = cls_c[cl];
+            if (cj > 0.0) {
+              const double cq = cj * exp_nonpos(fmin(gnew, 0.0));           // c_j q(j,k)
+              bound = fma(cq, ll[x] - gnew, bound);
+              const double val = cq - cls_cw[cl] * s_En[k];                   // the group's closed-form share already counts exp(b_j') E'_k
+              if (val != 0.0) fx_atomic_add(&s_acc[2 * k], __double2ll_rn(val * fx_scale));
+            }
+          }
+        }
+      }
+      if (round == 1) {
+        // normaliser of the class: exp(bb - mx) (M0' - sum_H E') + sum_hits exp(gg - mx)
+        const double rest = fmax(m0n - sumE, 0.0);
+        const double tot = fma(exp_nonpos(bb - mx), rest, ssum);
+        const double m = mx + log(tot);
+        const double bnew = bb - m;
+        const double wnew = exp(bnew);
+        if (have) {
+          sp_b[j] = bnew;
+          if (MODE == 0) sp_v[j] = vn;
+          if (c > 0.0) {
+            mass = fma(c, wnew, mass);
+            // non-hit part of the bound: c_j exp(b_j') ((l0 - b_j') (M0' - sum_H E') - (Ma' - sum_H E' a'))
+            bound = fma(c * wnew, (l0 - bnew) * rest - (man - sumEa), bound);
+          }
+        }
+        __syncwarp();
+        cls_m[lane] = m;
+        cls_cw[lane] = c * wnew;
+        cls_c[lane] = c;
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+  double *out = partials + (unsigned long long)blockIdx.x * pstride;
+  const double fx_inv = 1.0 / fx_scale;
+  for (int k = threadIdx.x; k < K; k += RS_NT) {
+    const long long v = (long long)(((unsigned long long)s_acc[2 * k + 1] << 32) | (unsigned long long)s_acc[2 * k]);
+    out[k] = (double)v * fx_inv;
+  }
+  bound = block_sum<RS_NT>(bound, s_blk);
+  mass = block_sum<RS_NT>(mass, s_blk);
+  if (threadIdx.x == 0) { out[K + RS_BOUND] = bound; out[K + RS_MASS] = mass; }
+  if constexpr (TAIL) {
+    if (tail != 0 && cta_is_last(ctl)) {
+      reduce_partials_cta<RS_NT>(partials, pstride, (int)gridDim.x, K + 2, va.red, va.seg);   // (slot RS_NORM stays: sweep A's norm)
+      if (threadIdx.x == 0) ctl->ticket = 0;
+      if (tail == 2) {
+        __syncthreads();
+        rcgs_ctl_b_step<RS_NT>(va, grp, ctl, K, MODE, 0, s_blk);
+      }
+    }
+  }
+}
+inline size_t rcgs_sweep_b_smem(int K) {
+  return (size_t)K * 32 + (size_t)(RS_NT / 32) * RS_STAGE * (16 + 4) + (size_t)(RS_NT / 32) * 96 * 8;
+}
+
+// Reduction of the partial vectors of sweep B over several CTAs (large grids x many groups); ctl_stage >= 0: the last
+// CTA takes the control step (one GPU), -1: the all-reduce and rcgs_ctl_b_kernel follow.
+__global__ void __launch_bounds__(FIN_NT)
+rcgs_finalize_kernel(const double *partials, int pstride, int n_ctas, ViArrays va, RcgsGroup grp, ViCtl *ctl, int K, int ctl_stage,
+                     int restart) {
+  if (ctl->done) return;
+  if (restart ? !ctl->didreset : ctl->stall != 0) return;
+  __shared__ double s_blk[32];
+  reduce_partials(partials, pstride, n_ctas, K + 2, va.red, (int)(blockIdx.x * FIN_NT + threadIdx.x), (int)(gridDim.x * FIN_NT));
+  if (ctl_stage < 0) return;
+  if (!cta_is_last(ctl)) return;
+  if (threadIdx.x == 0) ctl->ticket = 0;
+  __syncthreads();
+  rcgs_ctl_b_step<FIN_NT>(va, grp, ctl, K, ctl_stage, 0, s_blk);
+}
+
+// Start: gamma = log(1/K) everywhere (a = 0, b = log(1/K), hits log(1/K)), no direction; moments for the first sweep A.
+__global__ void __launch_bounds__(256) rcgs_init_groups_kernel(ViArrays va, RcgsGroup g, int K) {
+  __shared__ double scratch[32];
+  for (int k = threadIdx.x; k < K; k += 256) { g.a[k] = 0.0; g.u[k] = 0.0; g.a_new[k] = 0.0; g.u_new[k] = 0.0; }
+  __syncthreads();
+  rcgs_prep_a<256>(va, g, K, scratch);
+}
+
+} // namespace mswb

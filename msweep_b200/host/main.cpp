@@ -100,7 +100,7 @@ const char *kHelp =
     "  --gpus                       number of B200s to use (default: 1)\n"
     "  --algorithm                  rcgb200 | emb200 (aliases: rcggpu, emgpu; default: rcgb200)\n"
     "  --emprecision                float | double, for emb200 (default: double)\n"
-    "  --storage                    dense | sparse likelihood on the device, sparse for emb200 only (default: dense)\n"
+    "  --storage                    dense | sparse likelihood on the device (default: dense; sparse = lossless, O(hits) per class)\n"
     "  --max-iters                  optimiser iteration cap (default: 5000)\n"
     "  --tol                        stop when the bound changes by less than this (default: 0.000001)\n"
     "  --iters                      bootstrap replicates (default: 0)\n"
@@ -227,7 +227,6 @@ int main(int argc, char *argv[]) {
     else if (prec != "double") throw std::runtime_error("Unknown --emprecision `" + prec + "` (one of float, double)");
     const std::string store = args.str("storage", "dense");
     if (store == "sparse") {
-      if (vi.algo != MSWB_ALGO_EM) throw std::runtime_error("--storage sparse needs --algorithm emb200 (RCG keeps dense per-class state)");
       if (args.has("write-probs") || args.has("print-probs") || args.has("bin-reads"))
         throw std::runtime_error("--storage sparse cannot export the probability matrix; use --storage dense");
       storage = MSWB_STORE_SPARSE;

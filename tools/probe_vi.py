@@ -21,10 +21,10 @@ ctx = M.Context(0)
 t0 = time.time(); aln = M.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets); print(f"ec_build {time.time()-t0:.3f}s n_ecs={aln.n_ecs}", flush=True)
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6650.0
 for mode in a.modes.split(","):
-    storage = M.STORE_F32 if mode == "em32" else (M.STORE_SPARSE if mode == "emsp" else M.STORE_F64)
+    storage = M.STORE_F32 if mode == "em32" else (M.STORE_SPARSE if mode in ("emsp", "rcgsp") else M.STORE_F64)
     t0 = time.time(); lik = M.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=storage); ctx.sync()
     print(f"[{mode}] lik_build {time.time()-t0:.3f}s K={lik.n_groups} N={lik.n_ecs}", flush=True)
-    algo = M.ALGO_RCG if mode == "rcg" else M.ALGO_EM
+    algo = M.ALGO_RCG if mode in ("rcg", "rcgsp") else M.ALGO_EM
     s = lik.vi_begin(algo, tol=0.0, max_iters=10**6, time_kernels=not a.no_events)
     s.step(3); st = s.poll()
     ms0, n0 = st.pass_ms_sum, st.pass_launches

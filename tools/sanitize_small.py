@@ -26,7 +26,28 @@ for K, T, R in ((7, 70, 600), (300, 1500, 800), (1100, 3300, 300)):
         lik.close()
     aln.close()
 rng = np.random.default_rng(0)
-logl = rng.normal(-5, 2, size=(33, 129)); lc = np.log(rng.integers(1, 9, size=129).astype(float))
-lik = M.Likelihood.from_dense(ctx, logl, lc)
-lik.vi_run(M.ALGO_RCG, max_iters=5, tol=-1e300); lik.vi_run(M.ALGO_EM, max_iters=5, tol=0.0)
+# dense entry over the sub-warp tile shapes (rows of 1..32 pieces), both tails (last-CTA reduction + control step, and
+# finalize_ctl_kernel with MSWB_TAIL_MAX=0), fp64 and fp32 storage
+for K, N in ((3, 70), (8, 300), (13, 129), (30, 257), (50, 700), (33, 129)):
+    logl = rng.normal(-5, 2, size=(K, N)); lc = np.log(rng.integers(1, 9, size=N).astype(float))
+    for tail_max in (None, "0"):
+        if tail_max is not None:
+            os.environ["MSWB_TAIL_MAX"] = tail_max
+        lik = M.Likelihood.from_dense(ctx, logl, lc)
+        lik.vi_run(M.ALGO_RCG, max_iters=5, tol=-1e300); lik.vi_run(M.ALGO_EM, max_iters=5, tol=0.0)
+        lik.close()
+        lik = M.Likelihood.from_dense(ctx, logl, lc, storage=M.STORE_F32)
+        lik.vi_run(M.ALGO_EM, max_iters=5, tol=0.0)
+        lik.close()
+        os.environ.pop("MSWB_TAIL_MAX", None)
+# bootstrap replicates as device batches (EM, dense): ragged last slice, fp64 and fp32, three row shapes
+for K, T, R in ((6, 60, 500), (300, 1200, 700), (1100, 3300, 300)):
+    wl = synth.generate(R, T, K, n_present=3, n_templates=30, p_noise=0.05, seed=K + 1)
+    aln = M.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    for storage in (M.STORE_F64, M.STORE_F32):
+        lik = M.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=storage)
+        th, _ = lik.bootstrap_run(5, seed=3, algo=M.ALGO_EM, max_iters=6, tol=0.0)
+        assert np.all(np.abs(th.sum(axis=1) - 1) < 1e-6)
+        lik.close()
+    aln.close()
 print("sanitize run ok, launches:", M.launch_count())
