@@ -248,6 +248,7 @@ def parity_check(M, dist, ctx, rank, world):
     compare("rcg_min_hits", lik_mh.vi_run(M.ALGO_RCG), "rcg_mh")
     sp = M.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=M.STORE_SPARSE)
     compare("em_sparse", sp.vi_run(M.ALGO_EM), "em")
+    compare("rcg_sparse", sp.vi_run(M.ALGO_RCG), "rcg")
     for x in (lik, lik_mh, sp):
         x.close()
     aln.close()
@@ -267,7 +268,9 @@ def parity_check(M, dist, ctx, rank, world):
         ecs_ok = ecs_ok and int(dist.reduce_sum(aln_p.n_ecs)) == int(g["n_ecs"]) == lik_p.n_ecs_total
         compare("rcg_hash_partitioned", lik_p.vi_run(M.ALGO_RCG), "rcg")
         compare("em_hash_partitioned", lik_p.vi_run(M.ALGO_EM), "em")
-        lik_p.close(); aln_p.close()
+        sp_p = M.Likelihood.build(ctx, aln_p, wl.group_of_target, wl.group_sizes, storage=M.STORE_SPARSE)
+        compare("rcg_sparse_hash_partitioned", sp_p.vi_run(M.ALGO_RCG), "rcg")
+        sp_p.close(); lik_p.close(); aln_p.close()
     ecs_ok = bool(dist.reduce_sum(0 if ecs_ok else 1) == 0)
     out.update({"theta_maxabs": theta_err, "bound_rel": bound_rel, "iters_equal": bool(iters_ok), "n_ecs_equal": ecs_ok,
                 "ok": bool(theta_err < 1e-6 and bound_rel < 1e-9 and iters_ok and ecs_ok and out["min_hits_mask_equal"]),
@@ -407,7 +410,19 @@ def extra_c2_c5(a, torch, M, dist, ctx, stream, rank, world, want_c2, want_c5, p
                 if s["achieved_gbs"]:
                     s["frac_of_measured_peak"] = s["achieved_gbs"] / peak
             kept = wl.truth > 0
+            t0 = time.perf_counter()
+            sp = M.Likelihood.build(solo, aln, wl.group_of_target, wl.group_sizes, storage=M.STORE_SPARSE)
+            solo.sync(); t_lik_sp = time.perf_counter() - t0
+            r_rcg_sp, s_rcg_sp = run_to_convergence(M, solo, sp, M.ALGO_RCG)
+            r_em_sp, s_em_sp = run_to_convergence(M, solo, sp, M.ALGO_EM)
+            sp.close()
+            for s_, r_, ref_ in ((s_rcg_sp, r_rcg_sp, r_rcg), (s_em_sp, r_em_sp, r_em)):
+                s_["frac_of_measured_peak_own_bytes"] = s_["achieved_gbs"] / peak if s_["achieved_gbs"] else None
+                s_["max_abs_theta_diff_vs_dense"] = float(np.max(np.abs(r_.theta - ref_.theta)))
+                s_["iters_equal_dense"] = int(r_.iters) == int(ref_.iters)
             out["c2"] = {"config": "2: 1e7 reads / ~1e6 ECs x 60,000 refs in 1,000 lineages, fp64 VI on 1 GPU", **shape, "rcg": s_rcg, "em": s_em,
+                         "sparse_likelihood_s": round(t_lik_sp, 4), "rcg_sparse": s_rcg_sp, "em_sparse": s_em_sp,
+                         "e2e_seconds_from_host_csr_rcg_sparse": round(t_ec + t_lik_sp + s_rcg_sp["seconds"], 4),
                          "max_abs_theta_diff_em_vs_rcg": float(np.max(np.abs(r_rcg.theta - r_em.theta))),
                          "max_abs_err_vs_generating_theta": float(np.max(np.abs(r_rcg.theta - wl.truth))),
                          "present_lineages_recovered": int(np.sum(r_rcg.theta[kept] > 1e-4)), "present_lineages": int(kept.sum()),
@@ -418,7 +433,8 @@ def extra_c2_c5(a, torch, M, dist, ctx, stream, rank, world, want_c2, want_c5, p
             n_rep_job = B if world >= 8 else int(np.ceil(B / 8)) * world
             res = {}
             sparse = M.Likelihood.build(solo, aln, wl.group_of_target, wl.group_sizes, storage=M.STORE_SPARSE)
-            for name, algo, L in (("rcg", M.ALGO_RCG, lik), ("em_batched", M.ALGO_EM, lik), ("em_sparse", M.ALGO_EM, sparse)):
+            for name, algo, L in (("rcg", M.ALGO_RCG, lik), ("em_batched", M.ALGO_EM, lik), ("em_sparse", M.ALGO_EM, sparse),
+                                  ("rcg_sparse", M.ALGO_RCG, sparse)):
                 dist.barrier()
                 t0 = time.perf_counter()
                 thetas, iters = L.bootstrap_run(n_rep_job, seed=11, algo=algo, replica_rank=rank, replica_world=world)
@@ -435,7 +451,8 @@ def extra_c2_c5(a, torch, M, dist, ctx, stream, rank, world, want_c2, want_c5, p
             sparse.close()
             res["how"] = {"rcg": "one replicate after the other, each a cold-start RCG run (the reference's default algorithm)",
                           "em_batched": "dense fp64: all count vectors of the rank resampled first, then ONE sweep of the matrix per iteration serves every replicate still running (em_lin_batch_kernel)",
-                          "em_sparse": "lossless sparse storage: one replicate after the other, each pass reads ~90 B per class instead of 8 KB"}
+                          "em_sparse": "lossless sparse storage: one replicate after the other, each pass reads ~90 B per class instead of 8 KB",
+                          "rcg_sparse": "RCG on the sparse storage (separable state off the hits): one replicate after the other, the reference's default algorithm"}
             out["c5"] = {"config": f"5: --iters {B} bootstrap on 1e7 reads x 1,000 lineages, replicates spread over 8 GPUs "
                                    f"(this run: {n_rep_job} replicates on {world} GPU(s), replicas only, exact std::mt19937_64 resampling)",
                          **shape, **res}
@@ -469,7 +486,15 @@ def extra_c4(a, torch, M, ctx, stream, peak):
                 s["frac_of_measured_peak"] = s["achieved_gbs"] / peak
         out["max_abs_theta_diff_em_vs_rcg"] = float(np.max(np.abs(r_rcg.theta - r_em.theta)))
         out["max_abs_err_vs_generating_theta"] = float(np.max(np.abs(r_rcg.theta - wl.truth[kept])))
-        lik.close(); aln.close()
+        lik.close()
+        t0 = time.perf_counter(); sp = M.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, min_hits=1, storage=M.STORE_SPARSE); ctx.sync()
+        out["sparse_likelihood_mask_compaction_s"] = round(time.perf_counter() - t0, 4)
+        r_sp, out["rcg_sparse"] = run_to_convergence(M, ctx, sp, M.ALGO_RCG)
+        out["rcg_sparse"]["max_abs_theta_diff_vs_dense"] = float(np.max(np.abs(r_sp.theta - r_rcg.theta)))
+        out["rcg_sparse"]["iters_equal_dense"] = int(r_sp.iters) == int(r_rcg.iters)
+        r_sp, out["em_sparse"] = run_to_convergence(M, ctx, sp, M.ALGO_EM)
+        out["em_sparse"]["max_abs_theta_diff_vs_dense"] = float(np.max(np.abs(r_sp.theta - r_em.theta)))
+        sp.close(); aln.close()
     return out
 
 
@@ -488,6 +513,10 @@ def extra_sparse(a, torch, M, dist, ctx, stream, rank, world, wl_main, peak):
         n_job = dist.reduce_sum(lik.n_ecs)
         s = timed_series(torch, M, dist, stream, lik, M.ALGO_EM, steps, warmup)
         out = series_summary(s, steps, lik.n_ecs, N_GROUPS, peak)
+        s_rcg = timed_series(torch, M, dist, stream, lik, M.ALGO_RCG, 20, warmup)
+        out["rcg"] = series_summary(s_rcg, 20, lik.n_ecs, N_GROUPS, peak)
+        out["rcg"]["what"] = ("RCG (the reference's default optimiser) on the same job: dense state would be 3.2 TB; the sparse form keeps "
+                              "two K-vectors, two N-vectors and the hits")
         lik.close(); aln.close()
         torch.cuda.synchronize(); dist.barrier()
         t0 = time.perf_counter()

@@ -4,11 +4,12 @@
 // The reference draws `bootstrap_count` categorical samples one at a time from
 // std::discrete_distribution<uint32_t>(class counts) driven by std::mt19937_64, i.e. per draw:
 // one 64-bit Mersenne-Twister output u, p = double(u) * 2^-64 (nextafter(1,0) if that rounds to 1),
-// class = lower_bound(cumulative probabilities, p).  In MSWB_RNG_LIBSTDCXX_EXACT mode the raw
-// generator stream is produced on the host (it is inherently sequential and costs ~2 ns per draw) and
-// the expensive part — bootstrap_count binary searches over N cumulative probabilities plus the
-// histogram — runs on the device, so the resampled counts are bit-identical to the reference's.
-// MSWB_RNG_PHILOX replaces the stream by a counter-based generator evaluated on the device.
+// class = lower_bound(cumulative probabilities, p).  In MSWB_RNG_LIBSTDCXX_EXACT mode the very same generator
+// stream is produced ON THE DEVICE: the MT19937-64 recurrence x[k+312] = x[k+156] ^ f(x[k], x[k+1]) reaches back at
+// least 156 words, so one CTA advances the state 156 words at a time in parallel (mt64_generate_kernel: ~3 ms for the 1e7
+// draws of a replicate, against ~80 ms for std::mt19937_64 on a host core plus the copy); the binary searches over the N
+// cumulative probabilities and the histogram follow, and the resampled counts are bit-identical to the reference's.
+// MSWB_RNG_PHILOX replaces the stream by a counter-based generator.
 #include "handles.cuh"
 
 #include <cmath>
@@ -42,6 +43,54 @@ __global__ void resample_from_stream_kernel(const unsigned long long *__restrict
     const unsigned long long idx = n_cp ? lower_bound_idx(cp, n_cp, canonical_from_u64(stream[i])) : 0ull;
     atomicAdd(&hist[idx], 1u);
   }
+}
+
+// ---- std::mt19937_64 on the device ----------------------------------------------------------------------------------
+// state[0..311] = the generator's words, state[312] = how many of them have been consumed (312: refill first, the state
+// std::mt19937_64 is in right after seeding).  Produces the next n outputs of the stream into out (nullptr: discard — the
+// replicates of other ranks) and leaves the state where the stream continues.
+constexpr int MT_N = 312, MT_M = 156, MT_NT = 320;
+__device__ __forceinline__ unsigned long long mt64_temper(unsigned long long y) {
+  y ^= (y >> 29) & 0x5555555555555555ull;
+  y ^= (y << 17) & 0x71D67FFFEDA60000ull;
+  y ^= (y << 37) & 0xFFF7EEE000000000ull;
+  y ^= (y >> 43);
+  return y;
+}
+__device__ __forceinline__ unsigned long long mt64_twist(unsigned long long far, unsigned long long cur, unsigned long long nxt) {
+  const unsigned long long y = (cur & 0xFFFFFFFF80000000ull) | (nxt & 0x7FFFFFFFull);
+  return far ^ (y >> 1) ^ ((y & 1ull) ? 0xB5026F5AA96619E9ull : 0ull);
+}
+__global__ void __launch_bounds__(MT_NT) mt64_generate_kernel(unsigned long long *__restrict__ state, unsigned long long n,
+                                                              unsigned long long *__restrict__ out) {
+  __shared__ unsigned long long x[MT_N];
+  const int t = threadIdx.x;
+  for (int i = t; i < MT_N; i += MT_NT) x[i] = state[i];
+  unsigned long long pos = state[MT_N];
+  __syncthreads();
+  unsigned long long produced = 0;
+  while (produced < n) {
+    if (pos == MT_N) {
+      // words 0..155 depend on old words only; words 156..311 on the new first half and old words (word 311 on new word 0)
+      unsigned long long v = 0;
+      if (t < MT_M) v = mt64_twist(x[t + MT_M], x[t], x[t + 1]);
+      __syncthreads();
+      if (t < MT_M) x[t] = v;
+      __syncthreads();
+      if (t < MT_M) v = mt64_twist(x[t], x[t + MT_M], x[(t + MT_M + 1) % MT_N]);
+      __syncthreads();
+      if (t < MT_M) x[t + MT_M] = v;
+      __syncthreads();
+      pos = 0;
+    }
+    const unsigned long long take = min((unsigned long long)MT_N - pos, n - produced);
+    if (out) for (unsigned long long i = t; i < take; i += MT_NT) out[produced + i] = mt64_temper(x[pos + i]);
+    produced += take;
+    pos += take;
+  }
+  __syncthreads();
+  for (int i = t; i < MT_N; i += MT_NT) state[i] = x[i];
+  if (t == 0) state[MT_N] = pos;
 }
 
 // Philox-4x32-10 keyed by (seed, replicate), counter = draw index / 2; two 64-bit outputs per block.
@@ -89,12 +138,11 @@ struct Resampler {
   uint64_t N = 0, draws = 0;
   int rng_mode;
   uint64_t seed64 = 0;
-  std::mt19937_64 gen;
   DevBuf<double> cp;           // cumulative probabilities (empty when N < 2, as in libstdc++)
   uint64_t n_cp = 0;
+  DevBuf<unsigned long long> mt_state;     // [313] std::mt19937_64's words + consumed count (mt64_generate_kernel)
   DevBuf<unsigned long long> stream_dev;
-  PinnedBuf<unsigned long long> stream_host;
-  static constexpr uint64_t CHUNK = 1u << 22;
+  static constexpr uint64_t CHUNK = 1u << 24;   // draws generated and consumed at a time (128 MB of stream)
 
   Resampler(mswb_ctx *c, const mswb_lik *lik, int32_t seed, uint64_t bootstrap_count, int mode) : ctx(c), rng_mode(mode) {
     MSWB_REQUIRE(mode == MSWB_RNG_LIBSTDCXX_EXACT || mode == MSWB_RNG_PHILOX, "unknown rng mode");
@@ -123,14 +171,30 @@ struct Resampler {
       n_cp = N;
     }
     // src/BootstrapSample.cpp:48-53 (seed narrowed to int32_t by include/Sample.hpp:163-169)
-    if (seed == 26012023) { std::random_device rd; seed64 = rd(); gen = std::mt19937_64(seed64); }
-    else { gen = std::mt19937_64(seed); seed64 = (uint64_t)(int64_t)seed; }
-    if (mode == MSWB_RNG_LIBSTDCXX_EXACT) { stream_dev.alloc(CHUNK); stream_host.alloc(2 * CHUNK); }
+    if (seed == 26012023) { std::random_device rd; seed64 = rd(); }
+    else seed64 = (uint64_t)(int64_t)seed;
+    if (mode == MSWB_RNG_LIBSTDCXX_EXACT) {
+      // std::mersenne_twister_engine<uint64_t, 64, 312, ...>::seed(value): x[0] = value, x[i] = f * (x[i-1] ^ (x[i-1] >> 62)) + i,
+      // and the first output refills
+      std::vector<unsigned long long> st(MT_N + 1);
+      st[0] = seed64;
+      for (int i = 1; i < MT_N; ++i) st[i] = 6364136223846793005ull * (st[i - 1] ^ (st[i - 1] >> 62)) + (unsigned long long)i;
+      st[MT_N] = MT_N;
+      mt_state.alloc(MT_N + 1);
+      h2d(mt_state.p, st.data(), st.size(), s);
+      MSWB_CUDA(cudaStreamSynchronize(s));
+      stream_dev.alloc(std::min<uint64_t>(CHUNK, std::max<uint64_t>(draws, 1)));
+    }
   }
 
-  void skip() { if (rng_mode == MSWB_RNG_LIBSTDCXX_EXACT) gen.discard(draws); }
+  // another rank's replicate: its draws are consumed, nothing else
+  void skip() {
+    if (rng_mode != MSWB_RNG_LIBSTDCXX_EXACT || draws == 0) return;
+    mt64_generate_kernel<<<1, MT_NT, 0, ctx->stream>>>(mt_state.p, draws, nullptr);
+    MSWB_LAUNCHED();
+  }
 
-  // hist_dev[N] (zeroed here) receives the resampled class counts of the next replicate
+  // hist_dev[N] (zeroed here) receives the resampled class counts of the next replicate; everything is enqueued, nothing waits
   void next(uint64_t replicate, unsigned *hist_dev) {
     cudaStream_t s = ctx->stream;
     MSWB_CUDA(cudaMemsetAsync(hist_dev, 0, std::max<uint64_t>(N, 1) * sizeof(unsigned), s));
@@ -139,26 +203,13 @@ struct Resampler {
       if (draws) { resample_philox_kernel<<<grid, 256, 0, s>>>(seed64, replicate, draws, cp.p, n_cp, hist_dev); MSWB_LAUNCHED(); }
       return;
     }
-    // double-buffered: the host fills chunk c+1 while the device consumes chunk c
-    cudaEvent_t ev[2];
-    MSWB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-    MSWB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-    bool used[2] = {false, false};
-    int slot = 0;
-    for (uint64_t done = 0; done < draws; done += CHUNK, slot ^= 1) {
+    for (uint64_t done = 0; done < draws; done += CHUNK) {
       const uint64_t n = std::min<uint64_t>(CHUNK, draws - done);
-      unsigned long long *hbuf = stream_host.p + (size_t)slot * CHUNK;
-      if (used[slot]) MSWB_CUDA(cudaEventSynchronize(ev[slot]));
-      for (uint64_t i = 0; i < n; ++i) hbuf[i] = gen();
-      // the single device buffer is safe: copy and kernel are ordered on one stream
-      h2d(stream_dev.p, hbuf, n, s);
-      MSWB_CUDA(cudaEventRecord(ev[slot], s));
-      used[slot] = true;
+      mt64_generate_kernel<<<1, MT_NT, 0, s>>>(mt_state.p, n, stream_dev.p);
+      MSWB_LAUNCHED();
       resample_from_stream_kernel<<<grid, 256, 0, s>>>(stream_dev.p, n, cp.p, n_cp, hist_dev);
       MSWB_LAUNCHED();
     }
-    MSWB_CUDA(cudaStreamSynchronize(s));
-    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
   }
 };
 

@@ -138,47 +138,56 @@ static int ec_build_impl(mswb_ctx *ctx, uint64_t n_reads, uint64_t n_targets, co
     MSWB_REQUIRE(!bad, "pseudoalignment rows must hold strictly ascending target ids below n_targets");
     A->n_aligned = n_al;
 
-    // K2: stable LSD radix sort by hash (read ids stay ascending inside equal hashes), then run-length encode
+    // K2: stable LSD radix sort by hash (read ids stay ascending inside equal hashes), then run-length encode.
+    // Everything up to the pattern offsets is enqueued against capacity-n_al scratch, so that the class count and the
+    // pattern size come back in ONE round trip (two host synchronisations per build: this one and the one above).
     d_keys_out.alloc(n_al); d_ids_out.alloc(n_al); d_head.alloc(n_al); d_ec_of.alloc(n_al);
-    uint64_t n_ecs = 0;
+    DevBuf<uint64_t> t_hash, t_read_ptr, t_pat_ptr;
+    DevBuf<uint32_t> t_rep;
+    t_hash.alloc(n_al); t_rep.alloc(n_al); t_read_ptr.alloc(n_al + 1); t_pat_ptr.alloc(n_al + 1);
+    d_pat_len.alloc(n_al + 1);
+    MSWB_CUDA(cudaMemsetAsync(d_pat_len.p, 0, (n_al + 1) * sizeof(uint64_t), s));
+    uint64_t n_ecs = 0, pat_nnz = 0;
     if (n_al) {
       MSWB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_keys_in.p, d_keys_out.p, d_ids_in.p, d_ids_out.p, (int64_t)n_al, 0, 64, s));
       head_flags_kernel<<<grid, 256, 0, s>>>(d_keys_out.p, n_al, d_head.p);
       MSWB_LAUNCHED();
       MSWB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_head.p, d_ec_of.p, (int64_t)n_al, s));
+      scatter_heads_kernel<<<grid, 256, 0, s>>>(d_keys_out.p, d_ids_out.p, d_head.p, d_ec_of.p, n_al, d_row_ptr.p,
+                                                t_hash.p, t_rep.p, t_read_ptr.p, d_pat_len.p);
+      MSWB_LAUNCHED();
+      // pattern lengths sit at [0, n_ecs), zeros behind: the scan over the whole scratch ends in the pattern size
+      MSWB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_pat_len.p, t_pat_ptr.p, (int64_t)n_al + 1, s));
       uint32_t last_idx = 0, last_head = 0;
       d2h(&last_idx, d_ec_of.p + (n_al - 1), 1, s);
       d2h(&last_head, d_head.p + (n_al - 1), 1, s);
+      d2h(&pat_nnz, t_pat_ptr.p + n_al, 1, s);
       MSWB_CUDA(cudaStreamSynchronize(s));
       n_ecs = (uint64_t)last_idx + last_head;
     }
     A->n_ecs = n_ecs;
+    A->pat_nnz = pat_nnz;
     A->hash.alloc(n_ecs); A->count.alloc(n_ecs); A->rep_read.alloc(n_ecs);
     A->read_ptr.alloc(n_ecs + 1); A->pat_ptr.alloc(n_ecs + 1);
-    d_pat_len.alloc(n_ecs + 1);
-    MSWB_CUDA(cudaMemsetAsync(d_pat_len.p, 0, (n_ecs + 1) * sizeof(uint64_t), s));
+    A->pat_targets.alloc(pat_nnz);
     if (n_ecs) {
-      scatter_heads_kernel<<<grid, 256, 0, s>>>(d_keys_out.p, d_ids_out.p, d_head.p, d_ec_of.p, n_al, d_row_ptr.p,
-                                                A->hash.p, A->rep_read.p, A->read_ptr.p, d_pat_len.p);
-      MSWB_LAUNCHED();
+      MSWB_CUDA(cudaMemcpyAsync(A->hash.p, t_hash.p, n_ecs * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+      MSWB_CUDA(cudaMemcpyAsync(A->rep_read.p, t_rep.p, n_ecs * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+      MSWB_CUDA(cudaMemcpyAsync(A->read_ptr.p, t_read_ptr.p, n_ecs * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+      MSWB_CUDA(cudaMemcpyAsync(A->pat_ptr.p, t_pat_ptr.p, (n_ecs + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    } else {
+      MSWB_CUDA(cudaMemsetAsync(A->pat_ptr.p, 0, sizeof(uint64_t), s));
     }
     h2d(A->read_ptr.p + n_ecs, (const uint64_t *)&A->n_aligned, 1, s);
     if (n_ecs) {
       class_counts_kernel<<<grid, 256, 0, s>>>(A->read_ptr.p, n_ecs, A->count.p);
       MSWB_LAUNCHED();
-    }
-    MSWB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_pat_len.p, A->pat_ptr.p, (int64_t)n_ecs + 1, s));
-    uint64_t pat_nnz = 0;
-    d2h(&pat_nnz, A->pat_ptr.p + n_ecs, 1, s);
-    MSWB_CUDA(cudaStreamSynchronize(s));
-    A->pat_nnz = pat_nnz;
-    A->pat_targets.alloc(pat_nnz);
-    if (n_ecs) {
       gather_patterns_kernel<<<grid, 256, 0, s>>>(d_row_ptr.p, d_targets.p, A->rep_read.p, A->pat_ptr.p, n_ecs, A->pat_targets.p);
       MSWB_LAUNCHED();
     }
     A->read_ids = std::move(d_ids_out);
-    MSWB_CUDA(cudaStreamSynchronize(s));
+    // (no further synchronisation: everything downstream runs on the same stream, and the scratch buffers above are
+    // released through cudaFree / the block cache, both of which wait for the device)
     *out = A.release();
   });
 }

@@ -72,6 +72,7 @@ struct mswb_lik {
   mswb::DevBuf<double> gamma;    // [N x Kp] RCG log-responsibilities
   mswb::DevBuf<double> step;     // [N x Kp] RCG search direction
   mswb::DevBuf<double> last_dg;  // [K] digamma(N_k) of the last EM pass (posteriors on demand)
+  mswb::DevBuf<double> last_a;   // [K] group part of gamma after the last sparse RCG run (posteriors on demand)
   int last_algo = -1;
 
   // result of the last mswb_vi_assign, waiting for mswb_vi_assign_fetch

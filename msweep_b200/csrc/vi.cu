@@ -159,15 +159,78 @@ __global__ void posterior_tile_kernel(int source, const double *__restrict__ gam
   }
 }
 
+// The same tile from the SPARSE storage, one warp per class.
+//   source 0 (RCG): gamma = a_k + b_j off the hits, g_e on them (vi_sparse_rcg.cuh).
+//   source 1 (EM) : gamma = logl_jk + dg_k - L_j with logl = l0 off the hits, L_j = M_j + dg_max + log S_j,
+//                   S_j = P0_j W + sum_hits dP_e exp(dg_k - dg_max), W = sum_k exp(dg_k - dg_max) (aux[0], aux[1] = dg_max).
+__global__ void posterior_tile_sparse_kernel(int source, const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp,
+                                             const double *__restrict__ hit_val /* sp_g | nz_dP */, const double *__restrict__ nz_logl,
+                                             const double *__restrict__ cls_val /* sp_b | P0 */, const double *__restrict__ rowmax,
+                                             const double *__restrict__ grp_vec /* a | dg */, const double *__restrict__ aux, double l0,
+                                             unsigned long long row0, unsigned long long n_rows, int K, double *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long warp = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long j = warp; j < n_rows; j += n_warps) {
+    const unsigned long long row = row0 + j, a = nz_ptr[row], b = nz_ptr[row + 1];
+    if (source == 0) {
+      const double bj = cls_val[row];
+      for (int k = lane; k < K; k += 32) out[(size_t)k * n_rows + j] = grp_vec[k] + bj;
+      __syncwarp();
+      for (unsigned long long e = a + lane; e < b; e += 32) out[(size_t)(nz_grp[e] & SP_GRP_MASK) * n_rows + j] = hit_val[e];
+    } else {
+      const double mx = aux[1];
+      double s = 0.0;
+      for (unsigned long long e = a + lane; e < b; e += 32) s = fma(hit_val[e], exp(grp_vec[nz_grp[e] & SP_GRP_MASK] - mx), s);
+      s = warp_sum(s);
+      const double L = rowmax[row] + mx + log(fma(cls_val[row], aux[0], s));
+      for (int k = lane; k < K; k += 32) out[(size_t)k * n_rows + j] = l0 + grp_vec[k] - L;
+      __syncwarp();
+      for (unsigned long long e = a + lane; e < b; e += 32) {
+        const int k = (int)(nz_grp[e] & SP_GRP_MASK);
+        out[(size_t)k * n_rows + j] = nz_logl[e] + grp_vec[k] - L;
+      }
+    }
+    __syncwarp();
+  }
+}
+// aux[0] = sum_k exp(dg_k - max dg), aux[1] = max dg
+__global__ void posterior_aux_kernel(const double *__restrict__ dg, int K, double *__restrict__ aux) {
+  __shared__ double scratch[32];
+  double mx = -INFINITY;
+  for (int k = threadIdx.x; k < K; k += 256) mx = fmax(mx, dg[k]);
+  mx = block_max<256>(mx, scratch);
+  double w = 0.0;
+  for (int k = threadIdx.x; k < K; k += 256) w += exp(dg[k] - mx);
+  w = block_sum<256>(w, scratch);
+  if (threadIdx.x == 0) { aux[0] = w; aux[1] = mx; }
+}
+
 } // namespace mswb
 
 namespace mswb {
 // K x n tile of log-posteriors for classes [ec_begin, ec_begin + n) of the shard, on the device (group-major).
 void posterior_tile_dev(mswb_ctx *ctx, mswb_lik *lik, uint64_t ec_begin, uint64_t n, double *tile) {
-  MSWB_REQUIRE(lik->last_algo >= 0, "no optimisation has been run on this likelihood");
-  MSWB_REQUIRE(lik->storage != MSWB_STORE_SPARSE, "posterior export is not available in sparse storage (build the likelihood dense)");
+  MSWB_REQUIRE(lik->last_algo >= 0, "no optimisation has been run on this likelihood (posteriors of a bootstrap batch are not kept)");
   const int K = (int)lik->K;
   const int blocks = (int)std::min<uint64_t>(ceil_div(n, 8), (uint64_t)ctx->n_sms * 8);
+  if (lik->storage == MSWB_STORE_SPARSE) {
+    if (lik->last_algo == MSWB_ALGO_RCG) {
+      posterior_tile_sparse_kernel<<<blocks, 256, 0, ctx->stream>>>(0, lik->nz_ptr.p, lik->nz_grp.p, lik->sp_g.p, lik->nz_logl.p, lik->sp_b.p,
+                                                                    lik->rowmax.p, lik->last_a.p, nullptr, lik->l0, ec_begin, n, K, tile);
+      MSWB_LAUNCHED();
+    } else {
+      DevBuf<double> aux;
+      aux.alloc(2);
+      posterior_aux_kernel<<<1, 256, 0, ctx->stream>>>(lik->last_dg.p, K, aux.p);
+      MSWB_LAUNCHED();
+      posterior_tile_sparse_kernel<<<blocks, 256, 0, ctx->stream>>>(1, lik->nz_ptr.p, lik->nz_grp.p, lik->nz_dP.p, lik->nz_logl.p, lik->P0.p,
+                                                                    lik->rowmax.p, lik->last_dg.p, aux.p, lik->l0, ec_begin, n, K, tile);
+      MSWB_LAUNCHED();
+      MSWB_CUDA(cudaStreamSynchronize(ctx->stream));      // aux goes out of scope
+    }
+    return;
+  }
   if (lik->last_algo == MSWB_ALGO_RCG) {
     posterior_tile_kernel<double><<<blocks, 256, 0, ctx->stream>>>(0, lik->gamma.p, nullptr, (int)lik->Kp, nullptr, 0, nullptr, ec_begin, n, K, tile);
   } else if (lik->logl.p) {
@@ -873,6 +936,10 @@ int mswb_vi_finish(mswb_vi *vi, double *theta, double *N_k, mswb_vi_stat *stat) 
       // responsibilities of that pass on demand (mswb_vi_posteriors).
       vi->lik->last_dg.ensure(vi->K);
       MSWB_CUDA(cudaMemcpyAsync(vi->lik->last_dg.p, c.iter > 0 ? vi->dg_prev.p : vi->dg.p, vi->K * sizeof(double), cudaMemcpyDeviceToDevice, vi->ctx->stream));
+    }
+    if (vi->opts.algo == MSWB_ALGO_RCG && vi->lik->storage == MSWB_STORE_SPARSE) {
+      vi->lik->last_a.ensure(vi->K);
+      MSWB_CUDA(cudaMemcpyAsync(vi->lik->last_a.p, vi->rs_a.p, vi->K * sizeof(double), cudaMemcpyDeviceToDevice, vi->ctx->stream));
     }
     MSWB_CUDA(cudaStreamSynchronize(vi->ctx->stream));
     // rcgpar::mixture_components: theta_k = sum_j c_j q(j,k) / sum_j c_j = (N_k - alpha0_k) / sum_j c_j

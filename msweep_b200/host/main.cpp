@@ -100,7 +100,7 @@ const char *kHelp =
     "  --gpus                       number of B200s to use (default: 1)\n"
     "  --algorithm                  rcgb200 | emb200 (aliases: rcggpu, emgpu; default: rcgb200)\n"
     "  --emprecision                float | double, for emb200 (default: double)\n"
-    "  --storage                    dense | sparse likelihood on the device (default: dense; sparse = lossless, O(hits) per class)\n"
+    "  --storage                    auto | dense | sparse likelihood on the device (default: auto = sparse, lossless, O(hits) per class)\n"
     "  --max-iters                  optimiser iteration cap (default: 5000)\n"
     "  --tol                        stop when the bound changes by less than this (default: 0.000001)\n"
     "  --iters                      bootstrap replicates (default: 0)\n"
@@ -225,12 +225,13 @@ int main(int argc, char *argv[]) {
     const std::string prec = args.str("emprecision", "double");
     if (prec == "float") { if (vi.algo == MSWB_ALGO_EM) storage = MSWB_STORE_F32; }
     else if (prec != "double") throw std::runtime_error("Unknown --emprecision `" + prec + "` (one of float, double)");
-    const std::string store = args.str("storage", "dense");
-    if (store == "sparse") {
-      if (args.has("write-probs") || args.has("print-probs") || args.has("bin-reads"))
-        throw std::runtime_error("--storage sparse cannot export the probability matrix; use --storage dense");
-      storage = MSWB_STORE_SPARSE;
-    } else if (store != "dense") throw std::runtime_error("Unknown --storage `" + store + "` (one of dense, sparse)");
+    // auto: the lossless sparse form (O(hits) per class instead of O(groups): LL_WOR21 gives every group a class does
+    // not hit the same value) whenever the likelihood is fp64; --emprecision float is a dense form by definition.
+    const std::string store = args.str("storage", "auto");
+    if (store == "sparse" || (store == "auto" && storage == MSWB_STORE_F64)) storage = MSWB_STORE_SPARSE;
+    else if (store != "dense" && store != "auto") throw std::runtime_error("Unknown --storage `" + store + "` (one of auto, dense, sparse)");
+    if (store == "sparse" && args.str("emprecision", "double") == "float" && vi.algo == MSWB_ALGO_EM)
+      throw std::runtime_error("--storage sparse is an fp64 form; drop --emprecision float");
     vi.tol = args.num<double>("tol", 1e-6);
     vi.max_iters = args.num<uint64_t>("max-iters", 5000);
   } catch (std::exception &e) {

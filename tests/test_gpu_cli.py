@@ -69,12 +69,29 @@ def test_em_and_float_precision(data):
     assert np.max(np.abs(vals3 - vals2)) < 1e-3             # float EM stops elsewhere on the plateau (docs/gpubenchmarks.md:27)
 
 
-def test_sparse_storage_flag(data):
+def test_storage_flag(data):
+    """--storage auto (the default) = the lossless sparse form for fp64 likelihoods; dense and sparse give the reference's
+    numbers for both optimisers, probabilities included; sparse cannot be combined with --emprecision float."""
     d, wl, paths, g = data
-    (h, names, vals), (h2, _, vals2), _ = run_both(d, paths, g, ["--algorithm", "emb200", "--storage", "sparse"], "sp", oracle_algo="emgpu")
-    assert h[1:] == h2[1:] and np.max(np.abs(vals - vals2)) < 2e-6
-    r = subprocess.run([CLI, "--themisto", ",".join(paths), "-i", g, "--storage", "sparse"], capture_output=True, text=True)
-    assert r.returncode == 1 and "needs --algorithm emb200" in r.stderr
+    for algo, oracle_algo in (("emb200", "emgpu"), ("rcgb200", "rcgcpu")):
+        for store in ("sparse", "dense"):
+            (h, names, vals), (h2, _, vals2), _ = run_both(d, paths, g, ["--algorithm", algo, "--storage", store], "st_" + algo + store,
+                                                          oracle_algo=oracle_algo)
+            assert h[1:] == h2[1:] and np.max(np.abs(vals - vals2)) < 2e-6
+    outs = {}
+    for store in ("sparse", "dense"):
+        r = subprocess.run([CLI, "--themisto", ",".join(paths), "-i", g, "--storage", store, "--print-probs"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs[store] = r.stdout
+    rows = {k: [l.split("\t") for l in v.splitlines() if l and not l.startswith("#") and not l.startswith("ec_id") and l[0].isdigit()] for k, v in outs.items()}
+    assert len(rows["sparse"]) == len(rows["dense"]) > 0
+    for a, b in zip(rows["sparse"], rows["dense"]):
+        assert a[0] == b[0] and np.max(np.abs(np.array(a[1:], float) - np.array(b[1:], float))) < 2e-6
+    r = subprocess.run([CLI, "--themisto", ",".join(paths), "-i", g, "--storage", "sparse", "--algorithm", "emb200", "--emprecision", "float"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "fp64 form" in r.stderr
+    r = subprocess.run([CLI, "--themisto", ",".join(paths), "-i", g, "--storage", "compact"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unknown --storage" in r.stderr
 
 
 def test_min_hits_orders_pruned_groups_last(data):

@@ -236,6 +236,31 @@ def test_sparse_rcg_follows_the_dense_trajectory(case, oracle, mswb, ctx, min_hi
         assert np.max(np.abs(thetas[r] - want.theta)) < THETA_TOL
 
 
+@pytest.mark.parametrize("algo", ["rcg", "em"])
+def test_sparse_posteriors_and_bins_equal_the_dense_ones(case, oracle, mswb, ctx, algo):
+    """Posterior export (Sample::store_probs, src/Sample.cpp:63-85) and the binning hand-off from the sparse storage:
+    gamma = a_k + b_j off the hits (RCG) / l0 + digamma(N_k) - L_j (EM), explicit on the hits — the dense matrix, tile by tile."""
+    name, wl, ec, aln = case
+    code = mswb.ALGO_RCG if algo == "rcg" else mswb.ALGO_EM
+    if algo == "rcg" and len(wl.group_sizes) < 2:
+        pytest.skip("needs two groups")
+    dense = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+    sparse = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=mswb.STORE_SPARSE)
+    rd, rs = dense.vi_run(code), sparse.vi_run(code)
+    assert rd.iters == rs.iters
+    gd, gs = dense.posteriors(), sparse.posteriors()
+    assert gd.shape == gs.shape
+    assert np.max(np.abs(gd - gs)) < 1e-8
+    assert np.max(np.abs(np.exp(gs).sum(axis=0) - 1.0)) < 1e-12
+    n = min(7, sparse.n_ecs)
+    assert np.array_equal(sparse.posteriors(3 if sparse.n_ecs > 10 else 0, (3 if sparse.n_ecs > 10 else 0) + n),
+                          gs[:, (3 if sparse.n_ecs > 10 else 0):(3 if sparse.n_ecs > 10 else 0) + n])
+    with np.errstate(divide="ignore"):
+        thr = np.log(rs.theta) + 1e-6           # (away from ties: the two forms differ in the last bits)
+    bd, bs = dense.assign(aln, thr), sparse.assign(aln, thr)
+    assert all(np.array_equal(x, y) for x, y in zip(bd, bs))
+
+
 def test_golden_fixture(mswb, ctx):
     """The frozen numbers (no oracle at run time)."""
     g = np.load(os.path.join(GOLD, "small_case.npz"))

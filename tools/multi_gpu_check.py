@@ -25,6 +25,9 @@ res = {}
 for name, code in (("rcg", M.ALGO_RCG), ("em", M.ALGO_EM)):
     res[name] = lik.vi_run(code)
 res["rcg_mh"] = lik_mh.vi_run(M.ALGO_RCG)
+lik_sp = M.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=M.STORE_SPARSE)
+res["rcg_sparse"] = lik_sp.vi_run(M.ALGO_RCG)       # sparse RCG, EC-sharded: a rejected step stalls every rank at the same iteration
+res["em_sparse"] = lik_sp.vi_run(M.ALGO_EM)
 mask_mh, hits_mh = lik_mh.mask(want_hits=True)
 
 # hash-partitioned reads: rank r owns hash range [r, r+1) * 2^64 / world
@@ -46,8 +49,8 @@ if rank == 0:
     ec = orc.ec_build_csr(wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
     ref_l = orc.lik_build(ec, wl.group_of_target, wl.group_sizes)
     assert int(n_total) == ec.n_ecs == lik_p.n_ecs_total, (n_total, ec.n_ecs)
-    for name in ("rcg", "em"):
-        ref = orc.vi_run(name, ref_l.logl, ref_l.log_counts)
+    for name in ("rcg", "em", "rcg_sparse", "em_sparse"):
+        ref = orc.vi_run(name.split("_")[0], ref_l.logl, ref_l.log_counts)
         got = res[name]
         assert got.iters == ref.iters, (name, got.iters, ref.iters)
         assert np.max(np.abs(got.theta - ref.theta)) < 1e-6 and abs(got.bound - ref.bound) <= 1e-9 * abs(ref.bound)
