@@ -591,6 +591,8 @@ def main():
         s = timed_series(torch, M, dist, stream, lik, algo, a.steps, a.warmup)
         clocks = sampler.stop() if sampler else None
     res = s["res"]
+    # per-rank kernel time: at N > 1 a step lasts as long as the SLOWEST rank's pass (the others wait for it in the all-reduce)
+    pass_ms_max, pass_ms_min = dist.reduce_max(s["pass_ms"]), -dist.reduce_max(-s["pass_ms"])
     n_job = dist.reduce_sum(n_ecs_local)
     ms_per_step = s["ms_total"] / a.steps
     value = n_job * a.steps / (s["ms_total"] * 1e-3)
@@ -691,7 +693,9 @@ def main():
                          "frac_of_nominal_8TBs": achieved / 8000.0, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": ("em_sparse_pass_kernel" if a.storage == "sparse" else "em_lin_pass_kernel") if a.algo == "em" else "rcg_sweep_a_kernel + rcg_sweep_b_kernel",
                          "bytes_per_launch": bytes_per_launch, "kernel_ms": s["pass_ms"],
-                         "kernel_share_of_step": s["pass_ms"] * s["passes_per_iter"] / ms_per_step},
+                         "kernel_ms_over_ranks": {"min": pass_ms_min, "max": pass_ms_max},
+                         "kernel_share_of_step": s["pass_ms"] * s["passes_per_iter"] / ms_per_step,
+                         "slowest_rank_kernel_share_of_step": pass_ms_max * s["passes_per_iter"] / ms_per_step},
             "cpu_baseline": cb,
             "e2e": e2e,
             "gpu_launches": s["launches"],

@@ -49,7 +49,7 @@ __global__ void resample_from_stream_kernel(const unsigned long long *__restrict
 // state[0..311] = the generator's words, state[312] = how many of them have been consumed (312: refill first, the state
 // std::mt19937_64 is in right after seeding).  Produces the next n outputs of the stream into out (nullptr: discard — the
 // replicates of other ranks) and leaves the state where the stream continues.
-constexpr int MT_N = 312, MT_M = 156, MT_NT = 320;
+constexpr int MT_N = 312, MT_M = 156, MT_NT = 160;
 __device__ __forceinline__ unsigned long long mt64_temper(unsigned long long y) {
   y ^= (y >> 29) & 0x5555555555555555ull;
   y ^= (y << 17) & 0x71D67FFFEDA60000ull;
@@ -63,33 +63,33 @@ __device__ __forceinline__ unsigned long long mt64_twist(unsigned long long far,
 }
 __global__ void __launch_bounds__(MT_NT) mt64_generate_kernel(unsigned long long *__restrict__ state, unsigned long long n,
                                                               unsigned long long *__restrict__ out) {
-  __shared__ unsigned long long x[MT_N];
+  // two copies of the state: a refill reads one and writes the other, so each half-step needs ONE barrier
+  __shared__ unsigned long long xs[2][MT_N];
   const int t = threadIdx.x;
-  for (int i = t; i < MT_N; i += MT_NT) x[i] = state[i];
+  for (int i = t; i < MT_N; i += MT_NT) xs[0][i] = state[i];
   unsigned long long pos = state[MT_N];
+  int cur = 0;
   __syncthreads();
   unsigned long long produced = 0;
   while (produced < n) {
     if (pos == MT_N) {
-      // words 0..155 depend on old words only; words 156..311 on the new first half and old words (word 311 on new word 0)
-      unsigned long long v = 0;
-      if (t < MT_M) v = mt64_twist(x[t + MT_M], x[t], x[t + 1]);
+      const unsigned long long *x = xs[cur];
+      unsigned long long *y = xs[cur ^ 1];
+      // words 0..155 depend on old words only; words 156..311 on the NEW first half and old words (word 311 on new word 0)
+      if (t < MT_M) y[t] = mt64_twist(x[t + MT_M], x[t], x[t + 1]);
       __syncthreads();
-      if (t < MT_M) x[t] = v;
+      if (t < MT_M) y[t + MT_M] = mt64_twist(y[t], x[t + MT_M], t + MT_M + 1 < MT_N ? x[t + MT_M + 1] : y[0]);
       __syncthreads();
-      if (t < MT_M) v = mt64_twist(x[t], x[t + MT_M], x[(t + MT_M + 1) % MT_N]);
-      __syncthreads();
-      if (t < MT_M) x[t + MT_M] = v;
-      __syncthreads();
+      cur ^= 1;
       pos = 0;
     }
     const unsigned long long take = min((unsigned long long)MT_N - pos, n - produced);
-    if (out) for (unsigned long long i = t; i < take; i += MT_NT) out[produced + i] = mt64_temper(x[pos + i]);
+    if (out) for (unsigned long long i = t; i < take; i += MT_NT) out[produced + i] = mt64_temper(xs[cur][pos + i]);
     produced += take;
     pos += take;
   }
   __syncthreads();
-  for (int i = t; i < MT_N; i += MT_NT) state[i] = x[i];
+  for (int i = t; i < MT_N; i += MT_NT) state[i] = xs[cur][i];
   if (t == 0) state[MT_N] = pos;
 }
 

@@ -692,7 +692,7 @@ __device__ __forceinline__ ViArrays arrays_of_replicate(const ViArrays &base, in
 }
 
 template <typename ST, class TL, int BT>
-__global__ void __launch_bounds__(TL::NT, (TL::NT <= 256 && BT * TL::R * TL::KITER <= 16) ? 2 : 1)
+__global__ void __launch_bounds__(TL::NT, (TL::NT <= 256 && 4 * TL::R * TL::KITER + 2 * BT * TL::KITER * (16 / (int)sizeof(ST)) + 2 * TL::R * BT <= 100) ? 2 : 1)
 em_lin_batch_kernel(const ST *__restrict__ P, int ld, const double *__restrict__ rowmax, const double *__restrict__ counts,
                     unsigned long long counts_stride, ViArrays base, const int *__restrict__ active, int n_active,
                     double *partials, int pstride, unsigned long long N_pad, int K) {
@@ -757,21 +757,29 @@ em_lin_batch_kernel(const ST *__restrict__ P, int ld, const double *__restrict__
       for (int i = 0; i < KITER; ++i) wv[i] = inr[i] ? reinterpret_cast<const VT *>(sW + (size_t)b * ld)[t + TPR * i] : zero;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        ST a[VEC];
+        if constexpr (sizeof(ST) == 8) {
+          // fp64: one FMA chain per (row, replicate), no temporaries
+          double a = 0.0;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) a[v] = (ST)0;
+          for (int i = 0; i < KITER; ++i) { a = fma(pv[r][i].x, wv[i].x, a); a = fma(pv[r][i].y, wv[i].y, a); }
+          s[r * BT + b] = a;
+        } else {
+          ST a[VEC];
 #pragma unroll
-        for (int i = 0; i < KITER; ++i) {
-          ST e[VEC], ww[VEC];
-          unpack(pv[r][i], e);
-          unpack(wv[i], ww);
+          for (int v = 0; v < VEC; ++v) a[v] = (ST)0;
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) a[v] = fma(e[v], ww[v], a[v]);
+          for (int i = 0; i < KITER; ++i) {
+            ST e[VEC], ww[VEC];
+            unpack(pv[r][i], e);
+            unpack(wv[i], ww);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) a[v] = fma(e[v], ww[v], a[v]);
+          }
+          ST tot = a[0];
+#pragma unroll
+          for (int v = 1; v < VEC; ++v) tot += a[v];
+          s[r * BT + b] = (double)tot;
         }
-        ST tot = a[0];
-#pragma unroll
-        for (int v = 1; v < VEC; ++v) tot += a[v];
-        s[r * BT + b] = (double)tot;
       }
     }
     const double k = RowsRed<NP, 16, false>::run(s, lane);
@@ -805,18 +813,26 @@ em_lin_batch_kernel(const ST *__restrict__ P, int ld, const double *__restrict__
       for (int r = 0; r < R; ++r) inv[r] = (ST)__shfl_sync(0xffffffffu, inv_l, WPG > 1 ? r * BT + b : holder_lane<32, NP>(r * BT + b));
 #pragma unroll
       for (int i = 0; i < KITER; ++i) {
-        ST a[VEC];
+        if constexpr (sizeof(ST) == 8) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) a[v] = (ST)0;
+          for (int r = 0; r < R; ++r) {
+            acc[b][i][0] = fma(pv[r][i].x, inv[r], acc[b][i][0]);
+            acc[b][i][1] = fma(pv[r][i].y, inv[r], acc[b][i][1]);
+          }
+        } else {
+          ST a[VEC];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          ST e[VEC];
-          unpack(pv[r][i], e);
+          for (int v = 0; v < VEC; ++v) a[v] = (ST)0;
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) a[v] = fma(e[v], inv[r], a[v]);
+          for (int r = 0; r < R; ++r) {
+            ST e[VEC];
+            unpack(pv[r][i], e);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) a[v] = fma(e[v], inv[r], a[v]);
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[b][i][v] += (double)a[v];
         }
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[b][i][v] += (double)a[v];
       }
     }
   }
@@ -833,7 +849,7 @@ em_lin_batch_kernel(const ST *__restrict__ P, int ld, const double *__restrict__
 
 // Reduction + control step of the batched pass: gridDim.y = active replicates, the last CTA of a replicate's row
 // of CTAs takes its control step.
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 finalize_ctl_batch_kernel(const double *partials, int pstride, int n_ctas, int nvals, ViArrays base, ViCtl *ctls, int K,
                           const int *__restrict__ active) {
   const int slot = blockIdx.y, rep = active[slot];
@@ -1405,7 +1421,7 @@ inline size_t em_sparse_smem_bytes(int K) {
 // red[v] = sum over CTAs of partials[cta][v], fixed order; v < nvals.  ctl_mode: -1 none (several GPUs: the all-reduce
 // and a control kernel follow), else the last CTA takes the control step (0 EM dense, 1 EM sparse, 2 RCG stage 0).
 constexpr int FIN_NT = 128;
-__global__ void __launch_bounds__(FIN_NT)
+static __global__ void __launch_bounds__(FIN_NT)
 finalize_ctl_kernel(const double *partials, int pstride, int n_ctas, int nvals, ViArrays arrays, ViCtl *ctl, int K,
                     int ctl_mode, int ignore_stall) {
   if (ctl->done || (ctl->stall && !ignore_stall)) return;

@@ -18,9 +18,8 @@
 // trajectory differs from the dense sweeps only by summation order.  Bytes per iteration: ~150 per class + ~50 per hit,
 // against 56 K per class.
 //
-// Kernels: rcgs_prep_kernel (one CTA: the K-sized group vectors and moments of the step about to be taken),
-// rcgs_sweep_a_kernel (gradient norm), rcgs_sweep_b_kernel<MODE> (step / restart, renormalise, N_k, bound), and the control
-// step.  One warp per chunk of 32 classes, hits read hit-parallel (coalesced) and parked in shared memory, class sums
+// Kernels: rcgs_sweep_a_kernel (gradient norm), rcgs_sweep_b_kernel<MODE> (the K-sized group part of the step in its
+// prologue, then step / restart, renormalise, N_k, bound), and the control step.  One warp per chunk of 32 classes, hits read hit-parallel (coalesced) and parked in shared memory, class sums
 // class-parallel in list order, per-group sums in the fixed-point accumulators of the sparse EM pass (bit-reproducible).
 #pragma once
 #include "vi_kernels.cuh"
@@ -34,8 +33,8 @@ struct RcgsGroup {
   double *ec;             // [K] e_k - ebar with e_k = psi_k - a_k   (sweep A)
   double *mom;            // [RCGS_MOM] see below
 };
-// mom[]: moments of the committed state (sweep A) and of the candidate (sweep B)
-constexpr int RM_M0 = 0, RM_EBAR = 1, RM_M2C = 2, RM_M0N = 3, RM_MAN = 4, RM_SHIFT = 5, RM_BETA = 6, RCGS_MOM = 8;
+// mom[]: moments of the committed state (sweep A)
+constexpr int RM_M0 = 0, RM_EBAR = 1, RM_M2C = 2, RCGS_MOM = 4;
 // slots of the reduced vector behind the K per-group sums (the norm sits last so that the all-reduce after sweep B,
 // K + 2 values, leaves it alone)
 constexpr int RS_BOUND = 0, RS_MASS = 1, RS_NORM = 2;
@@ -61,53 +60,59 @@ __device__ __forceinline__ void rcgs_prep_a(const ViArrays &va, const RcgsGroup 
   if (threadIdx.x == 0) { g.mom[RM_M0] = m0; g.mom[RM_EBAR] = ebar; g.mom[RM_M2C] = m2; }
 }
 
-// The group part of the step about to be taken.  mode 0: u' = e + beta u, a' = a + u'.  mode 1 (restart): a' = psi, u' = 0.
-// a' is shifted to max 0 (the shift goes into the class offsets); M0' = sum exp(a'), Ma' = sum exp(a') a'.
-constexpr int RCGS_PREP_NT = 256;
-__global__ void __launch_bounds__(RCGS_PREP_NT) rcgs_prep_kernel(ViArrays va, RcgsGroup g, ViCtl *ctl, int K, int mode) {
-  if (ctl->done) return;
-  if (mode == 0 ? ctl->stall != 0 : !ctl->didreset) return;
-  __shared__ double scratch[32];
+// The group part of the step about to be taken, computed by EVERY CTA of sweep B in its prologue (K-sized: a few
+// microseconds; one launch less per iteration than a kernel of its own) into shared memory; CTA 0 also publishes it for
+// the control step.  MODE 0: u' = e + beta u, a' = a + u'.  MODE 1 (restart): a' = psi, u' = 0.  a' is shifted to max 0
+// (the shift goes into the class offsets); M0' = sum exp(a'), Ma' = sum exp(a') a'.  All CTAs compute identical bits.
+struct RcgsStep { double m0n, man, shift, beta; };
+template <int MODE, int NT>
+__device__ __forceinline__ RcgsStep rcgs_prep_step(const ViArrays &va, const RcgsGroup &g, const ViCtl *ctl, int K, double *s_an,
+                                                   double *s_En, double *scratch) {
   double beta_eff = 0.0;
-  if (mode == 0) {
+  if (MODE == 0) {
     const double beta = va.red[K + RS_NORM] / ctl->oldnorm;
     // the direction memory is empty before the first accepted step and after a restart
     beta_eff = (!ctl->didreset && beta > 0.0 && ctl->iter > 0) ? beta : 0.0;
   }
+  const bool publish = blockIdx.x == 0;
   double mx = -INFINITY;
-  for (int k = threadIdx.x; k < K; k += RCGS_PREP_NT) {
+  for (int k = threadIdx.x; k < K; k += NT) {
     double an, un;
-    if (mode == 0) { un = fma(beta_eff, g.u[k], va.dg[k] - g.a[k]); an = g.a[k] + un; }
+    if (MODE == 0) { un = fma(beta_eff, g.u[k], va.dg[k] - g.a[k]); an = g.a[k] + un; }
     else { un = 0.0; an = va.dg[k]; }
-    g.u_new[k] = un;
-    g.a_new[k] = an;
+    if (publish) g.u_new[k] = un;
+    s_an[k] = an;
     mx = fmax(mx, an);
   }
-  mx = block_max<RCGS_PREP_NT>(mx, scratch);
+  mx = block_max<NT>(mx, scratch);
   double m0 = 0.0, ma = 0.0;
-  for (int k = threadIdx.x; k < K; k += RCGS_PREP_NT) {
-    const double an = g.a_new[k] - mx, E = exp(an);
-    g.a_new[k] = an;
+  for (int k = threadIdx.x; k < K; k += NT) {
+    const double an = s_an[k] - mx, E = exp(an);
+    s_an[k] = an; s_En[k] = E;
+    if (publish) g.a_new[k] = an;
     m0 += E; ma = fma(E, an, ma);
   }
-  m0 = block_sum<RCGS_PREP_NT>(m0, scratch);
-  ma = block_sum<RCGS_PREP_NT>(ma, scratch);
-  if (threadIdx.x == 0) { g.mom[RM_M0N] = m0; g.mom[RM_MAN] = ma; g.mom[RM_SHIFT] = mx; g.mom[RM_BETA] = beta_eff; }
+  m0 = block_sum<NT>(m0, scratch);
+  ma = block_sum<NT>(ma, scratch);
+  return RcgsStep{m0, ma, mx, beta_eff};
 }
 
 // ---- warp-level plumbing shared by the two sweeps ------------------------------------------------------------------
 constexpr int RS_NT = 256;
 constexpr int RS_STAGE = 224;      // hits a warp parks at a time
+constexpr int RS_PF = 4;           // sweep A: slabs of 32 hits of the NEXT chunk kept in flight in registers
+constexpr int RS_PFB = 1;          // sweep B: one slab (four values per hit: deeper prefetch spills at two CTAs per SM, and one CTA
+                                   // per SM with four slabs measured slower: 2.34 vs 1.93 ms on 2e7 x 2000)
 
 // Sweep A: newnorm = sum_j (S2_j - S1_j^2), the direction centred per class by c_j = (l0 - b_j) + ebar so that every term
 // vanishes at the optimum (no cancellation between large sums):
 //   delta_e = (logl_e + psi_k - g_e) - c_j   on the hits,   ec_k = e_k - ebar on the non-hit groups (sum_k E_k ec_k = 0)
 //   S1_j = sum_hits (q_e delta_e - exp(b_j) E_k ec_k)
 //   S2_j = exp(b_j) M2c + sum_hits (q_e delta_e^2 - exp(b_j) E_k ec_k^2)
-__global__ void __launch_bounds__(RS_NT, 3)
+static __global__ void __launch_bounds__(RS_NT, 2)
 rcgs_sweep_a_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
                     const double *__restrict__ sp_b, const double *__restrict__ sp_g, ViArrays va, RcgsGroup grp, ViCtl *ctl,
-                    double *partials, int pstride, unsigned long long N, int K, double l0) {
+                    double *partials, int pstride, unsigned long long N, unsigned long long nnz, int K, double l0) {
   if (ctl->done || ctl->stall) return;
   extern __shared__ __align__(16) unsigned char s_dyn_rs[];
   double *s_E = reinterpret_cast<double *>(s_dyn_rs);            // [K] exp(a_k)
@@ -129,36 +134,72 @@ rcgs_sweep_a_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restr
   const unsigned long long per = (n_chunks + warps_total - 1) / warps_total;
   const unsigned long long ch_begin = min(n_chunks, ((unsigned long long)blockIdx.x * (RS_NT / 32) + warp) * per);
   const unsigned long long ch_end = min(n_chunks, ch_begin + per);
-  for (unsigned long long ch = ch_begin; ch < ch_end; ++ch) {
+  // A warp walks a contiguous run of chunks: while chunk i is being summed, the per-class values of chunk i + 1 and the
+  // first RS_PF x 32 hits behind the current range are already in flight in registers (the sweep is bound by load latency).
+  const unsigned long long last_hit = nnz ? nnz - 1 : 0;
+  struct ClsA { unsigned long long a, b; double bj; bool have; };
+  auto load_cls = [&](unsigned long long ch) {
     const unsigned long long j = ch * 32 + lane;
-    const bool have = j < N;
-    const unsigned long long a = nz_ptr[have ? j : N], b = nz_ptr[have ? j + 1 : N];
-    const double bj = have ? sp_b[j] : 0.0;
-    const double wj = have ? exp(bj) : 0.0;
-    const unsigned long long h0 = __shfl_sync(0xffffffffu, a, 0), h1 = __shfl_sync(0xffffffffu, b, 31);
-    __syncwarp();
-    cls_w[lane] = wj;
-    cls_c[lane] = (l0 - bj) + ebar;
-    __syncwarp();
-    double s1 = 0.0, s2 = wj * m2c;
-    for (unsigned long long q0 = h0; q0 < h1; q0 += RS_STAGE) {
-      const int n_here = (int)min((unsigned long long)RS_STAGE, h1 - q0);
-      __syncwarp();
-      for (int x = lane; x < n_here; x += 32) {                  // hit-parallel, coalesced
-        const uint32_t kg = nz_grp[q0 + x];
-        const int k = (int)(kg & SP_GRP_MASK), c = (int)(kg >> 24);
-        const double g = sp_g[q0 + x];
-        const double delta = (nz_logl[q0 + x] + s_psi[k] - g) - cls_c[c];
-        const double q = exp_nonpos(fmin(g, 0.0));
-        const double Ew = cls_w[c] * s_E[k], ec = s_ec[k];
-        x1[x] = fma(q, delta, -Ew * ec);
-        x2[x] = fma(q * delta, delta, -Ew * ec * ec);
-      }
-      __syncwarp();
-      const unsigned long long lo = max(a, q0), hi = min(b, q0 + (unsigned long long)n_here);
-      for (unsigned long long x = lo; x < hi; ++x) { s1 += x1[x - q0]; s2 += x2[x - q0]; }   // class-parallel, list order
+    ClsA c;
+    c.have = j < N;
+    c.a = nz_ptr[c.have ? j : N]; c.b = nz_ptr[c.have ? j + 1 : N];
+    c.bj = c.have ? sp_b[j] : 0.0;
+    return c;
+  };
+  uint32_t pk[RS_PF];
+  double pl[RS_PF], pg[RS_PF];
+  auto load_hits = [&](unsigned long long base) {
+#pragma unroll
+    for (int k = 0; k < RS_PF; ++k) {
+      const unsigned long long e = min(base + (unsigned long long)(32 * k + lane), last_hit);
+      pk[k] = nz_grp[e]; pl[k] = nz_logl[e]; pg[k] = sp_g[e];
     }
-    if (have) nn += s2 - s1 * s1;
+  };
+  auto hit_terms = [&](uint32_t kg, double lg, double g, double &t1, double &t2) {
+    const int k = (int)(kg & SP_GRP_MASK), c = (int)(kg >> 24);
+    const double delta = (lg + s_psi[k] - g) - cls_c[c];
+    const double q = exp_nonpos(fmin(g, 0.0));
+    const double Ew = cls_w[c] * s_E[k], ec = s_ec[k];
+    t1 = fma(q, delta, -Ew * ec);
+    t2 = fma(q * delta, delta, -Ew * ec * ec);
+  };
+  if (ch_begin < ch_end) {
+    ClsA nxt = load_cls(ch_begin);
+    load_hits(__shfl_sync(0xffffffffu, nxt.a, 0));
+    for (unsigned long long ch = ch_begin; ch < ch_end; ++ch) {
+      const ClsA cur = nxt;
+      const unsigned long long h0 = __shfl_sync(0xffffffffu, cur.a, 0), h1 = __shfl_sync(0xffffffffu, cur.b, 31);
+      if (ch + 1 < ch_end) nxt = load_cls(ch + 1);
+      const double wj = cur.have ? exp(cur.bj) : 0.0;
+      __syncwarp();
+      cls_w[lane] = wj;
+      cls_c[lane] = (l0 - cur.bj) + ebar;
+      __syncwarp();
+      double s1 = 0.0, s2 = wj * m2c;
+      if (h1 - h0 <= RS_STAGE) {
+        const int n_here = (int)(h1 - h0);
+#pragma unroll
+        for (int k = 0; k < RS_PF; ++k) {
+          const int x = 32 * k + lane;
+          if (x < n_here) hit_terms(pk[k], pl[k], pg[k], x1[x], x2[x]);
+        }
+        for (int x = 32 * RS_PF + lane; x < n_here; x += 32) hit_terms(nz_grp[h0 + x], nz_logl[h0 + x], sp_g[h0 + x], x1[x], x2[x]);
+        if (ch + 1 < ch_end) load_hits(h1);
+        __syncwarp();
+        for (int x = (int)(cur.a - h0), xe = (int)(cur.b - h0); x < xe; ++x) { s1 += x1[x]; s2 += x2[x]; }   // class-parallel, list order
+      } else {
+        for (unsigned long long q0 = h0; q0 < h1; q0 += RS_STAGE) {
+          const int n_here = (int)min((unsigned long long)RS_STAGE, h1 - q0);
+          __syncwarp();
+          for (int x = lane; x < n_here; x += 32) hit_terms(nz_grp[q0 + x], nz_logl[q0 + x], sp_g[q0 + x], x1[x], x2[x]);
+          __syncwarp();
+          const unsigned long long lo = max(cur.a, q0), hi = min(cur.b, q0 + (unsigned long long)n_here);
+          for (unsigned long long x = lo; x < hi; ++x) { s1 += x1[x - q0]; s2 += x2[x - q0]; }
+        }
+        if (ch + 1 < ch_end) load_hits(h1);
+      }
+      if (cur.have) nn += s2 - s1 * s1;
+    }
   }
   nn = block_sum<RS_NT>(nn, s_blk);
   if (threadIdx.x == 0) partials[(unsigned long long)blockIdx.x * pstride + K + RS_NORM] = nn;
@@ -181,7 +222,7 @@ __device__ __forceinline__ void rcgs_ctl_b_step(const ViArrays &va, const RcgsGr
   __shared__ int s_accept;
   const double mass = __ldcg(va.red + K + RS_MASS);
   double lg = 0.0;
-  for (int k = threadIdx.x; k < K; k += NT) lg += lgamma(va.alpha0[k] + fma(exp(g.a_new[k]), mass, __ldcg(va.red + k)));
+  for (int k = threadIdx.x; k < K; k += NT) lg += lgamma(va.alpha0[k] + fma(exp(__ldcg(g.a_new + k)), mass, __ldcg(va.red + k)));
   lg = block_sum<NT>(lg, scratch);
   const double cand = __ldcg(va.red + K + RS_BOUND) + lg + ctl->bound_const;
   if (threadIdx.x == 0) {
@@ -211,17 +252,18 @@ __device__ __forceinline__ void rcgs_ctl_b_step(const ViArrays &va, const RcgsGr
   __syncthreads();
   if (!s_accept) return;
   for (int k = threadIdx.x; k < K; k += NT) {
-    const double nk = va.alpha0[k] + fma(exp(g.a_new[k]), mass, __ldcg(va.red + k));
+    const double an = __ldcg(g.a_new + k);
+    const double nk = va.alpha0[k] + fma(exp(an), mass, __ldcg(va.red + k));
     va.N_k[k] = nk;
     va.dg[k] = digamma_series(nk) - 1.0;
-    g.a[k] = g.a_new[k];
-    g.u[k] = g.u_new[k];
+    g.a[k] = an;
+    g.u[k] = __ldcg(g.u_new + k);
   }
   __syncthreads();
   rcgs_prep_a<NT>(va, g, K, scratch);
 }
 
-__global__ void __launch_bounds__(256) rcgs_ctl_b_kernel(ViArrays va, RcgsGroup g, ViCtl *ctl, int K, int stage, int stall_on_reject) {
+static __global__ void __launch_bounds__(256) rcgs_ctl_b_kernel(ViArrays va, RcgsGroup g, ViCtl *ctl, int K, int stage, int stall_on_reject) {
   if (ctl->done) return;
   if (stage == 0 ? ctl->stall != 0 : !ctl->didreset) return;
   __shared__ double scratch[32];
@@ -241,7 +283,8 @@ __global__ void __launch_bounds__(RS_NT, 2)
 rcgs_sweep_b_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
                     const double *__restrict__ counts, double *__restrict__ sp_b, double *__restrict__ sp_v,
                     double *__restrict__ sp_g, double *__restrict__ sp_t, ViArrays va, RcgsGroup grp, ViCtl *ctl,
-                    double *partials, int pstride, unsigned long long N, int K, double l0, double fx_scale, int tail) {
+                    double *partials, int pstride, unsigned long long N, unsigned long long nnz, int K, double l0, double fx_scale,
+                    int tail) {
   if (ctl->done) return;
   if (MODE == 1 ? !ctl->didreset : ctl->stall != 0) return;
   extern __shared__ __align__(16) unsigned char s_dyn_rs[];
@@ -254,13 +297,10 @@ rcgs_sweep_b_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restr
   double *s_cls = s_ll + (RS_NT / 32) * RS_STAGE;                  // [warps][3][32]: per class of the chunk
   uint32_t *s_key = reinterpret_cast<uint32_t *>(s_cls + (RS_NT / 32) * 96);   // [warps][RS_STAGE]
   __shared__ double s_blk[32];
-  for (int k = threadIdx.x; k < K; k += RS_NT) {
-    const double an = grp.a_new[k];
-    s_an[k] = an; s_En[k] = exp(an); s_psi[k] = va.dg[k];
-    s_acc[2 * k] = 0u; s_acc[2 * k + 1] = 0u;
-  }
-  const double m0n = grp.mom[RM_M0N], man = grp.mom[RM_MAN], shift = grp.mom[RM_SHIFT];
-  const double beta = MODE == 0 ? grp.mom[RM_BETA] : 0.0;
+  for (int k = threadIdx.x; k < K; k += RS_NT) { s_psi[k] = va.dg[k]; s_acc[2 * k] = 0u; s_acc[2 * k + 1] = 0u; }
+  const RcgsStep stp = rcgs_prep_step<MODE, RS_NT>(va, grp, ctl, K, s_an, s_En, s_blk);
+  const double m0n = stp.m0n, man = stp.man, shift = stp.shift;
+  const double beta = MODE == 0 ? stp.beta : 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *gg = s_gg + warp * RS_STAGE, *ll = s_ll + warp * RS_STAGE;
@@ -272,89 +312,136 @@ rcgs_sweep_b_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restr
   const unsigned long long per = (n_chunks + warps_total - 1) / warps_total;
   const unsigned long long ch_begin = min(n_chunks, ((unsigned long long)blockIdx.x * (RS_NT / 32) + warp) * per);
   const unsigned long long ch_end = min(n_chunks, ch_begin + per);
-  for (unsigned long long ch = ch_begin; ch < ch_end; ++ch) {
+  // As in sweep A: the per-class values of chunk i + 1 and the first RS_PFB x 32 hits behind the current range are in
+  // flight in registers while chunk i is processed (a hit of the next chunk is touched by no other warp meanwhile).
+  const unsigned long long last_hit = nnz ? nnz - 1 : 0;
+  struct ClsB { unsigned long long a, b; double c, bj, vj; bool have; };
+  auto load_cls = [&](unsigned long long ch) {
     const unsigned long long j = ch * 32 + lane;
-    const bool have = j < N;
-    const unsigned long long a = nz_ptr[have ? j : N], b = nz_ptr[have ? j + 1 : N];
-    const double c = have ? counts[j] : 0.0;
-    double bj = 0.0, vj = 0.0;
-    if (MODE == 0 && have) { bj = sp_b[j]; vj = sp_v[j]; }
-    const unsigned long long h0 = __shfl_sync(0xffffffffu, a, 0), h1 = __shfl_sync(0xffffffffu, b, 31);
-    const double vn = MODE == 0 ? fma(beta, vj, l0 - bj) : 0.0;       // class part of the step
-    const double bb = MODE == 0 ? bj + vn + shift : l0 + shift;        // class part of gamma before normalisation
-    const bool one_piece = h1 - h0 <= RS_STAGE;
-    double mx = bb, sumE = 0.0, sumEa = 0.0, ssum = 0.0;
-    for (int round = 0; round < 3; ++round) {
-      for (unsigned long long q0 = h0; q0 < h1; q0 += RS_STAGE) {
-        const int n_here = (int)min((unsigned long long)RS_STAGE, h1 - q0);
-        if (round == 0 || !one_piece) {
-          __syncwarp();
-          for (int x = lane; x < n_here; x += 32) {               // hit-parallel, coalesced
-            const uint32_t kg = nz_grp[q0 + x];
-            const int k = (int)(kg & SP_GRP_MASK);
-            const double lg = nz_logl[q0 + x];
-            double g2;
-            if (MODE == 0) {
-              const double g = sp_g[q0 + x];
-              double tn;
-              if (round == 0) { tn = fma(beta, sp_t[q0 + x], lg + s_psi[k] - g); sp_t[q0 + x] = tn; }   // the new direction leaves at once
-              else tn = sp_t[q0 + x];                             // (a chunk in several pieces: the step is already the new one)
-              g2 = g + tn;
-            } else {
-              g2 = lg + s_psi[k];
+    ClsB d;
+    d.have = j < N;
+    d.a = nz_ptr[d.have ? j : N]; d.b = nz_ptr[d.have ? j + 1 : N];
+    d.c = d.have ? counts[j] : 0.0;
+    d.bj = (MODE == 0 && d.have) ? sp_b[j] : 0.0;
+    d.vj = (MODE == 0 && d.have) ? sp_v[j] : 0.0;
+    return d;
+  };
+  uint32_t pk[RS_PFB];
+  double pl[RS_PFB], pg[RS_PFB], pt[RS_PFB];
+  auto load_hits = [&](unsigned long long base) {
+#pragma unroll
+    for (int k = 0; k < RS_PFB; ++k) {
+      const unsigned long long e = min(base + (unsigned long long)(32 * k + lane), last_hit);
+      pk[k] = nz_grp[e]; pl[k] = nz_logl[e];
+      if (MODE == 0) { pg[k] = sp_g[e]; pt[k] = sp_t[e]; }
+    }
+  };
+  // round 0 of one hit: the new direction leaves at once; returns gamma before normalisation
+  auto step_hit = [&](unsigned long long e, uint32_t kg, double lg, double g, double t) {
+    const int k = (int)(kg & SP_GRP_MASK);
+    if (MODE == 0) {
+      const double tn = fma(beta, t, lg + s_psi[k] - g);
+      sp_t[e] = tn;
+      return g + tn;
+    }
+    return lg + s_psi[k];
+  };
+  if (ch_begin < ch_end) {
+    ClsB nxt = load_cls(ch_begin);
+    load_hits(__shfl_sync(0xffffffffu, nxt.a, 0));
+    for (unsigned long long ch = ch_begin; ch < ch_end; ++ch) {
+      const ClsB cur = nxt;
+      const unsigned long long j = ch * 32 + lane;
+      const unsigned long long h0 = __shfl_sync(0xffffffffu, cur.a, 0), h1 = __shfl_sync(0xffffffffu, cur.b, 31);
+      if (ch + 1 < ch_end) nxt = load_cls(ch + 1);
+      const double vn = MODE == 0 ? fma(beta, cur.vj, l0 - cur.bj) : 0.0;     // class part of the step
+      const double bb = MODE == 0 ? cur.bj + vn + shift : l0 + shift;          // class part of gamma before normalisation
+      const bool one_piece = h1 - h0 <= RS_STAGE;
+      double mx = bb, sumE = 0.0, sumEa = 0.0, ssum = 0.0;
+      for (int round = 0; round < 3; ++round) {
+        for (unsigned long long q0 = h0; q0 < h1; q0 += RS_STAGE) {
+          const int n_here = (int)min((unsigned long long)RS_STAGE, h1 - q0);
+          if (round == 0 && one_piece) {
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < RS_PFB; ++k) {                        // the hits that arrived in registers
+              const int x = 32 * k + lane;
+              if (x < n_here) { key[x] = pk[k]; ll[x] = pl[k]; gg[x] = step_hit(h0 + x, pk[k], pl[k], pg[k], pt[k]); }
             }
-            key[x] = kg; gg[x] = g2; ll[x] = lg;
+            for (int x = 32 * RS_PFB + lane; x < n_here; x += 32) {   // the rest straight from memory
+              const uint32_t kg = nz_grp[h0 + x];
+              const double lg = nz_logl[h0 + x];
+              key[x] = kg; ll[x] = lg;
+              gg[x] = step_hit(h0 + x, kg, lg, MODE == 0 ? sp_g[h0 + x] : 0.0, MODE == 0 ? sp_t[h0 + x] : 0.0);
+            }
+            if (ch + 1 < ch_end) load_hits(h1);
+            __syncwarp();
+          } else if (!one_piece) {
+            __syncwarp();
+            for (int x = lane; x < n_here; x += 32) {                 // a chunk in several pieces: parked again in every round
+              const uint32_t kg = nz_grp[q0 + x];
+              const double lg = nz_logl[q0 + x];
+              double g2;
+              if (MODE == 0) {
+                const double g = sp_g[q0 + x];
+                g2 = round == 0 ? step_hit(q0 + x, kg, lg, g, sp_t[q0 + x]) : g + sp_t[q0 + x];   // (later rounds: the step is already the new one)
+              } else {
+                g2 = lg + s_psi[kg & SP_GRP_MASK];
+              }
+              key[x] = kg; gg[x] = g2; ll[x] = lg;
+            }
+            __syncwarp();
           }
-          __syncwarp();
-        }
-        if (round == 0) {                                         // class-parallel, list order
-          const unsigned long long lo = max(a, q0), hi = min(b, q0 + (unsigned long long)n_here);
-          for (unsigned long long x = lo; x < hi; ++x) {
-            mx = fmax(mx, gg[x - q0]);
-            const int k = (int)(key[x - q0] & SP_GRP_MASK);
-            sumE += s_En[k];
-            sumEa = fma(s_En[k], s_an[k], sumEa);
-          }
-        } else if (round == 1) {
-          const unsigned long long lo = max(a, q0), hi = min(b, q0 + (unsigned long long)n_here);
-          for (unsigned long long x = lo; x < hi; ++x) ssum += exp_nonpos(gg[x - q0] - mx);
-        } else {
-          for (int x = lane; x < n_here; x += 32) {               // hit-parallel: normalised gamma out, N_k scatter, bound
-            const uint32_t kg = key[x];
-            const int k = (int)(kg & SP_GRP_MASK), cl = (int)(kg >> 24);
-            const double gnew = gg[x] - cls_m[cl];
-            sp_g[q0 + x] = gnew;
-            const double cj = cls_c[cl];
-            if (cj > 0.0) {
-              const double cq = cj * exp_nonpos(fmin(gnew, 0.0));           // c_j q(j,k)
-              bound = fma(cq, ll[x] - gnew, bound);
-              const double val = cq - cls_cw[cl] * s_En[k];                   // the group's closed-form share already counts exp(b_j') E'_k
-              if (val != 0.0) fx_atomic_add(&s_acc[2 * k], __double2ll_rn(val * fx_scale));
+          if (round == 0) {                                         // class-parallel, list order
+            const unsigned long long lo = max(cur.a, q0), hi = min(cur.b, q0 + (unsigned long long)n_here);
+            for (unsigned long long x = lo; x < hi; ++x) {
+              mx = fmax(mx, gg[x - q0]);
+              const int k = (int)(key[x - q0] & SP_GRP_MASK);
+              sumE += s_En[k];
+              sumEa = fma(s_En[k], s_an[k], sumEa);
+            }
+          } else if (round == 1) {
+            const unsigned long long lo = max(cur.a, q0), hi = min(cur.b, q0 + (unsigned long long)n_here);
+            for (unsigned long long x = lo; x < hi; ++x) ssum += exp_nonpos(gg[x - q0] - mx);
+          } else {
+            for (int x = lane; x < n_here; x += 32) {               // hit-parallel: normalised gamma out, N_k scatter, bound
+              const uint32_t kg = key[x];
+              const int k = (int)(kg & SP_GRP_MASK), cl = (int)(kg >> 24);
+              const double gnew = gg[x] - cls_m[cl];
+              sp_g[q0 + x] = gnew;
+              const double cj = cls_c[cl];
+              if (cj > 0.0) {
+                const double cq = cj * exp_nonpos(fmin(gnew, 0.0));           // c_j q(j,k)
+                bound = fma(cq, ll[x] - gnew, bound);
+                const double val = cq - cls_cw[cl] * s_En[k];                   // the group's closed-form share already counts exp(b_j') E'_k
+                if (val != 0.0) fx_atomic_add(&s_acc[2 * k], __double2ll_rn(val * fx_scale));
+              }
             }
           }
         }
-      }
-      if (round == 1) {
-        // normaliser of the class: exp(bb - mx) (M0' - sum_H E') + sum_hits exp(gg - mx)
-        const double rest = fmax(m0n - sumE, 0.0);
-        const double tot = fma(exp_nonpos(bb - mx), rest, ssum);
-        const double m = mx + log(tot);
-        const double bnew = bb - m;
-        const double wnew = exp(bnew);
-        if (have) {
-          sp_b[j] = bnew;
-          if (MODE == 0) sp_v[j] = vn;
-          if (c > 0.0) {
-            mass = fma(c, wnew, mass);
-            // non-hit part of the bound: c_j exp(b_j') ((l0 - b_j') (M0' - sum_H E') - (Ma' - sum_H E' a'))
-            bound = fma(c * wnew, (l0 - bnew) * rest - (man - sumEa), bound);
+        if (!one_piece && round == 0 && ch + 1 < ch_end) load_hits(h1);
+        if (round == 1) {
+          // normaliser of the class: exp(bb - mx) (M0' - sum_H E') + sum_hits exp(gg - mx)
+          const double rest = fmax(m0n - sumE, 0.0);
+          const double tot = fma(exp_nonpos(bb - mx), rest, ssum);
+          const double m = mx + log(tot);
+          const double bnew = bb - m;
+          const double wnew = exp(bnew);
+          if (cur.have) {
+            sp_b[j] = bnew;
+            if (MODE == 0) sp_v[j] = vn;
+            if (cur.c > 0.0) {
+              mass = fma(cur.c, wnew, mass);
+              // non-hit part of the bound: c_j exp(b_j') ((l0 - b_j') (M0' - sum_H E') - (Ma' - sum_H E' a'))
+              bound = fma(cur.c * wnew, (l0 - bnew) * rest - (man - sumEa), bound);
+            }
           }
+          __syncwarp();
+          cls_m[lane] = m;
+          cls_cw[lane] = cur.c * wnew;
+          cls_c[lane] = cur.c;
+          __syncwarp();
         }
-        __syncwarp();
-        cls_m[lane] = m;
-        cls_cw[lane] = c * wnew;
-        cls_c[lane] = c;
-        __syncwarp();
       }
     }
   }
@@ -385,7 +472,7 @@ inline size_t rcgs_sweep_b_smem(int K) {
 
 // Reduction of the partial vectors of sweep B over several CTAs (large grids x many groups); ctl_stage >= 0: the last
 // CTA takes the control step (one GPU), -1: the all-reduce and rcgs_ctl_b_kernel follow.
-__global__ void __launch_bounds__(FIN_NT)
+static __global__ void __launch_bounds__(FIN_NT)
 rcgs_finalize_kernel(const double *partials, int pstride, int n_ctas, ViArrays va, RcgsGroup grp, ViCtl *ctl, int K, int ctl_stage,
                      int restart) {
   if (ctl->done) return;
@@ -400,7 +487,7 @@ rcgs_finalize_kernel(const double *partials, int pstride, int n_ctas, ViArrays v
 }
 
 // Start: gamma = log(1/K) everywhere (a = 0, b = log(1/K), hits log(1/K)), no direction; moments for the first sweep A.
-__global__ void __launch_bounds__(256) rcgs_init_groups_kernel(ViArrays va, RcgsGroup g, int K) {
+static __global__ void __launch_bounds__(256) rcgs_init_groups_kernel(ViArrays va, RcgsGroup g, int K) {
   __shared__ double scratch[32];
   for (int k = threadIdx.x; k < K; k += 256) { g.a[k] = 0.0; g.u[k] = 0.0; g.a_new[k] = 0.0; g.u_new[k] = 0.0; }
   __syncthreads();

@@ -196,3 +196,49 @@ def test_bin_reads_files(data):
     assert sorted(f for f in os.listdir(d / "bins_one") if f.endswith(".bin")) == [one + ".bin"]
     r = subprocess.run([CLI, *common[:-2], "--target-groups", "no_such_group", "-o", str(d / "bins_one" / "y")], capture_output=True, text=True)
     assert r.returncode == 1 and r.stderr.startswith("Binning the reads failed:")
+
+
+def test_rcg_optl_dense_has_the_rcgpar_argument_list(oracle, tmp_path):
+    """b200::rcg_optl_dense(ctx, logl K x N, log_times_observed, alpha0, tol, max_iters, ostream&) -> K x N log-posteriors: what
+    rcgpar::rcg_optl_omp / em_torch return at src/mSWEEP.cpp:194-202, so that an unmodified call site can bind (INTEGRATION.md §2)."""
+    rng = np.random.default_rng(3)
+    K, N = 9, 400
+    logl = rng.normal(-6.0, 2.0, size=(K, N))
+    logl[rng.integers(0, K, size=N), np.arange(N)] = -0.4
+    lc = np.log(rng.integers(1, 30, size=N).astype(np.float64))
+    alpha0 = rng.uniform(0.5, 2.0, size=K)
+    np.concatenate([logl.ravel(), lc, alpha0]).tofile(tmp_path / "in.bin")
+    src = tmp_path / "dense.cpp"
+    src.write_text('''#include "msweep_b200.hpp"
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+int main(int argc, char **argv) {
+  const uint32_t K = std::atoi(argv[2]); const uint64_t N = std::atoll(argv[3]); const int algo = std::atoi(argv[4]);
+  std::vector<double> buf((size_t)K * N + N + K);
+  std::ifstream(argv[1], std::ios::binary).read((char *)buf.data(), buf.size() * sizeof(double));
+  std::vector<double> logl(buf.begin(), buf.begin() + (size_t)K * N), lc(buf.begin() + (size_t)K * N, buf.begin() + (size_t)K * N + N),
+      a0(buf.end() - K, buf.end()), theta;
+  try {
+    b200::Context ctx(0);
+    std::ofstream quiet;                                   // never opened: the reference's non-verbose log (src/mSWEEP.cpp:190)
+    std::vector<double> gamma = b200::rcg_optl_dense(ctx, logl, K, N, lc, a0, 1e-6, 5000, quiet, algo, MSWB_STORE_F64, &theta);
+    fwrite(gamma.data(), sizeof(double), gamma.size(), stdout);
+    fwrite(theta.data(), sizeof(double), theta.size(), stdout);
+    try { b200::rcg_optl_dense(ctx, logl, K, N + 1, lc, a0, 1e-6, 10, quiet); return 3; } catch (const std::runtime_error &) {}
+  } catch (const std::exception &e) { std::cerr << e.what() << std::endl; return 1; }
+  return 0;
+}
+''')
+    exe = tmp_path / "dense"
+    lib = os.path.join(ROOT, "msweep_b200", "lib")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "msweep_b200", "host"),
+                    str(src), "-o", str(exe), "-L", lib, "-lmsweep_b200", f"-Wl,-rpath,{lib}"], check=True)
+    for algo, name in ((0, "rcg"), (1, "em")):
+        out = subprocess.run([str(exe), str(tmp_path / "in.bin"), str(K), str(N), str(algo)], capture_output=True, check=True).stdout
+        got = np.frombuffer(out, np.float64)
+        gamma, theta = got[:K * N].reshape(K, N), got[K * N:]
+        ref = oracle.vi_run(name, logl, lc, alpha0=alpha0, want_gamma=True)
+        assert np.max(np.abs(theta - ref.theta)) < 1e-6
+        assert np.max(np.abs(np.exp(gamma) - np.exp(ref.gamma))) < 1e-6
+        assert np.max(np.abs(np.exp(gamma).sum(axis=0) - 1.0)) < 1e-12

@@ -14,6 +14,14 @@ for K, T, R in ((7, 70, 600), (300, 1500, 800), (1100, 3300, 300)):
         lik = M.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, min_hits=1 if K == 7 else 0, storage=storage)
         r = lik.vi_run(M.ALGO_EM, max_iters=6, tol=0.0)
         assert abs(r.theta.sum() - 1) < 1e-6
+        if storage == M.STORE_SPARSE:
+            lik.posteriors(0, min(50, lik.n_ecs))
+            r = lik.vi_run(M.ALGO_RCG, max_iters=6, tol=-1e300)          # sparse RCG: separable state off the hits
+            assert abs(r.theta.sum() - 1) < 1e-9
+            lik.posteriors(0, min(50, lik.n_ecs))
+            with np.errstate(divide="ignore"):
+                bins = lik.assign(aln, np.log(r.theta))
+            lik.bootstrap_run(2, seed=3, max_iters=4)                     # device MT19937-64 stream + sparse RCG replicates
         if storage == M.STORE_F64:
             r = lik.vi_run(M.ALGO_RCG, max_iters=6, tol=-1e300)
             assert abs(r.theta.sum() - 1) < 1e-9
