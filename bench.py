@@ -518,6 +518,11 @@ def extra_sparse(a, torch, M, dist, ctx, stream, rank, world, wl_main, peak):
         out["rcg"]["what"] = ("RCG (the reference's default optimiser) on the same job: dense state would be 3.2 TB; the sparse form keeps "
                               "two K-vectors, two N-vectors and the hits")
         lik.close(); aln.close()
+        pinned = []
+        if wl is not wl_main:                                   # the e2e leg copies from PINNED host memory, like the headline's
+            for arr in (wl.row_ptr, wl.targets):
+                if int(torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)) == 0:
+                    pinned.append(arr)
         torch.cuda.synchronize(); dist.barrier()
         t0 = time.perf_counter()
         aln = M.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets, partitioned=world > 1)
@@ -526,6 +531,8 @@ def extra_sparse(a, torch, M, dist, ctx, stream, rank, world, wl_main, peak):
         torch.cuda.synchronize()
         sec = dist.reduce_max(time.perf_counter() - t0)
         lik.close(); aln.close()
+        for arr in pinned:
+            torch.cuda.cudart().cudaHostUnregister(arr.ctypes.data)
     out.update({"config": f"3 in full: {a.sparse_ecs:.3g} ECs x {N_GROUPS} lineages, EM/VB, lossless sparse fp64 storage, "
                           f"{'one GPU' if world == 1 else f'strong-scaled over {world} GPUs (EC shards, one all-reduce of K+3 doubles per pass)'}",
                 "ecs_job": int(n_job), "ecs_per_gpu": int(out.pop("ecs")), "scaling": "strong", "generate_s": round(t_gen, 1),

@@ -242,3 +242,15 @@ int main(int argc, char **argv) {
         assert np.max(np.abs(theta - ref.theta)) < 1e-6
         assert np.max(np.abs(np.exp(gamma) - np.exp(ref.gamma))) < 1e-6
         assert np.max(np.abs(np.exp(gamma).sum(axis=0) - 1.0)) < 1e-12
+
+
+def test_bootstrap_count_is_honoured(data):
+    """--bootstrap-count: the flag's value is the number of pseudoalignments resampled per replicate (help text, src/mSWEEP.cpp:141).
+    The reference's ConstructSample passes --iters in its place unless --bin-reads is given (src/Sample.cpp:38-39, SURVEY §9: a quirk);
+    this binary and the oracle CLI both use the flag's value — an intentional deviation recorded in DESIGN.md §3.  Fewer draws give noisier replicates."""
+    d, wl, paths, g = data
+    (h, names, vals), (h2, _, vals2), _ = run_both(d, paths, g, ["--iters", "4", "--seed", "5", "--bootstrap-count", "300"], "bc")
+    assert h[1:] == h2[1:] and np.max(np.abs(vals - vals2)) < 2e-6
+    (_, _, full), _, _ = run_both(d, paths, g, ["--iters", "4", "--seed", "5"], "bcfull")
+    top = int(np.argmax(full[:, 0]))
+    assert np.std(vals[top, 1:]) > 3 * np.std(full[top, 1:])          # 300 draws against all aligned reads

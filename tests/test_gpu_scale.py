@@ -83,3 +83,37 @@ def test_likelihood_and_optimiser_invariants_at_scale(big, mswb, ctx):
     # run-to-run bit reproducibility (no atomics on the path)
     c = lik.vi_run(mswb.ALGO_RCG, tol=1e-6, max_iters=400)
     assert np.array_equal(c.theta, rcg.theta) and c.bound == rcg.bound and c.iters == rcg.iters
+
+
+def test_sparse_storage_at_scale(big, mswb, ctx):
+    """Both optimisers on the sparse storage against the dense fp64 sweeps on the same ~1e6 x 1000 problem: RCG iteration by
+    iteration over a fixed number of iterations (before the stopping rule — decided at a relative 1e-14 of the bound here —
+    gets a say), the converged abundances, bit-reproducibility, posterior tiles."""
+    wl, aln = big
+    dense = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+    sparse = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=mswb.STORE_SPARSE)
+    traces = {}
+    for name, lik in (("dense", dense), ("sparse", sparse)):
+        s = lik.vi_begin(mswb.ALGO_RCG, tol=-1e300, max_iters=60)
+        s.step(60)
+        tb, tg, tr = s.trace()
+        traces[name] = (tb, tg, tr, s.finish())
+    (tb_d, tg_d, tr_d, r_d), (tb_s, tg_s, tr_s, r_s) = traces["dense"], traces["sparse"]
+    # the same restart pattern and bound, iteration by iteration — as long as the accept / reject decisions are not
+    # themselves decided by rounding (late in the run a step may change the bound by less than one ulp of 1e7)
+    differ = np.flatnonzero(tr_d != tr_s)
+    n_same = int(differ[0]) if len(differ) else len(tr_d)
+    assert n_same >= 30, (n_same, tr_d, tr_s)
+    assert np.max(np.abs(tb_d[:n_same] - tb_s[:n_same]) / np.abs(tb_d[:n_same])) < 1e-11
+    assert np.allclose(tg_d[:30], tg_s[:30], rtol=1e-6, atol=1e-9 * tg_d[0])
+    if n_same == len(tr_d):
+        assert np.max(np.abs(r_d.theta - r_s.theta)) < 1e-9
+    conv_d, conv_s = dense.vi_run(mswb.ALGO_RCG), sparse.vi_run(mswb.ALGO_RCG)
+    assert conv_d.converged and conv_s.converged and abs(conv_d.iters - conv_s.iters) <= 3
+    assert np.max(np.abs(conv_d.theta - conv_s.theta)) < 1e-6 and abs(conv_d.bound - conv_s.bound) < 1e-9 * abs(conv_d.bound)
+    again = sparse.vi_run(mswb.ALGO_RCG)
+    assert np.array_equal(again.theta, conv_s.theta) and again.bound == conv_s.bound and again.iters == conv_s.iters
+    g_d, g_s = dense.posteriors(1000, 1300), sparse.posteriors(1000, 1300)
+    assert np.max(np.abs(np.exp(g_d) - np.exp(g_s))) < 1e-7
+    em_d, em_s = dense.vi_run(mswb.ALGO_EM, tol=0.0, max_iters=50), sparse.vi_run(mswb.ALGO_EM, tol=0.0, max_iters=50)
+    assert np.max(np.abs(em_d.theta - em_s.theta)) < 1e-11 and abs(em_d.bound - em_s.bound) < 1e-12 * abs(em_d.bound)

@@ -11,12 +11,13 @@ wl = synth.generate(1_000_000, 3000, 50, n_present=5, n_templates=2000, p_noise=
 ctx = M.Context(0)
 aln = M.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
 out = {"ecs": aln.n_ecs}
-for algo, code in (("rcg", M.ALGO_RCG), ("em", M.ALGO_EM)):
-    lik = M.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+for algo, code, storage in (("rcg", M.ALGO_RCG, M.STORE_F64), ("em", M.ALGO_EM, M.STORE_F64), ("rcg_sparse", M.ALGO_RCG, M.STORE_SPARSE),
+                            ("em_sparse", M.ALGO_EM, M.STORE_SPARSE)):
+    lik = M.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=storage)
     for tag in ("cold", "warm", "warm2"):
         ctx.sync(); t0 = time.perf_counter(); r = lik.vi_run(code); ctx.sync(); out[f"{algo}_{tag}_ms"] = round((time.perf_counter() - t0) * 1e3, 3)
     out[f"{algo}_iters"] = r.iters
-    s = lik.vi_begin(code, tol=-1e300 if algo == "rcg" else 0.0, max_iters=10**6)
+    s = lik.vi_begin(code, tol=-1e300 if algo.startswith("rcg") else 0.0, max_iters=10**6)
     s.step(20); s.poll()
     for n in (100, 1000):
         l0 = M.launch_count(); t0 = time.perf_counter(); s.step(n); st = s.poll(); dt = time.perf_counter() - t0
