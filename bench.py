@@ -672,6 +672,7 @@ def main():
     if "c4" in extras_sel and world == 1:
         guarded("c4", lambda: extra_c4(a, torch, M, ctx, stream, peak))
     if "c1" in extras_sel and world == 1 and rank == 0:
+        ctx.trim()      # the binary is another process: do not leave it a device whose memory this one has parked
         guarded("c1", lambda: extra_c1(a))
 
     cb = None

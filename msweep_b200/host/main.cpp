@@ -245,7 +245,8 @@ int main(int argc, char *argv[]) {
     // auto: the lossless sparse form (O(hits) per class instead of O(groups): LL_WOR21 gives every group a class does
     // not hit the same value) whenever the likelihood is fp64; --emprecision float is a dense form by definition.
     const std::string store = args.str("storage", "auto");
-    if (store == "sparse" || (store == "auto" && storage == MSWB_STORE_F64)) storage = MSWB_STORE_SPARSE;
+    // (the sparse sweeps keep their K-vectors in shared memory: up to 4096 groups; wider groupings stay dense in auto mode)
+    if (store == "sparse" || (store == "auto" && storage == MSWB_STORE_F64 && grouping.sizes.size() <= 4096)) storage = MSWB_STORE_SPARSE;
     else if (store != "dense" && store != "auto") throw std::runtime_error("Unknown --storage `" + store + "` (one of auto, dense, sparse)");
     if (store == "sparse" && args.str("emprecision", "double") == "float" && vi.algo == MSWB_ALGO_EM)
       throw std::runtime_error("--storage sparse is an fp64 form; drop --emprecision float");
