@@ -194,6 +194,13 @@ MSWB_API int  mswb_bootstrap_run(mswb_ctx *ctx, mswb_lik *lik, const double *alp
                         uint64_t n_replicates, uint64_t bootstrap_count, int32_t seed, int rng_mode,
                         int replica_rank, int replica_world, double *thetas, mswb_vi_stat *stats);
 
+/* Jump-ahead of std::mt19937_64 (host arithmetic, no device work).  The reference seeds ONE generator and draws all
+ * replicates from it (src/BootstrapSample.cpp:48-60), so replicate r starts r * bootstrap_count outputs into the stream;
+ * mswb_bootstrap_run uses this to stand a rank at the start of its own replicates without producing the others' draws.
+ * state[312]: the generator's words with all 312 consumed (as right after seeding); state_out[312]: the same n_outputs
+ * outputs later.  The low 31 bits of state_out[0] are not part of the generator's state. */
+MSWB_API int  mswb_mt64_jump(const uint64_t *state, uint64_t n_outputs, uint64_t *state_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,15 @@ def pattern_hash(targets) -> int:
     return int(lib().mswb_pattern_hash(t.ctypes.data if len(t) else None, len(t)))
 
 
+def mt64_jump(state, n_outputs: int) -> np.ndarray:
+    """mswb_mt64_jump: the 312 words of std::mt19937_64 (at a refill boundary) n_outputs outputs later (host arithmetic)."""
+    st = np.ascontiguousarray(state, np.uint64)
+    assert st.shape == (312,)
+    out = np.zeros(312, np.uint64)
+    _check(lib().mswb_mt64_jump(st.ctypes.data_as(C.c_void_p), C.c_uint64(n_outputs), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
 def launch_count() -> int:
     return int(lib().mswb_launch_count())
 

@@ -13,6 +13,7 @@
 #include "handles.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 #include <random>
 
@@ -131,6 +132,11 @@ int mswb_vi_run_batch_dev_counts(mswb_ctx *ctx, mswb_lik *lik, const double *alp
                                  uint64_t counts_stride, int B, double sum_counts, const mswb_vi_opts *opts, double *thetas,
                                  mswb_vi_stat *stats);
 
+namespace mswb {      // mt64_jump.cu
+bool mt64_jump_available();
+void mt64_jump(const uint64_t *state, uint64_t n_outputs, uint64_t *out);
+}
+
 namespace {
 
 struct Resampler {
@@ -138,6 +144,11 @@ struct Resampler {
   uint64_t N = 0, draws = 0;
   int rng_mode;
   uint64_t seed64 = 0;
+  // Jump mode (replicates spread over ranks): the host keeps the generator's words at the start of replicate host_rep and
+  // moves them with mt64_jump — the draws of the other ranks' replicates are never produced.
+  bool jump_mode = false;
+  std::vector<unsigned long long> host_win;
+  uint64_t host_rep = 0;
   DevBuf<double> cp;           // cumulative probabilities (empty when N < 2, as in libstdc++)
   uint64_t n_cp = 0;
   DevBuf<unsigned long long> mt_state;     // [313] std::mt19937_64's words + consumed count (mt64_generate_kernel)
@@ -180,6 +191,7 @@ struct Resampler {
       st[0] = seed64;
       for (int i = 1; i < MT_N; ++i) st[i] = 6364136223846793005ull * (st[i - 1] ^ (st[i - 1] >> 62)) + (unsigned long long)i;
       st[MT_N] = MT_N;
+      host_win = st;
       mt_state.alloc(MT_N + 1);
       h2d(mt_state.p, st.data(), st.size(), s);
       MSWB_CUDA(cudaStreamSynchronize(s));
@@ -187,9 +199,20 @@ struct Resampler {
     }
   }
 
+  // Replicates of other ranks ahead: jump over them when producing their draws would cost more than the two polynomials
+  // a run needs (about 0.1 s of host time; the generator makes ~6e8 draws a second).  MSWB_MT_JUMP=0 / 1 overrides.
+  void choose_jump(uint64_t n_replicates, int replica_rank, int replica_world) {
+    if (rng_mode != MSWB_RNG_LIBSTDCXX_EXACT || draws == 0 || replica_world <= 1) return;
+    uint64_t mine = 0;
+    for (uint64_t r = 0; r < n_replicates; ++r) mine += (int)(r % (uint64_t)replica_world) == replica_rank;
+    const char *e = std::getenv("MSWB_MT_JUMP");
+    const bool want = e ? std::atoi(e) != 0 : (double)draws * (double)(n_replicates - mine) >= 5e7;
+    if (want && (double)draws * (double)n_replicates < 1.8e19 && mt64_jump_available()) { jump_mode = true; host_rep = 0; }
+  }
+
   // another rank's replicate: its draws are consumed, nothing else
   void skip() {
-    if (rng_mode != MSWB_RNG_LIBSTDCXX_EXACT || draws == 0) return;
+    if (rng_mode != MSWB_RNG_LIBSTDCXX_EXACT || draws == 0 || jump_mode) return;
     mt64_generate_kernel<<<1, MT_NT, 0, ctx->stream>>>(mt_state.p, draws, nullptr);
     MSWB_LAUNCHED();
   }
@@ -202,6 +225,17 @@ struct Resampler {
     if (rng_mode == MSWB_RNG_PHILOX) {
       if (draws) { resample_philox_kernel<<<grid, 256, 0, s>>>(seed64, replicate, draws, cp.p, n_cp, hist_dev); MSWB_LAUNCHED(); }
       return;
+    }
+    if (jump_mode) {
+      MSWB_REQUIRE(replicate >= host_rep, "bootstrap replicates must be taken in ascending order");
+      if (replicate != host_rep) {
+        std::vector<unsigned long long> moved(MT_N + 1);
+        mt64_jump(reinterpret_cast<const uint64_t *>(host_win.data()), (replicate - host_rep) * draws, reinterpret_cast<uint64_t *>(moved.data()));
+        moved[MT_N] = MT_N;
+        host_win.swap(moved);
+        host_rep = replicate;
+      }
+      h2d(mt_state.p, host_win.data(), host_win.size(), s);      // (pageable source: staged before the call returns)
     }
     for (uint64_t done = 0; done < draws; done += CHUNK) {
       const uint64_t n = std::min<uint64_t>(CHUNK, draws - done);
@@ -241,6 +275,7 @@ int mswb_bootstrap_run(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const
     MSWB_REQUIRE(replica_world >= 1 && replica_rank >= 0 && replica_rank < replica_world, "bad replica rank / world");
     MSWB_CUDA(cudaSetDevice(ctx->device));
     Resampler rs(ctx, lik, seed, bootstrap_count, rng_mode);
+    rs.choose_jump(n_replicates, replica_rank, replica_world);
     DevBuf<unsigned> hist;
     DevBuf<double> counts;
     hist.alloc(rs.N);

@@ -44,7 +44,7 @@ __global__ void vi_init_kernel(ViArrays a, ViCtl *ctl, int K, int algo, double t
     ctl->bound_const = bound_const; ctl->tol = tol; ctl->sum_counts = sum_counts; ctl->dg_max = mx;
     ctl->iter = 0; ctl->max_iters = max_iters; ctl->resets = 0;
     ctl->use_old = 0; ctl->didreset = 0; ctl->converged = 0; ctl->fault = 0;
-    ctl->stall = 0; ctl->ticket = 0u; ctl->pad_ = 0;
+    ctl->stall = 0; ctl->ticket = 0u; ctl->epoch = 0u;
     ctl->done = max_iters == 0 ? 1 : 0;
   }
 }
@@ -682,6 +682,59 @@ void rcgs_iteration(mswb_vi *vi) {
   MSWB_LAUNCHED();
 }
 
+// Small problems on one GPU: up to n iterations in one cooperative launch (rcgs_fused_kernel).  Returns false when the
+// problem is not of that kind (the caller then enqueues the iterations one by one).  MSWB_FUSED=0 turns it off.
+bool rcgs_fusable(mswb_vi *vi, int *grid_out, size_t *smem_out) {
+  mswb_lik *L = vi->lik;
+  mswb_ctx *ctx = vi->ctx;
+  const int K = vi->K;
+  if (vi->opts.algo != MSWB_ALGO_RCG || L->storage != MSWB_STORE_SPARSE || ctx->world != 1) return false;
+  if (const char *e = getenv("MSWB_FUSED")) if (e[0] == '0') return false;
+  static std::map<int, int> coop;                    // device -> cooperative launches supported
+  static std::mutex mu;
+  int can;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = coop.find(ctx->device);
+    if (it == coop.end()) {
+      int v = 0;
+      MSWB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, ctx->device));
+      it = coop.emplace(ctx->device, v).first;
+    }
+    can = it->second;
+  }
+  if (!can) return false;
+  const size_t smem = std::max(rcgs_sweep_a_smem(K), rcgs_sweep_b_smem(K));
+  if (smem > SMEM_BUDGET) return false;
+  const int grid = persistent_grid(ctx, rcgs_fused_kernel, RS_NT, smem, ceil_div(L->N, (uint64_t)RS_NT), grid_cap(vi, K + 2));
+  if (tail_mode(vi, grid, K + 2) != 2) return false;  // only where the last CTA would reduce and take the control step anyway
+  if (grid_out) *grid_out = grid;
+  if (smem_out) *smem_out = smem;
+  return true;
+}
+bool rcgs_fused_steps(mswb_vi *vi, uint64_t n) {
+  int grid = 0;
+  size_t smem = 0;
+  if (n == 0 || !rcgs_fusable(vi, &grid, &smem)) return false;
+  mswb_lik *L = vi->lik;
+  mswb_ctx *ctx = vi->ctx;
+  const int K = vi->K;
+  vi->grid = grid;
+  const uint64_t *nz_ptr = L->nz_ptr.p; const uint32_t *nz_grp = L->nz_grp.p; const double *nz_logl = L->nz_logl.p;
+  const double *counts = vi->counts;
+  double *sp_b = L->sp_b.p, *sp_v = L->sp_v.p, *sp_g = L->sp_g.p, *sp_t = L->sp_t.p;
+  ViArrays va = vi->arrays; RcgsGroup rs = vi->rs; ViCtl *ctl = vi->ctl.p;
+  double *partials = vi->partials.p; int pstride = vi->pstride;
+  unsigned long long N = L->N, nnz = L->nnz, steps = n;
+  int Kk = K; double l0 = L->l0, fx = vi->fx_scale;
+  void *args[] = {&nz_ptr, &nz_grp, &nz_logl, &counts, &sp_b, &sp_v, &sp_g, &sp_t, &va, &rs, &ctl, &partials, &pstride, &N, &nnz, &Kk, &l0, &fx, &steps};
+  PassTimer timer(vi);
+  MSWB_CUDA(cudaLaunchCooperativeKernel((const void *)rcgs_fused_kernel, dim3(grid), dim3(RS_NT), args, smem, ctx->stream));
+  MSWB_LAUNCHED();
+  timer.stop();
+  return true;
+}
+
 void rcgs_restart_stalled(mswb_vi *vi) {
   mswb_ctx *ctx = vi->ctx;
   const int K = vi->K;
@@ -859,7 +912,8 @@ int mswb_vi_step(mswb_vi *vi, uint64_t n_iters) {
   return guarded([&] {
     MSWB_REQUIRE(vi, "vi is NULL");
     MSWB_CUDA(cudaSetDevice(vi->ctx->device));
-    for (uint64_t i = 0; i < n_iters; ++i) {
+    const bool fused = rcgs_fused_steps(vi, n_iters);
+    for (uint64_t i = 0; i < n_iters && !fused; ++i) {
       if (vi->opts.algo == MSWB_ALGO_RCG) { if (vi->lik->storage == MSWB_STORE_SPARSE) rcgs_iteration(vi); else rcg_iteration(vi); }
       else em_iteration(vi);
     }
@@ -922,7 +976,8 @@ static int vi_run_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const
   mswb_vi *vi = nullptr;
   if (vi_begin_impl(ctx, lik, alpha0, log_counts, counts_dev, counts_dev_sum, opts, &vi)) return 1;
   int rc = guarded([&] {
-    const uint64_t every = opts->poll_every ? opts->poll_every : 8;
+    // (a fused launch stops by itself once the optimiser is done: nothing is wasted by asking for many iterations at a time)
+    const uint64_t every = opts->poll_every ? opts->poll_every : (rcgs_fusable(vi, nullptr, nullptr) ? 64 : 8);
     uint64_t reported = 0;
     std::vector<double> tb, tg;
     for (;;) {

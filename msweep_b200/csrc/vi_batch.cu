@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(CTL_NT) vi_init_batch_kernel(ViArrays base, Vi
     ctl->bound_const = bound_const; ctl->tol = tol; ctl->sum_counts = sum_counts; ctl->dg_max = mx;
     ctl->iter = 0; ctl->max_iters = max_iters; ctl->resets = 0;
     ctl->use_old = 0; ctl->didreset = 0; ctl->converged = 0; ctl->fault = 0;
-    ctl->stall = 0; ctl->ticket = 0u; ctl->pad_ = 0;
+    ctl->stall = 0; ctl->ticket = 0u; ctl->epoch = 0u;
     ctl->done = max_iters == 0 ? 1 : 0;
   }
 }

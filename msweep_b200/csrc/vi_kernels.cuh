@@ -44,7 +44,7 @@ struct ViCtl {
   int use_old, didreset, converged, done, fault;
   int stall;             // several GPUs: an RCG step lost ground; iterations pause until the host has enqueued the restart
   unsigned int ticket;   // CTAs of the running sweep that have delivered their partial vector (the last one reduces them)
-  int pad_;
+  unsigned int epoch;    // grid rendezvous of the fused small-problem kernels: bumped by the last arrival
 };
 
 // Per-group vectors of one optimisation (all device pointers).

@@ -109,11 +109,11 @@ constexpr int RS_PFB = 1;          // sweep B: one slab (four values per hit: de
 //   delta_e = (logl_e + psi_k - g_e) - c_j   on the hits,   ec_k = e_k - ebar on the non-hit groups (sum_k E_k ec_k = 0)
 //   S1_j = sum_hits (q_e delta_e - exp(b_j) E_k ec_k)
 //   S2_j = exp(b_j) M2c + sum_hits (q_e delta_e^2 - exp(b_j) E_k ec_k^2)
-static __global__ void __launch_bounds__(RS_NT, 2)
-rcgs_sweep_a_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
-                    const double *__restrict__ sp_b, const double *__restrict__ sp_g, ViArrays va, RcgsGroup grp, ViCtl *ctl,
-                    double *partials, int pstride, unsigned long long N, unsigned long long nnz, int K, double l0) {
-  if (ctl->done || ctl->stall) return;
+// (the body is shared with rcgs_fused_kernel; it ends with the CTA's partial norm stored)
+__device__ __forceinline__ void
+rcgs_sweep_a_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
+                  const double *sp_b, const double *sp_g, const ViArrays &va, const RcgsGroup &grp,
+                  double *partials, int pstride, unsigned long long N, unsigned long long nnz, int K, double l0) {
   extern __shared__ __align__(16) unsigned char s_dyn_rs[];
   double *s_E = reinterpret_cast<double *>(s_dyn_rs);            // [K] exp(a_k)
   double *s_ec = s_E + K;                                         // [K]
@@ -203,11 +203,24 @@ rcgs_sweep_a_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restr
   }
   nn = block_sum<RS_NT>(nn, s_blk);
   if (threadIdx.x == 0) partials[(unsigned long long)blockIdx.x * pstride + K + RS_NORM] = nn;
+}
+// the gradient norm from the CTAs' partial norms (one CTA, fixed order)
+__device__ __forceinline__ void rcgs_sum_norms(const double *partials, int pstride, const ViArrays &va, int K) {
+  __shared__ double s_blk[32];
+  double acc = 0.0;
+  for (int c = threadIdx.x; c < (int)gridDim.x; c += RS_NT) acc += __ldcg(partials + (size_t)c * pstride + K + RS_NORM);
+  acc = block_sum<RS_NT>(acc, s_blk);
+  if (threadIdx.x == 0) va.red[K + RS_NORM] = acc;
+}
+static __global__ void __launch_bounds__(RS_NT, 2)
+rcgs_sweep_a_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
+                    const double *__restrict__ sp_b, const double *__restrict__ sp_g, ViArrays va, RcgsGroup grp, ViCtl *ctl,
+                    double *partials, int pstride, unsigned long long N, unsigned long long nnz, int K, double l0) {
+  if (ctl->done || ctl->stall) return;
+  rcgs_sweep_a_body(nz_ptr, nz_grp, nz_logl, sp_b, sp_g, va, grp, partials, pstride, N, nnz, K, l0);
   if (cta_is_last(ctl)) {
-    double acc = 0.0;
-    for (int c = threadIdx.x; c < (int)gridDim.x; c += RS_NT) acc += __ldcg(partials + (size_t)c * pstride + K + RS_NORM);
-    acc = block_sum<RS_NT>(acc, s_blk);
-    if (threadIdx.x == 0) { va.red[K + RS_NORM] = acc; ctl->ticket = 0; }
+    rcgs_sum_norms(partials, pstride, va, K);
+    if (threadIdx.x == 0) ctl->ticket = 0;
   }
 }
 inline size_t rcgs_sweep_a_smem(int K) { return (size_t)K * 24 + (size_t)(RS_NT / 32) * RS_STAGE * 16 + (size_t)(RS_NT / 32) * 64 * 8; }
@@ -278,15 +291,13 @@ static __global__ void __launch_bounds__(256) rcgs_ctl_b_kernel(ViArrays va, Rcg
 // Three rounds over the chunk's hits: (0) new step out, gamma parked, class maximum and hit-group moments; (1) the
 // normaliser; (2) normalised gamma out, N_k scatter, bound.  A chunk that fits one stage is parked once.
 // tail: 0 none (rcgs_finalize_kernel follows), 1 the last CTA reduces the partial vectors, 2 ... and takes the control step.
-template <int MODE, bool TAIL>
-__global__ void __launch_bounds__(RS_NT, 2)
-rcgs_sweep_b_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
-                    const double *__restrict__ counts, double *__restrict__ sp_b, double *__restrict__ sp_v,
-                    double *__restrict__ sp_g, double *__restrict__ sp_t, ViArrays va, RcgsGroup grp, ViCtl *ctl,
-                    double *partials, int pstride, unsigned long long N, unsigned long long nnz, int K, double l0, double fx_scale,
-                    int tail) {
-  if (ctl->done) return;
-  if (MODE == 1 ? !ctl->didreset : ctl->stall != 0) return;
+// (the body is shared with rcgs_fused_kernel; it ends with the CTA's partial vector stored)
+template <int MODE>
+__device__ __forceinline__ void
+rcgs_sweep_b_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
+                  const double *__restrict__ counts, double *sp_b, double *sp_v, double *sp_g, double *sp_t,
+                  const ViArrays &va, const RcgsGroup &grp, const ViCtl *ctl,
+                  double *partials, int pstride, unsigned long long N, unsigned long long nnz, int K, double l0, double fx_scale) {
   extern __shared__ __align__(16) unsigned char s_dyn_rs[];
   double *s_an = reinterpret_cast<double *>(s_dyn_rs);            // [K] a'_k
   double *s_En = s_an + K;                                         // [K] exp(a'_k)
@@ -455,14 +466,80 @@ rcgs_sweep_b_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restr
   bound = block_sum<RS_NT>(bound, s_blk);
   mass = block_sum<RS_NT>(mass, s_blk);
   if (threadIdx.x == 0) { out[K + RS_BOUND] = bound; out[K + RS_MASS] = mass; }
+}
+template <int MODE, bool TAIL>
+__global__ void __launch_bounds__(RS_NT, 2)
+rcgs_sweep_b_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
+                    const double *__restrict__ counts, double *__restrict__ sp_b, double *__restrict__ sp_v,
+                    double *__restrict__ sp_g, double *__restrict__ sp_t, ViArrays va, RcgsGroup grp, ViCtl *ctl,
+                    double *partials, int pstride, unsigned long long N, unsigned long long nnz, int K, double l0, double fx_scale,
+                    int tail) {
+  if (ctl->done) return;
+  if (MODE == 1 ? !ctl->didreset : ctl->stall != 0) return;
+  rcgs_sweep_b_body<MODE>(nz_ptr, nz_grp, nz_logl, counts, sp_b, sp_v, sp_g, sp_t, va, grp, ctl, partials, pstride, N, nnz, K, l0, fx_scale);
   if constexpr (TAIL) {
     if (tail != 0 && cta_is_last(ctl)) {
+      __shared__ double s_tail[32];
       reduce_partials_cta<RS_NT>(partials, pstride, (int)gridDim.x, K + 2, va.red, va.seg);   // (slot RS_NORM stays: sweep A's norm)
       if (threadIdx.x == 0) ctl->ticket = 0;
       if (tail == 2) {
         __syncthreads();
-        rcgs_ctl_b_step<RS_NT>(va, grp, ctl, K, MODE, 0, s_blk);
+        rcgs_ctl_b_step<RS_NT>(va, grp, ctl, K, MODE, 0, s_tail);
       }
+    }
+  }
+}
+
+// ---- small problems: whole iterations in ONE launch ---------------------------------------------------------------
+// When an iteration takes tens of microseconds, three launches and their drains are most of it.  rcgs_fused_kernel is a
+// cooperative launch (every CTA resident) that runs up to `n_steps` iterations: sweep A, a grid rendezvous whose last
+// arrival sums the norms, sweep B, a rendezvous whose last arrival reduces the partial vectors and takes the control step,
+// and the restart sweep when that step was rejected.  One GPU only (no collective inside a kernel).
+// The rendezvous: every CTA takes a ticket; the last one runs `last_does`, resets the ticket and bumps ViCtl.epoch; the
+// others wait for the bump.  Fences on both sides as in cooperative groups' grid.sync(): what a CTA wrote before arriving
+// is visible to every CTA after leaving, plain loads included.
+template <class F>
+__device__ __forceinline__ void grid_rendezvous(ViCtl *ctl, unsigned &epoch, F &&last_does) {
+  if (cta_is_last(ctl)) {
+    last_does();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ctl->ticket = 0;
+      __threadfence();
+      atomicExch(&ctl->epoch, epoch + 1u);
+    }
+  } else if (threadIdx.x == 0) {
+    while (*reinterpret_cast<volatile unsigned *>(&ctl->epoch) != epoch + 1u) {}
+    __threadfence();
+  }
+  __syncthreads();
+  epoch += 1u;
+}
+
+static __global__ void __launch_bounds__(RS_NT, 2)
+rcgs_fused_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
+                  const double *__restrict__ counts, double *sp_b, double *sp_v, double *sp_g, double *sp_t, ViArrays va, RcgsGroup grp,
+                  ViCtl *ctl, double *partials, int pstride, unsigned long long N, unsigned long long nnz, int K, double l0,
+                  double fx_scale, unsigned long long n_steps) {
+  __shared__ double s_tail[32];
+  unsigned epoch = *reinterpret_cast<volatile unsigned *>(&ctl->epoch);
+  for (unsigned long long it = 0; it < n_steps; ++it) {
+    if (*reinterpret_cast<volatile int *>(&ctl->done)) break;          // (the same value in every CTA: read between rendezvous)
+    rcgs_sweep_a_body(nz_ptr, nz_grp, nz_logl, sp_b, sp_g, va, grp, partials, pstride, N, nnz, K, l0);
+    grid_rendezvous(ctl, epoch, [&] { rcgs_sum_norms(partials, pstride, va, K); });
+    rcgs_sweep_b_body<0>(nz_ptr, nz_grp, nz_logl, counts, sp_b, sp_v, sp_g, sp_t, va, grp, ctl, partials, pstride, N, nnz, K, l0, fx_scale);
+    grid_rendezvous(ctl, epoch, [&] {
+      reduce_partials_cta<RS_NT>(partials, pstride, (int)gridDim.x, K + 2, va.red, va.seg);
+      __syncthreads();
+      rcgs_ctl_b_step<RS_NT>(va, grp, ctl, K, 0, 0, s_tail);
+    });
+    if (*reinterpret_cast<volatile int *>(&ctl->didreset)) {
+      rcgs_sweep_b_body<1>(nz_ptr, nz_grp, nz_logl, counts, sp_b, sp_v, sp_g, sp_t, va, grp, ctl, partials, pstride, N, nnz, K, l0, fx_scale);
+      grid_rendezvous(ctl, epoch, [&] {
+        reduce_partials_cta<RS_NT>(partials, pstride, (int)gridDim.x, K + 2, va.red, va.seg);
+        __syncthreads();
+        rcgs_ctl_b_step<RS_NT>(va, grp, ctl, K, 1, 0, s_tail);
+      });
     }
   }
 }

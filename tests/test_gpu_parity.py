@@ -236,6 +236,44 @@ def test_sparse_rcg_follows_the_dense_trajectory(case, oracle, mswb, ctx, min_hi
         assert np.max(np.abs(thetas[r] - want.theta)) < THETA_TOL
 
 
+def test_fused_small_problem_kernel_equals_the_launch_per_sweep_path(case, mswb, ctx, monkeypatch):
+    """Small problems on one GPU run whole RCG iterations inside one cooperative launch (rcgs_fused_kernel: the sweeps of
+    vi_sparse_rcg.cuh between grid rendezvous).  Same code, same summation orders: the result must equal the three-launch
+    path bit for bit — trajectory, restarts, abundances — however the iterations are cut into launches."""
+    name, wl, ec, aln = case
+    if len(wl.group_sizes) < 2:
+        pytest.skip("needs two groups")
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=mswb.STORE_SPARSE)
+    runs = {}
+    for label, fused, chunk in (("launches", "0", 8), ("fused", "1", 8), ("fused_1", "1", 1), ("fused_100", "1", 100)):
+        monkeypatch.setenv("MSWB_FUSED", fused)
+        n0 = mswb.launch_count()
+        sess = lik.vi_begin(mswb.ALGO_RCG, tol=1e-6, max_iters=300)
+        while True:
+            sess.step(chunk)
+            st = sess.poll()
+            if st.converged or st.iters >= 300:
+                break
+        tb, tg, tr = sess.trace()
+        r = sess.finish()
+        runs[label] = (tb, tg, tr, r, mswb.launch_count() - n0)
+    tb0, tg0, tr0, r0, n_launches = runs["launches"]
+    for label in ("fused", "fused_1", "fused_100"):
+        tb, tg, tr, r, n = runs[label]
+        assert r.iters == r0.iters and r.converged == r0.converged and r.resets == r0.resets, label
+        assert np.array_equal(tb, tb0) and np.array_equal(tg, tg0) and np.array_equal(tr, tr0), label
+        assert np.array_equal(r.theta, r0.theta) and r.bound == r0.bound, label
+    assert runs["fused_100"][4] < n_launches / 3            # the iterations really ran inside few launches
+    monkeypatch.setenv("MSWB_FUSED", "1")
+    # the restart sweep inside the fused loop: a start that overshoots (large prior counts make early steps lose ground)
+    a0 = np.full(lik.n_groups, 50.0)
+    monkeypatch.setenv("MSWB_FUSED", "0")
+    want = lik.vi_run(mswb.ALGO_RCG, alpha0=a0, tol=1e-6, max_iters=300)
+    monkeypatch.setenv("MSWB_FUSED", "1")
+    got = lik.vi_run(mswb.ALGO_RCG, alpha0=a0, tol=1e-6, max_iters=300)
+    assert got.iters == want.iters and got.resets == want.resets and np.array_equal(got.theta, want.theta)
+
+
 @pytest.mark.parametrize("algo", ["rcg", "em"])
 def test_sparse_posteriors_and_bins_equal_the_dense_ones(case, oracle, mswb, ctx, algo):
     """Posterior export (Sample::store_probs, src/Sample.cpp:63-85) and the binning hand-off from the sparse storage:
@@ -502,6 +540,35 @@ def test_bootstrap_run_matches_reference_loop(oracle, mswb, ctx):
     t1, _ = lik.bootstrap_run(B, seed=99, replica_rank=1, replica_world=2)
     merged = np.where(np.isnan(t0), t1, t0)
     assert np.array_equal(merged, thetas)
+
+
+@pytest.mark.parametrize("algo_name,storage", [("rcg", "sparse"), ("em", "f64")])
+def test_bootstrap_ranks_jump_over_each_others_draws(mswb, ctx, monkeypatch, algo_name, storage):
+    """One std::mt19937_64 serves all replicates (src/BootstrapSample.cpp:48-60).  A rank that owns every third replicate
+    either produces and drops the draws in between (MSWB_MT_JUMP=0) or jumps the generator over them (mt64_jump.cu):
+    the replicates must come out bit-identical, and equal to the single-rank run."""
+    wl = synth.generate(9000, 90, 7, n_present=3, n_templates=60, seed=31)
+    aln = mswb.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes,
+                                storage=mswb.STORE_SPARSE if storage == "sparse" else mswb.STORE_F64)
+    algo = mswb.ALGO_RCG if algo_name == "rcg" else mswb.ALGO_EM
+    B, W = 8, 3
+    whole, it_whole = lik.bootstrap_run(B, seed=-5, algo=algo)
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MSWB_MT_JUMP", mode)
+        merged = np.full_like(whole, np.nan)
+        for r in range(W):
+            t, it = lik.bootstrap_run(B, seed=-5, algo=algo, replica_rank=r, replica_world=W)
+            mine = np.arange(B) % W == r
+            assert np.all(np.isnan(t[~mine])) and not np.any(np.isnan(t[mine]))
+            merged[mine] = t[mine]
+            assert [it[i] for i in np.flatnonzero(mine)] == [it_whole[i] for i in np.flatnonzero(mine)]
+        assert np.array_equal(merged, whole), mode
+    # a fixed number of draws per replicate (--bootstrap-count) moves the replicate boundaries
+    monkeypatch.setenv("MSWB_MT_JUMP", "1")
+    whole, _ = lik.bootstrap_run(5, seed=11, algo=algo, bootstrap_count=1234)
+    t, _ = lik.bootstrap_run(5, seed=11, algo=algo, bootstrap_count=1234, replica_rank=1, replica_world=2)
+    assert np.array_equal(t[[1, 3]], whole[[1, 3]])
 
 
 @pytest.mark.parametrize("storage,K", [("f64", 6), ("f64", 300), ("f64", 1100), ("f32", 300)])

@@ -16,8 +16,12 @@ for K, T, R in ((7, 70, 600), (300, 1500, 800), (1100, 3300, 300)):
         assert abs(r.theta.sum() - 1) < 1e-6
         if storage == M.STORE_SPARSE:
             lik.posteriors(0, min(50, lik.n_ecs))
-            r = lik.vi_run(M.ALGO_RCG, max_iters=6, tol=-1e300)          # sparse RCG: separable state off the hits
+            r = lik.vi_run(M.ALGO_RCG, max_iters=6, tol=-1e300)          # sparse RCG: separable state off the hits (fused launch)
             assert abs(r.theta.sum() - 1) < 1e-9
+            os.environ["MSWB_FUSED"] = "0"                               # ... and one launch per sweep
+            r2 = lik.vi_run(M.ALGO_RCG, max_iters=6, tol=-1e300)
+            os.environ.pop("MSWB_FUSED")
+            assert np.array_equal(r.theta, r2.theta)
             lik.posteriors(0, min(50, lik.n_ecs))
             with np.errstate(divide="ignore"):
                 bins = lik.assign(aln, np.log(r.theta))
