@@ -518,6 +518,27 @@ def extra_sparse(a, torch, M, dist, ctx, stream, rank, world, wl_main, peak):
         out["rcg"]["what"] = ("RCG (the reference's default optimiser) on the same job: dense state would be 3.2 TB; the sparse form keeps "
                               "two K-vectors, two N-vectors and the hits")
         lik.close(); aln.close()
+        if world > 1:
+            # A/B of the per-pass collective on this very job: the library's one-shot exchange over NVLink peer memory inside
+            # its control kernel (csrc/peer.cuh) against ncclAllReduce + a control kernel (a second context with MSWB_PEER=0)
+            out["collective"] = "peer-memory one-shot exchange (in-kernel, rank-ordered sum)" if ctx.peer_active else "ncclAllReduce"
+            if ctx.peer_active:
+                try:
+                    os.environ["MSWB_PEER"] = "0"
+                    nid = dist.broadcast_bytes(M.nccl_unique_id() if rank == 0 else None, M.NCCL_ID_BYTES)
+                    ctx2 = M.Context(ctx.device, rank, world, nid, cuda_stream=stream.cuda_stream)
+                finally:
+                    os.environ.pop("MSWB_PEER", None)
+                aln2 = M.Alignment(ctx2, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets, partitioned=True)
+                lik2 = M.Likelihood.build(ctx2, aln2, wl.group_of_target, wl.group_sizes, storage=M.STORE_SPARSE)
+                s2 = timed_series(torch, M, dist, stream, lik2, M.ALGO_EM, steps, warmup)
+                s2r = timed_series(torch, M, dist, stream, lik2, M.ALGO_RCG, 20, warmup)
+                out["collective_ab"] = {"em_ms_per_step": {"peer": s["ms_total"] / steps, "nccl": s2["ms_total"] / steps},
+                                        "rcg_ms_per_step": {"peer": s_rcg["ms_total"] / 20, "nccl": s2r["ms_total"] / 20},
+                                        "em_launches_per_step": {"peer": s["launches"] / steps, "nccl": s2["launches"] / steps},
+                                        "theta_maxabs_peer_vs_nccl": float(np.max(np.abs(s["res"].theta - s2["res"].theta))),
+                                        "nccl_peer_active": bool(ctx2.peer_active)}
+                lik2.close(); aln2.close(); ctx2.close()
         pinned = []
         if wl is not wl_main:                                   # the e2e leg copies from PINNED host memory, like the headline's
             for arr in (wl.row_ptr, wl.targets):
@@ -707,6 +728,8 @@ def main():
             "cpu_baseline": cb,
             "e2e": e2e,
             "gpu_launches": s["launches"],
+            "collective": None if world == 1 else ("peer-memory one-shot exchange inside the control kernel (csrc/peer.cuh)" if ctx.peer_active
+                                                  else "ncclAllReduce + control kernel"),
             "clocks": clocks,
             "extras": extras or None,
             "check": {"theta_sum": theta_sum, "bound": res.bound, ("multi_gpu_parity" if world > 1 else "parity"): check},

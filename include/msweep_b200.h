@@ -76,6 +76,13 @@ MSWB_API int  mswb_ctx_trim(mswb_ctx *ctx);
  * of waiting for a peer that has failed.  May be called from another host thread than the one driving ctx; a process
  * that holds several ranks calls it on every context when one of them fails.  The context can still be destroyed. */
 MSWB_API int  mswb_ctx_abort(mswb_ctx *ctx);
+/* 1 when the per-pass all-reduce of this context (K + 3 doubles per EM pass, a scalar and K + 1 per RCG
+ * iteration) runs as a one-shot exchange over NVLink peer memory inside the library's own control kernel — every rank
+ * maps every other rank's receive block at context creation (CUDA IPC between processes, peer access between the
+ * contexts of one process) and sums the world's vectors in rank order; 0 when NCCL carries it (one GPU, no peer access
+ * between some pair of devices, or MSWB_PEER=0 in the environment).  The decision is taken collectively: all ranks of
+ * a world answer the same.  mswb_ctx_abort also ends a wait on a peer that will never arrive. */
+MSWB_API int  mswb_ctx_peer_active(const mswb_ctx *ctx);
 /* Creates the CUDA primary context of `device` (seconds on a cold process); call it from a side thread while
  * the host is still parsing its inputs so that mswb_ctx_create returns immediately afterwards. */
 MSWB_API int  mswb_device_warmup(int device);

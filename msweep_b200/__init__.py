@@ -107,6 +107,11 @@ class Context:
         """mswb_ctx_trim: hand the parked device blocks of this context's GPU back to the driver."""
         _check(lib().mswb_ctx_trim(self.h))
 
+    @property
+    def peer_active(self) -> bool:
+        """mswb_ctx_peer_active: the per-pass all-reduce runs over NVLink peer memory inside our own kernel (else NCCL)."""
+        return bool(lib().mswb_ctx_peer_active(self.h))
+
     def abort(self) -> None:
         """mswb_ctx_abort: abort the NCCL communicator (a peer failed); pending collectives end with an error."""
         _check(lib().mswb_ctx_abort(self.h))

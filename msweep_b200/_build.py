@@ -24,7 +24,7 @@ HOST_CXX = "/usr/bin/g++"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 CU_SOURCES = ["ctx.cu", "ec_build.cu", "likelihood.cu", "vi.cu", "vi_batch.cu", "bootstrap.cu", "mt64_jump.cu", "assign.cu"]
-HEADERS = ["common.cuh", "handles.cuh", "vi_kernels.cuh", "vi_sparse_rcg.cuh", "mathfn.cuh", os.path.join("..", "..", "include", "msweep_b200.h")]
+HEADERS = ["common.cuh", "peer.cuh", "handles.cuh", "vi_kernels.cuh", "vi_sparse_rcg.cuh", "mathfn.cuh", os.path.join("..", "..", "include", "msweep_b200.h")]
 
 
 def _mtime(path: str) -> float:

@@ -94,6 +94,110 @@ __global__ void __launch_bounds__(MT_NT) mt64_generate_kernel(unsigned long long
   if (t == 0) state[MT_N] = pos;
 }
 
+// ---- the same stream in PARALLEL segments ---------------------------------------------------------------------------
+// One CTA advances the generator at ~6e8 outputs a second: the 1e7 draws of a config-5 replicate take 18 ms, about as long
+// as the optimiser run that consumes them.  MT19937-64 is linear over GF(2) (mt64_jump.cu): the state L outputs ahead is
+// g_L(A) applied to the state, g_L = z^L mod phi computed once per bootstrap run on the host.  So a replicate's draws are
+// cut into segments of L outputs (L a multiple of 312: every segment starts at a refill boundary of the sequential
+// generator), mt64_chain_kernel walks the segment starts B_0, B_1 = g_L(A) B_0, ... (one CTA: 19937 steps of the recurrence
+// into shared memory, then word m of the next start = XOR of raw[i + m] over the set coefficients i — ~70 us a start) and
+// mt64_segments_kernel generates all segments at once, one CTA each.  The outputs and the state left behind are those of
+// the sequential generator bit for bit (tests/test_gpu_parity.py::test_bootstrap_counts_bit_exact,
+// test_mt64_segments_equal_the_sequential_stream).
+constexpr int MT_RAW = 19937 + MT_N;          // raw words the application of a jump polynomial reads
+constexpr int MT_CHAIN_NT = 960;              // three groups of 320 threads (312 active) share the set coefficients
+constexpr size_t MT_CHAIN_SMEM = (size_t)(MT_RAW + 313 + 3 * 320) * sizeof(unsigned long long);
+
+// state[0..311] + state[312] = consumed count (the sequential generator's state).  First the n_head outputs still waiting in
+// the current array are tempered out (the array is then a refill boundary), then starts[s] = the array jumped s segments
+// ahead, s = 0 .. n_starts - 1, each with its consumed count set to 312.
+__global__ void __launch_bounds__(MT_CHAIN_NT) mt64_chain_kernel(unsigned long long *__restrict__ state, unsigned long long n_head,
+                                                                  unsigned long long *__restrict__ out,
+                                                                  const unsigned long long *__restrict__ gbits, int n_starts,
+                                                                  unsigned long long *__restrict__ starts) {
+  extern __shared__ unsigned long long mt_sm[];
+  unsigned long long *raw = mt_sm;               // [MT_RAW]
+  unsigned long long *g = raw + MT_RAW;          // [313]
+  unsigned long long *part = g + 313;            // [3][320]
+  const int t = threadIdx.x;
+  const unsigned long long pos = state[MT_N];
+  for (int i = t; i < 313; i += MT_CHAIN_NT) g[i] = gbits[i];
+  for (int i = t; i < MT_N; i += MT_CHAIN_NT) raw[i] = state[i];
+  __syncthreads();
+  if (out) for (unsigned long long i = t; i < n_head; i += MT_CHAIN_NT) out[i] = mt64_temper(raw[pos + i]);
+  if (t == 0) state[MT_N] = pos + n_head;
+  for (int s = 0; s < n_starts; ++s) {
+    for (int i = t; i < MT_N; i += MT_CHAIN_NT) starts[(size_t)s * (MT_N + 1) + i] = raw[i];
+    if (t == 0) starts[(size_t)s * (MT_N + 1) + MT_N] = MT_N;
+    if (s + 1 == n_starts) break;
+    // the recurrence reaches back at least 156 words: blocks of 156 words in parallel, five warps behind a named barrier
+    if (t < 160) {
+      for (int k0 = MT_N; k0 < MT_RAW; k0 += MT_M) {
+        const int k = k0 + t;
+        if (t < MT_M && k < MT_RAW) raw[k] = mt64_twist(raw[k - MT_M], raw[k - MT_N], raw[k - MT_N + 1]);
+        asm volatile("bar.sync 1, 160;" ::: "memory");
+      }
+    }
+    __syncthreads();
+    const int grp = t / 320, m = t - grp * 320;
+    unsigned long long acc = 0ull;
+    if (m < MT_N) {
+      for (int w = grp; w < 313; w += 3) {
+        unsigned long long bits = g[w];
+        while (bits) {
+          const int i = 64 * w + __ffsll((long long)bits) - 1;
+          bits &= bits - 1ull;
+          acc ^= raw[i + m];
+        }
+      }
+    }
+    part[t] = acc;
+    __syncthreads();
+    if (t < MT_N) raw[t] = part[t] ^ part[320 + t] ^ part[640 + t];
+    __syncthreads();
+  }
+}
+
+// CTA s: the outputs [s * seg_len, min((s + 1) * seg_len, n)) of the stream that continues from starts[s]; the last CTA leaves
+// the generator's state in `state_out`.
+__global__ void __launch_bounds__(MT_NT) mt64_segments_kernel(const unsigned long long *__restrict__ starts, unsigned long long seg_len,
+                                                             unsigned long long n, unsigned long long *__restrict__ out,
+                                                             unsigned long long *__restrict__ state_out) {
+  __shared__ unsigned long long xs[2][MT_N];
+  const int t = threadIdx.x;
+  const unsigned long long first = (unsigned long long)blockIdx.x * seg_len;
+  if (first >= n) return;
+  const unsigned long long mine = min(seg_len, n - first);
+  const unsigned long long *st = starts + (size_t)blockIdx.x * (MT_N + 1);
+  for (int i = t; i < MT_N; i += MT_NT) xs[0][i] = st[i];
+  unsigned long long pos = MT_N;
+  int cur = 0;
+  __syncthreads();
+  unsigned long long produced = 0;
+  out += first;
+  while (produced < mine) {
+    if (pos == MT_N) {
+      const unsigned long long *x = xs[cur];
+      unsigned long long *y = xs[cur ^ 1];
+      if (t < MT_M) y[t] = mt64_twist(x[t + MT_M], x[t], x[t + 1]);
+      __syncthreads();
+      if (t < MT_M) y[t + MT_M] = mt64_twist(y[t], x[t + MT_M], t + MT_M + 1 < MT_N ? x[t + MT_M + 1] : y[0]);
+      __syncthreads();
+      cur ^= 1;
+      pos = 0;
+    }
+    const unsigned long long take = min((unsigned long long)MT_N - pos, mine - produced);
+    for (unsigned long long i = t; i < take; i += MT_NT) out[produced + i] = mt64_temper(xs[cur][pos + i]);
+    produced += take;
+    pos += take;
+  }
+  if (first + mine == n) {
+    __syncthreads();
+    for (int i = t; i < MT_N; i += MT_NT) state_out[i] = xs[cur][i];
+    if (t == 0) state_out[MT_N] = pos;
+  }
+}
+
 // Philox-4x32-10 keyed by (seed, replicate), counter = draw index / 2; two 64-bit outputs per block.
 __device__ __forceinline__ void philox_round(unsigned (&c)[4], unsigned (&k)[2]) {
   const unsigned long long p0 = 0xD2511F53ull * c[0], p1 = 0xCD9E8D57ull * c[2];
@@ -135,6 +239,7 @@ int mswb_vi_run_batch_dev_counts(mswb_ctx *ctx, mswb_lik *lik, const double *alp
 namespace mswb {      // mt64_jump.cu
 bool mt64_jump_available();
 void mt64_jump(const uint64_t *state, uint64_t n_outputs, uint64_t *out);
+void mt64_jump_poly(uint64_t n_outputs, uint64_t *bits_out);
 }
 
 namespace {
@@ -154,6 +259,12 @@ struct Resampler {
   DevBuf<unsigned long long> mt_state;     // [313] std::mt19937_64's words + consumed count (mt64_generate_kernel)
   DevBuf<unsigned long long> stream_dev;
   static constexpr uint64_t CHUNK = 1u << 24;   // draws generated and consumed at a time (128 MB of stream)
+  // parallel segments (mt64_chain_kernel / mt64_segments_kernel): used when a replicate has enough draws to pay for the
+  // jump polynomial (~50 ms of host time, once per run) and the chain; MSWB_MT_SEGMENTS=0 / n overrides
+  int n_segments = 0;
+  uint64_t seg_len = 0;
+  uint64_t host_pos = MT_N;                     // consumed count of the device generator, tracked on the host
+  DevBuf<unsigned long long> seg_poly, seg_starts;
 
   Resampler(mswb_ctx *c, const mswb_lik *lik, int32_t seed, uint64_t bootstrap_count, int mode) : ctx(c), rng_mode(mode) {
     MSWB_REQUIRE(mode == MSWB_RNG_LIBSTDCXX_EXACT || mode == MSWB_RNG_PHILOX, "unknown rng mode");
@@ -199,6 +310,53 @@ struct Resampler {
     }
   }
 
+  // Decide whether the stream of a replicate is generated in parallel segments; n_mine = replicates this rank resamples.
+  void choose_segments(uint64_t n_mine) {
+    if (rng_mode != MSWB_RNG_LIBSTDCXX_EXACT || draws == 0) return;
+    int want = 16;
+    if (const char *e = std::getenv("MSWB_MT_SEGMENTS")) want = std::atoi(e);
+    else if ((double)draws * (double)n_mine < 4e7) want = 0;          // the polynomial would cost more than it saves
+    if (want < 2 || !mt64_jump_available()) return;
+    want = std::min(want, 64);
+    const uint64_t per_chunk = std::min<uint64_t>(CHUNK, draws);
+    seg_len = (uint64_t)MT_N * ceil_div(per_chunk, (uint64_t)MT_N * (uint64_t)want);
+    std::vector<unsigned long long> bits(313);
+    mt64_jump_poly(seg_len, reinterpret_cast<uint64_t *>(bits.data()));
+    seg_poly.alloc(313);
+    h2d(seg_poly.p, bits.data(), bits.size(), ctx->stream);
+    MSWB_CUDA(cudaStreamSynchronize(ctx->stream));
+    seg_starts.alloc((size_t)want * (MT_N + 1));
+    MSWB_CUDA(cudaFuncSetAttribute(mt64_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_CHAIN_SMEM));
+    n_segments = want;
+  }
+
+  static uint64_t pos_after(uint64_t pos, uint64_t n) {      // consumed count of the array after n more outputs
+    if (n <= (uint64_t)MT_N - pos) return pos + n;
+    const uint64_t rest = n - ((uint64_t)MT_N - pos);
+    return (rest - 1) % (uint64_t)MT_N + 1;
+  }
+
+  // the next n outputs of the stream into stream_dev (n <= CHUNK)
+  void generate(uint64_t n) {
+    cudaStream_t s = ctx->stream;
+    if (n_segments >= 2 && n > (uint64_t)MT_N) {
+      const uint64_t head = std::min<uint64_t>(n, (uint64_t)MT_N - host_pos);
+      const uint64_t rest = n - head;
+      const int n_starts = (int)ceil_div(rest, seg_len);
+      MSWB_REQUIRE(n_starts <= n_segments, "segment plan does not cover the chunk");
+      mt64_chain_kernel<<<1, MT_CHAIN_NT, MT_CHAIN_SMEM, s>>>(mt_state.p, head, stream_dev.p, seg_poly.p, n_starts, seg_starts.p);
+      MSWB_LAUNCHED();
+      if (n_starts > 0) {
+        mt64_segments_kernel<<<n_starts, MT_NT, 0, s>>>(seg_starts.p, seg_len, rest, stream_dev.p + head, mt_state.p);
+        MSWB_LAUNCHED();
+      }
+    } else {
+      mt64_generate_kernel<<<1, MT_NT, 0, s>>>(mt_state.p, n, stream_dev.p);
+      MSWB_LAUNCHED();
+    }
+    host_pos = pos_after(host_pos, n);
+  }
+
   // Replicates of other ranks ahead: jump over them when producing their draws would cost more than the two polynomials
   // a run needs (about 0.1 s of host time; the generator makes ~6e8 draws a second).  MSWB_MT_JUMP=0 / 1 overrides.
   void choose_jump(uint64_t n_replicates, int replica_rank, int replica_world) {
@@ -215,6 +373,7 @@ struct Resampler {
     if (rng_mode != MSWB_RNG_LIBSTDCXX_EXACT || draws == 0 || jump_mode) return;
     mt64_generate_kernel<<<1, MT_NT, 0, ctx->stream>>>(mt_state.p, draws, nullptr);
     MSWB_LAUNCHED();
+    host_pos = pos_after(host_pos, draws);
   }
 
   // hist_dev[N] (zeroed here) receives the resampled class counts of the next replicate; everything is enqueued, nothing waits
@@ -236,11 +395,11 @@ struct Resampler {
         host_rep = replicate;
       }
       h2d(mt_state.p, host_win.data(), host_win.size(), s);      // (pageable source: staged before the call returns)
+      host_pos = MT_N;
     }
     for (uint64_t done = 0; done < draws; done += CHUNK) {
       const uint64_t n = std::min<uint64_t>(CHUNK, draws - done);
-      mt64_generate_kernel<<<1, MT_NT, 0, s>>>(mt_state.p, n, stream_dev.p);
-      MSWB_LAUNCHED();
+      generate(n);
       resample_from_stream_kernel<<<grid, 256, 0, s>>>(stream_dev.p, n, cp.p, n_cp, hist_dev);
       MSWB_LAUNCHED();
     }
@@ -257,6 +416,7 @@ int mswb_bootstrap_resample(mswb_ctx *ctx, const mswb_lik *lik, int32_t seed, ui
     MSWB_REQUIRE(ctx && lik && out, "NULL argument");
     MSWB_CUDA(cudaSetDevice(ctx->device));
     Resampler rs(ctx, lik, seed, bootstrap_count, rng_mode);
+    rs.choose_segments(n_replicates);
     DevBuf<unsigned> hist;
     hist.alloc(rs.N);
     for (uint64_t r = 0; r < n_replicates; ++r) {
@@ -276,6 +436,11 @@ int mswb_bootstrap_run(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const
     MSWB_CUDA(cudaSetDevice(ctx->device));
     Resampler rs(ctx, lik, seed, bootstrap_count, rng_mode);
     rs.choose_jump(n_replicates, replica_rank, replica_world);
+    {
+      uint64_t n_mine = 0;
+      for (uint64_t r = 0; r < n_replicates; ++r) n_mine += (int)(r % (uint64_t)replica_world) == replica_rank;
+      rs.choose_segments(n_mine);
+    }
     DevBuf<unsigned> hist;
     DevBuf<double> counts;
     hist.alloc(rs.N);

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/msweep_b200.h"
+#include "peer.cuh"
 
 namespace mswb {
 
@@ -172,6 +173,14 @@ struct mswb_ctx {
   bool own_stream = false;
   std::atomic<void *> nccl_comm{nullptr};   // (mswb_ctx_abort may take it away from another thread)
   mswb::DevBuf<double> comm_buf;       // staging for the per-pass all-reduce
-  void allreduce_sum(double *buf_dev, size_t count);           // no-op when world == 1
-  void allreduce_sum_u64(unsigned long long *buf_dev, size_t count);
+  // One-shot all-reduce over NVLink peer memory (peer.cuh): set up at context creation when every rank of the world can
+  // map every other rank's block (one process per GPU: CUDA IPC; one thread per GPU: peer access); else NCCL carries it.
+  bool peer_ok = false;
+  mswb::PeerView peer{};
+  void *peer_block = nullptr;               // this rank's receive area + flags (cudaMalloc)
+  std::vector<void *> peer_ipc;             // blocks of other processes opened through CUDA IPC
+  cudaStream_t side_stream = nullptr;       // for the abort word (must not queue behind a waiting kernel)
+  void allreduce_sum(double *buf_dev, size_t count);           // no-op when world == 1; peer memory or NCCL
+  void allreduce_sum_u64(unsigned long long *buf_dev, size_t count);   // NCCL
+  void peer_check();                        // throws when a peer exchange gave up (call after a stream synchronisation)
 };

@@ -2,6 +2,8 @@
 #include "common.cuh"
 
 #include <dlfcn.h>
+#include <unistd.h>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -135,8 +137,177 @@ static NcclApi &nccl() {
                           (nccl().GetErrorString ? nccl().GetErrorString(_r) : "?") + " (" #expr ")"); \
   } while (0)
 
+// ---- one-shot all-reduce over peer memory (peer.cuh) ----------------------------------------------
+namespace mswb {
+static __global__ void __launch_bounds__(256) peer_allreduce_kernel(double *buf, int count, PeerView pv) {
+  peer_allreduce_cta<256>(buf, count, pv);
+}
+
+namespace {
+// What a rank tells the others about its block (summed as 64-bit words over a zeroed table: a gather).
+struct PeerRecord {
+  unsigned long long pid, host, ptr, device;
+  cudaIpcMemHandle_t handle;
+};
+static_assert(sizeof(PeerRecord) % 8 == 0, "the record travels as 64-bit words");
+constexpr size_t REC_WORDS = sizeof(PeerRecord) / 8;
+
+unsigned long long host_id() {
+  char name[256] = {0};
+  gethostname(name, sizeof(name) - 1);
+  unsigned long long h = 1469598103934665603ull;
+  for (const char *c = name; *c; ++c) { h ^= (unsigned char)*c; h *= 1099511628211ull; }
+  // processes of one box share a boot id even when containers rename the host
+  if (FILE *f = fopen("/proc/sys/kernel/random/boot_id", "r")) {
+    char b[64] = {0};
+    if (fgets(b, sizeof(b), f)) for (const char *c = b; *c; ++c) { h ^= (unsigned char)*c; h *= 1099511628211ull; }
+    fclose(f);
+  }
+  return h;
+}
+
+bool peer_wanted() { const char *e = getenv("MSWB_PEER"); return !(e && e[0] == '0'); }
+unsigned long long peer_timeout_ns() {
+  double sec = 300.0;
+  if (const char *e = getenv("MSWB_PEER_TIMEOUT_S")) sec = std::max(0.001, atof(e));
+  return (unsigned long long)(sec * 1e9);
+}
+
+void peer_fill_view(mswb_ctx *ctx, const std::vector<void *> &blocks) {
+  PeerView &v = ctx->peer;
+  std::memset(&v, 0, sizeof(v));
+  for (int p = 0; p < ctx->world; ++p) {
+    unsigned char *b = static_cast<unsigned char *>(blocks[p]);
+    v.recv[p] = reinterpret_cast<double *>(b);
+    v.flags[p] = reinterpret_cast<unsigned long long *>(b + PEER_RECV_DOUBLES * 8);
+  }
+  unsigned long long *tail = v.flags[ctx->rank] + PEER_FLAG_WORDS;
+  v.seq = tail; v.abort_word = tail + 1; v.error_word = tail + 2;
+  v.timeout_ns = peer_timeout_ns();
+  v.world = ctx->world; v.rank = ctx->rank;
+  ctx->peer_ok = true;
+}
+
+void peer_release(mswb_ctx *ctx) {
+  ctx->peer_ok = false;
+  for (void *p : ctx->peer_ipc) cudaIpcCloseMemHandle(p);
+  ctx->peer_ipc.clear();
+  if (ctx->peer_block) cudaFree(ctx->peer_block);
+  ctx->peer_block = nullptr;
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  ctx->side_stream = nullptr;
+  cudaGetLastError();
+}
+
+bool peer_alloc_block(mswb_ctx *ctx) {
+  if (cudaMalloc(&ctx->peer_block, PEER_BLOCK_BYTES) != cudaSuccess) { cudaGetLastError(); ctx->peer_block = nullptr; return false; }
+  if (cudaMemset(ctx->peer_block, 0, PEER_BLOCK_BYTES) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
+// One process per GPU (or one thread per GPU with its own mswb_ctx_create): the ranks gather each other's records over
+// the NCCL communicator they already share, map the blocks (CUDA IPC across processes, peer access inside one), and
+// agree — with one more sum — whether EVERY rank succeeded; otherwise all of them keep NCCL for the data path.
+void peer_setup_exchange(mswb_ctx *ctx) {
+  if (!peer_wanted() || ctx->world > PEER_MAX_WORLD) return;
+  const int W = ctx->world;
+  unsigned long long failed = peer_alloc_block(ctx) ? 0ull : 1ull;
+  PeerRecord mine;
+  std::memset(&mine, 0, sizeof(mine));
+  mine.pid = (unsigned long long)getpid(); mine.host = host_id();
+  mine.ptr = (unsigned long long)(uintptr_t)ctx->peer_block; mine.device = (unsigned long long)ctx->device;
+  if (!failed && cudaIpcGetMemHandle(&mine.handle, ctx->peer_block) != cudaSuccess) { cudaGetLastError(); failed = 1ull; }
+  const size_t words = (size_t)W * REC_WORDS + 1;
+  std::vector<unsigned long long> table(words, 0ull);
+  std::memcpy(&table[(size_t)ctx->rank * REC_WORDS], &mine, sizeof(mine));
+  table[words - 1] = failed;
+  DevBuf<unsigned long long> dev;
+  dev.alloc(words);
+  h2d(dev.p, table.data(), words, ctx->stream);
+  ctx->allreduce_sum_u64(dev.p, words);
+  d2h(table.data(), dev.p, words, ctx->stream);
+  MSWB_CUDA(cudaStreamSynchronize(ctx->stream));
+  bool ok = table[words - 1] == 0ull;
+  std::vector<void *> blocks(W, nullptr);
+  if (ok) {
+    for (int p = 0; p < W && ok; ++p) {
+      PeerRecord r;
+      std::memcpy(&r, &table[(size_t)p * REC_WORDS], sizeof(r));
+      if (p == ctx->rank) { blocks[p] = ctx->peer_block; continue; }
+      if (r.host != mine.host) { ok = false; break; }
+      if (r.pid == mine.pid) {
+        // another context of this process: plain peer access
+        int can = 0;
+        if ((int)r.device == ctx->device) { blocks[p] = (void *)(uintptr_t)r.ptr; continue; }
+        if (cudaDeviceCanAccessPeer(&can, ctx->device, (int)r.device) != cudaSuccess || !can) { cudaGetLastError(); ok = false; break; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess((int)r.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = false; break; }
+        cudaGetLastError();
+        blocks[p] = (void *)(uintptr_t)r.ptr;
+      } else {
+        void *mapped = nullptr;
+        if (cudaIpcOpenMemHandle(&mapped, r.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        ctx->peer_ipc.push_back(mapped);
+        blocks[p] = mapped;
+      }
+    }
+  }
+  // second round: did every rank map every block?
+  unsigned long long bad = ok ? 0ull : 1ull;
+  h2d(dev.p, &bad, 1, ctx->stream);
+  ctx->allreduce_sum_u64(dev.p, 1);
+  d2h(&bad, dev.p, 1, ctx->stream);
+  MSWB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (bad != 0ull) { peer_release(ctx); return; }
+  peer_fill_view(ctx, blocks);
+}
+
+// One host thread per GPU inside one process (mswb_ctx_create_group): no exchange needed.
+void peer_setup_group(int n, mswb_ctx **ctxs) {
+  if (!peer_wanted() || n < 2 || n > PEER_MAX_WORLD) return;
+  bool ok = true;
+  for (int i = 0; i < n && ok; ++i) {
+    if (cudaSetDevice(ctxs[i]->device) != cudaSuccess) { ok = false; break; }
+    ok = peer_alloc_block(ctxs[i]);
+    for (int j = 0; j < n && ok; ++j) {
+      if (j == i || ctxs[j]->device == ctxs[i]->device) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, ctxs[i]->device, ctxs[j]->device) != cudaSuccess || !can) { ok = false; break; }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+      cudaGetLastError();
+    }
+  }
+  if (!ok) {
+    cudaGetLastError();
+    for (int i = 0; i < n; ++i) { cudaSetDevice(ctxs[i]->device); peer_release(ctxs[i]); }
+    return;
+  }
+  std::vector<void *> blocks(n);
+  for (int i = 0; i < n; ++i) blocks[i] = ctxs[i]->peer_block;
+  for (int i = 0; i < n; ++i) peer_fill_view(ctxs[i], blocks);
+}
+} // namespace
+} // namespace mswb
+
+void mswb_ctx::peer_check() {
+  if (!peer_ok) return;
+  unsigned long long err = 0ull;
+  MSWB_CUDA(cudaMemcpy(&err, peer.error_word, sizeof(err), cudaMemcpyDeviceToHost));
+  MSWB_REQUIRE(err == 0ull, "a peer rank did not arrive at the all-reduce (it failed, was aborted, or the wait timed out: MSWB_PEER_TIMEOUT_S)");
+}
+
 void mswb_ctx::allreduce_sum(double *buf_dev, size_t count) {
   if (world == 1 || count == 0) return;
+  if (peer_ok && count <= (size_t)mswb::PEER_SLOT_DOUBLES) {
+    mswb::peer_allreduce_kernel<<<1, 256, 0, stream>>>(buf_dev, (int)count, peer);
+    MSWB_LAUNCHED();
+    return;
+  }
   void *comm = nccl_comm.load();
   MSWB_REQUIRE(comm, "the communicator of this context has been aborted (a peer rank failed)");
   MSWB_NCCL(nccl().AllReduce(buf_dev, buf_dev, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, stream));
@@ -189,6 +360,7 @@ int mswb_ctx_create(int device, int rank, int world_size, const void *nccl_id, v
       void *comm = nullptr;
       MSWB_NCCL(nccl().CommInitRank(&comm, world_size, id, rank));
       ctx->nccl_comm = comm;
+      mswb::peer_setup_exchange(ctx.get());
     }
     *out = ctx.release();
   });
@@ -209,12 +381,23 @@ int mswb_ctx_create_group(int n, const int *devices, mswb_ctx **out) {
       out[i]->world = n;
       out[i]->nccl_comm = comms[i];
     }
+    mswb::peer_setup_group(n, out);
   });
 }
 
 int mswb_ctx_abort(mswb_ctx *ctx) {
   return mswb::guarded([&] {
     MSWB_REQUIRE(ctx, "ctx is NULL");
+    if (ctx->peer_ok && ctx->side_stream) {
+      // a kernel of this rank may be waiting for a peer that will never push: end the wait
+      int cur = 0;
+      cudaGetDevice(&cur);
+      cudaSetDevice(ctx->device);
+      cudaMemsetAsync(ctx->peer.abort_word, 0xff, sizeof(unsigned long long), ctx->side_stream);
+      cudaStreamSynchronize(ctx->side_stream);
+      cudaSetDevice(cur);
+      cudaGetLastError();
+    }
     void *comm = ctx->nccl_comm.exchange(nullptr);
     if (!comm) return;
     MSWB_REQUIRE(nccl().CommAbort, "ncclCommAbort is not available in the loaded NCCL");
@@ -222,11 +405,14 @@ int mswb_ctx_abort(mswb_ctx *ctx) {
   });
 }
 
+int mswb_ctx_peer_active(const mswb_ctx *ctx) { return ctx && ctx->peer_ok ? 1 : 0; }
+
 void mswb_ctx_destroy(mswb_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (void *comm = ctx->nccl_comm.exchange(nullptr)) nccl().CommDestroy(comm);
+  mswb::peer_release(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   mswb::dev_cache_flush(ctx->device);
   delete ctx;

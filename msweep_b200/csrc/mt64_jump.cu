@@ -203,6 +203,26 @@ void mt64_jump(const uint64_t *state, uint64_t n_outputs, uint64_t *out) {
   apply(*g, state, out);
 }
 
+// Coefficients of z^J mod phi as 313 words (bit i = coefficient of z^i): the device applies them itself when a replicate's
+// stream is generated in parallel segments (bootstrap.cu: mt64_chain_kernel).
+void mt64_jump_poly(uint64_t n_outputs, uint64_t *bits_out) {
+  const Field &f = field();
+  if (!f.ok) throw Error("mt19937_64 jump-ahead failed its self-check");
+  std::shared_ptr<const Poly> g;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    auto it = g_cache.find(n_outputs);
+    if (it != g_cache.end()) g = it->second;
+  }
+  if (!g) {
+    g = std::make_shared<const Poly>(f.power_of_z(n_outputs));
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    if (g_cache.size() >= 64) g_cache.clear();
+    g_cache[n_outputs] = g;
+  }
+  std::copy(g->begin(), g->end(), bits_out);
+}
+
 } // namespace mswb
 
 extern "C" int mswb_mt64_jump(const uint64_t *state, uint64_t n_outputs, uint64_t *state_out) {

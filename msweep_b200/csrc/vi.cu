@@ -63,6 +63,33 @@ __global__ void __launch_bounds__(CTL_NT) rcg_ctl_b_kernel(ViArrays a, ViCtl *ct
   rcg_ctl_b_step<CTL_NT>(a, ctl, K, stage, stall_on_reject, scratch);
 }
 
+// Several GPUs with peer memory (peer.cuh): the exchange of the reduced vector and the control step behind it are ONE
+// launch of one CTA — instead of ncclAllReduce + a control kernel.  The exchange itself is unconditional (every rank
+// executes the same sequence of collectives); the control step keeps the early exits of the kernels above.
+__device__ __forceinline__ void peer_gave_up(ViCtl *ctl) {
+  if (threadIdx.x == 0) { ctl->fault = 2; ctl->done = 1; }
+}
+__global__ void __launch_bounds__(CTL_NT) peer_em_ctl_kernel(ViArrays a, ViCtl *ctl, int K, int sparse, PeerView pv) {
+  __shared__ double scratch[32];
+  if (!peer_allreduce_cta<CTL_NT>(a.red, K + RED_EXTRA, pv)) { peer_gave_up(ctl); return; }
+  if (ctl->done) return;
+  em_ctl_step<CTL_NT>(a, ctl, K, sparse, scratch);
+}
+__global__ void __launch_bounds__(CTL_NT) peer_rcg_ctl_b_kernel(ViArrays a, ViCtl *ctl, int K, int stage, int stall_on_reject, PeerView pv) {
+  __shared__ double scratch[32];
+  if (!peer_allreduce_cta<CTL_NT>(a.red, K + 1, pv)) { peer_gave_up(ctl); return; }
+  if (ctl->done) return;
+  if (stage == 0 ? ctl->stall != 0 : !ctl->didreset) return;
+  rcg_ctl_b_step<CTL_NT>(a, ctl, K, stage, stall_on_reject, scratch);
+}
+__global__ void __launch_bounds__(256) peer_rcgs_ctl_b_kernel(ViArrays va, RcgsGroup g, ViCtl *ctl, int K, int stage, int stall_on_reject, PeerView pv) {
+  __shared__ double scratch[32];
+  if (!peer_allreduce_cta<256>(va.red, K + 2, pv)) { peer_gave_up(ctl); return; }
+  if (ctl->done) return;
+  if (stage == 0 ? ctl->stall != 0 : !ctl->didreset) return;
+  rcgs_ctl_b_step<256>(va, g, ctl, K, stage, stall_on_reject, scratch);
+}
+
 __global__ void fill_kernel(double *p, size_t n, double v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -417,9 +444,10 @@ int grid_cap(const mswb_vi *vi, int nvals) {
 }
 
 // ctl_mode: -1 none, 0 EM dense, 1 EM sparse, 2 RCG stage 0 (finalize_ctl_kernel)
-void launch_finalize(mswb_vi *vi, int nvals, int ctl_mode, int ignore_stall = 0) {
-  finalize_ctl_kernel<<<(nvals + FIN_NT - 1) / FIN_NT, FIN_NT, 0, vi->ctx->stream>>>(
-      vi->partials.p, vi->pstride, vi->grid, nvals, vi->arrays, vi->ctl.p, vi->K, ctl_mode, ignore_stall);
+// peer: the last CTA exchanges the reduced vector over peer memory before its control step (several GPUs)
+void launch_finalize(mswb_vi *vi, int nvals, int ctl_mode, int ignore_stall = 0, int peer = 0) {
+  finalize_ctl_kernel<<<finalize_grid(nvals), FIN_NT, 0, vi->ctx->stream>>>(
+      vi->partials.p, vi->pstride, vi->grid, nvals, vi->arrays, vi->ctl.p, vi->K, ctl_mode, ignore_stall, peer, vi->ctx->peer);
   MSWB_LAUNCHED();
 }
 
@@ -576,6 +604,14 @@ void em_iteration(mswb_vi *vi) {
     if (tail == 0) launch_finalize(vi, nvals, sparse);
     return;
   }
+  if (ctx->peer_ok) {
+    // peer memory: the exchange and the control step ride in the last CTA of the reduction (2 launches per iteration),
+    // or in one control CTA behind a sweep whose own last CTA reduced (small problems)
+    if (tail == 0) { launch_finalize(vi, nvals, sparse, 0, 1); return; }
+    peer_em_ctl_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, sparse, ctx->peer);
+    MSWB_LAUNCHED();
+    return;
+  }
   if (tail == 0) launch_finalize(vi, nvals, -1);
   ctx->allreduce_sum(vi->red.p, nvals);
   em_ctl_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, sparse);
@@ -611,6 +647,12 @@ void rcg_iteration(mswb_vi *vi) {
   if (ctx->world == 1) {
     if (tail == 0) launch_finalize(vi, K + 1, 2);
     MSWB_TILE_DISPATCH_RCG(slots, 4, (launch_sweep_b<TL, 1, true>(vi, 1, 2)));
+    return;
+  }
+  if (ctx->peer_ok) {
+    if (tail == 0) { launch_finalize(vi, K + 1, 2, 0, 1); return; }
+    peer_rcg_ctl_b_kernel<<<1, CTL_NT, 0, s>>>(vi->arrays, vi->ctl.p, K, 0, 1, ctx->peer);
+    MSWB_LAUNCHED();
     return;
   }
   if (tail == 0) launch_finalize(vi, K + 1, -1);
@@ -667,15 +709,23 @@ void rcgs_iteration(mswb_vi *vi) {
   }
   if (ctx->world == 1) {
     if (tail == 0) {
-      rcgs_finalize_kernel<<<(K + 2 + FIN_NT - 1) / FIN_NT, FIN_NT, 0, s>>>(vi->partials.p, vi->pstride, vi->grid, vi->arrays, vi->rs, vi->ctl.p, K, 0, 0);
+      rcgs_finalize_kernel<<<finalize_grid(K + 2), FIN_NT, 0, s>>>(vi->partials.p, vi->pstride, vi->grid, vi->arrays, vi->rs, vi->ctl.p, K, 0, 0, 0, ctx->peer);
       MSWB_LAUNCHED();
     }
     launch_rcgs_sweep_b<1>(vi, 2);
     return;
   }
   if (tail == 0) {
-    rcgs_finalize_kernel<<<(K + 2 + FIN_NT - 1) / FIN_NT, FIN_NT, 0, s>>>(vi->partials.p, vi->pstride, vi->grid, vi->arrays, vi->rs, vi->ctl.p, K, -1, 0);
+    const int fused = ctx->peer_ok ? 1 : 0;
+    rcgs_finalize_kernel<<<finalize_grid(K + 2), FIN_NT, 0, s>>>(vi->partials.p, vi->pstride, vi->grid, vi->arrays, vi->rs, vi->ctl.p, K,
+                                                                 fused ? 0 : -1, 0, fused, ctx->peer);
     MSWB_LAUNCHED();
+    if (fused) return;
+  }
+  if (ctx->peer_ok) {
+    peer_rcgs_ctl_b_kernel<<<1, 256, 0, s>>>(vi->arrays, vi->rs, vi->ctl.p, K, 0, 1, ctx->peer);
+    MSWB_LAUNCHED();
+    return;
   }
   ctx->allreduce_sum(vi->red.p, K + 2);
   rcgs_ctl_b_kernel<<<1, 256, 0, s>>>(vi->arrays, vi->rs, vi->ctl.p, K, 0, 1);
@@ -739,6 +789,11 @@ void rcgs_restart_stalled(mswb_vi *vi) {
   mswb_ctx *ctx = vi->ctx;
   const int K = vi->K;
   launch_rcgs_sweep_b<1>(vi, 1);
+  if (ctx->peer_ok) {
+    peer_rcgs_ctl_b_kernel<<<1, 256, 0, ctx->stream>>>(vi->arrays, vi->rs, vi->ctl.p, K, 1, 1, ctx->peer);
+    MSWB_LAUNCHED();
+    return;
+  }
   ctx->allreduce_sum(vi->red.p, K + 2);
   rcgs_ctl_b_kernel<<<1, 256, 0, ctx->stream>>>(vi->arrays, vi->rs, vi->ctl.p, K, 1, 1);
   MSWB_LAUNCHED();
@@ -753,6 +808,11 @@ void rcg_restart_stalled(mswb_vi *vi) {
   if (L->storage == MSWB_STORE_SPARSE) { rcgs_restart_stalled(vi); return; }
   const int slots = L->Kp / 2;
   MSWB_TILE_DISPATCH_RCG(slots, 4, (launch_sweep_b<TL, 1, true>(vi, 1, 1)));
+  if (ctx->peer_ok) {
+    peer_rcg_ctl_b_kernel<<<1, CTL_NT, 0, ctx->stream>>>(vi->arrays, vi->ctl.p, K, 1, 1, ctx->peer);
+    MSWB_LAUNCHED();
+    return;
+  }
   ctx->allreduce_sum(vi->red.p, K + 1);
   rcg_ctl_b_kernel<<<1, CTL_NT, 0, ctx->stream>>>(vi->arrays, vi->ctl.p, K, 1, 1);
   MSWB_LAUNCHED();
@@ -788,6 +848,7 @@ ViCtl poll_ctl(mswb_vi *vi) {
     vi->events_used = 0;
   }
   // (the flag travels in the all-reduced vector: every rank sees it at the same iteration and none is left in a collective)
+  MSWB_REQUIRE(c.fault != 2, "a peer rank did not arrive at the all-reduce (it failed, was aborted, or the wait timed out: MSWB_PEER_TIMEOUT_S)");
   MSWB_REQUIRE(!c.fault, "EM pass: a class normaliser under/overflowed in the linear domain (extreme prior counts)");
   return c;
 }
@@ -872,6 +933,7 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
       ctx->allreduce_sum(vi->block_sums.p + nb, 1);
       d2h(&vi->sum_counts, vi->block_sums.p + nb, 1, s);
       MSWB_CUDA(cudaStreamSynchronize(s));
+      ctx->peer_check();
       vi->counts = vi->own_counts.p;
     } else {
       vi->counts = lik->counts.p;

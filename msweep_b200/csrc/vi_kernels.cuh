@@ -348,6 +348,36 @@ __device__ __forceinline__ void reduce_partials_cta(const double *partials, int 
   }
 }
 
+// The same sum spread over a GRID (finalize kernels: many CTAs x many columns): a CTA owns tiles of 32 columns, warp w
+// adds the partial vectors w, w + NT/32, ... in ascending order — 256-byte coalesced rows, eight independent loads in flight
+// per lane instead of one chain over all CTAs — and warp 0 adds the warps' sums in warp order.  Fixed order for a given
+// (NT, n_ctas): run-to-run reproducible.  s_tile: NT doubles of shared memory.
+template <int NT>
+__device__ __forceinline__ void reduce_partials_tiled(const double *partials, int pstride, int n_ctas, int nvals, double *red,
+                                                      double *s_tile) {
+  constexpr int NWARP = NT / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int v0 = (int)blockIdx.x * 32; v0 < nvals; v0 += (int)gridDim.x * 32) {
+    const int v = v0 + lane;
+    double a = 0.0;
+    if (v < nvals) {
+      const double *p = partials + v;
+#pragma unroll 8
+      for (int c = warp; c < n_ctas; c += NWARP) a += __ldcg(p + (size_t)c * pstride);
+    }
+    __syncthreads();
+    s_tile[warp * 32 + lane] = a;
+    __syncthreads();
+    if (warp == 0 && v < nvals) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < NWARP; ++w) t += s_tile[w * 32 + lane];
+      red[v] = t;
+    }
+  }
+}
+inline int finalize_grid(int nvals) { return (nvals + 31) / 32; }
+
 __device__ __forceinline__ void trace_push(const ViArrays &a, ViCtl *ctl, double gnorm, int reset) {
   if (ctl->iter < a.trace_cap) {
     a.trace_bound[ctl->iter] = ctl->bound;
@@ -856,9 +886,9 @@ finalize_ctl_batch_kernel(const double *partials, int pstride, int n_ctas, int n
   ViCtl *ctl = ctls + rep;
   if (ctl->done) return;
   __shared__ double s_blk[32];
+  __shared__ double s_tile[128];
   const ViArrays a = arrays_of_replicate(base, rep, K, pstride);
-  reduce_partials(partials + (size_t)slot * n_ctas * pstride, pstride, n_ctas, nvals, a.red, (int)(blockIdx.x * 128 + threadIdx.x),
-                  (int)(gridDim.x * 128));
+  reduce_partials_tiled<128>(partials + (size_t)slot * n_ctas * pstride, pstride, n_ctas, nvals, a.red, s_tile);
   if (!cta_is_last(ctl)) return;
   if (threadIdx.x == 0) ctl->ticket = 0;
   __syncthreads();
@@ -1420,19 +1450,28 @@ inline size_t em_sparse_smem_bytes(int K) {
 // ---- separate reduction (+ control) kernel: large grids x many groups ---------------------------------
 // red[v] = sum over CTAs of partials[cta][v], fixed order; v < nvals.  ctl_mode: -1 none (several GPUs: the all-reduce
 // and a control kernel follow), else the last CTA takes the control step (0 EM dense, 1 EM sparse, 2 RCG stage 0).
-constexpr int FIN_NT = 128;
+constexpr int FIN_NT = 256;
+// peer != 0 (several GPUs with peer memory, peer.cuh): the last CTA also exchanges the reduced vector with the other ranks
+// and takes the control step — pass + this kernel are the whole iteration, as on one GPU.
 static __global__ void __launch_bounds__(FIN_NT)
 finalize_ctl_kernel(const double *partials, int pstride, int n_ctas, int nvals, ViArrays arrays, ViCtl *ctl, int K,
-                    int ctl_mode, int ignore_stall) {
+                    int ctl_mode, int ignore_stall, int peer, PeerView pv) {
   if (ctl->done || (ctl->stall && !ignore_stall)) return;
   __shared__ double s_blk[32];
-  reduce_partials(partials, pstride, n_ctas, nvals, arrays.red, (int)(blockIdx.x * FIN_NT + threadIdx.x), (int)(gridDim.x * FIN_NT));
+  __shared__ double s_tile[FIN_NT];
+  reduce_partials_tiled<FIN_NT>(partials, pstride, n_ctas, nvals, arrays.red, s_tile);
   if (ctl_mode < 0) return;
   if (!cta_is_last(ctl)) return;
   if (threadIdx.x == 0) ctl->ticket = 0;
   __syncthreads();
+  if (peer) {
+    if (!peer_allreduce_cta<FIN_NT>(arrays.red, nvals, pv)) {
+      if (threadIdx.x == 0) { ctl->fault = 2; ctl->done = 1; }
+      return;
+    }
+  }
   if (ctl_mode <= 1) em_ctl_step<FIN_NT>(arrays, ctl, K, ctl_mode, s_blk);
-  else rcg_ctl_b_step<FIN_NT>(arrays, ctl, K, 0, 0, s_blk);
+  else rcg_ctl_b_step<FIN_NT>(arrays, ctl, K, 0, peer ? 1 : 0, s_blk);
 }
 
 } // namespace mswb

@@ -101,6 +101,7 @@ __device__ __forceinline__ RcgsStep rcgs_prep_step(const ViArrays &va, const Rcg
 constexpr int RS_NT = 256;
 constexpr int RS_STAGE = 224;      // hits a warp parks at a time
 constexpr int RS_PF = 4;           // sweep A: slabs of 32 hits of the NEXT chunk kept in flight in registers
+constexpr int RS_STAGE_B = 192;    // sweep B parks three doubles per hit (gamma, logl, exp(gamma - class max)): two CTAs per SM up to K = 2000
 constexpr int RS_PFB = 1;          // sweep B: one slab (four values per hit: deeper prefetch spills at two CTAs per SM, and one CTA
                                    // per SM with four slabs measured slower: 2.34 vs 1.93 ms on 2e7 x 2000)
 
@@ -303,10 +304,11 @@ rcgs_sweep_b_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restric
   double *s_En = s_an + K;                                         // [K] exp(a'_k)
   double *s_psi = s_En + K;                                        // [K]
   unsigned *s_acc = reinterpret_cast<unsigned *>(s_psi + K);       // [K][2] fixed-point accumulators
-  double *s_gg = reinterpret_cast<double *>(s_acc + 2 * (size_t)K);   // [warps][RS_STAGE] gamma of the parked hits (before normalisation)
-  double *s_ll = s_gg + (RS_NT / 32) * RS_STAGE;                   // [warps][RS_STAGE] logl of the parked hits
-  double *s_cls = s_ll + (RS_NT / 32) * RS_STAGE;                  // [warps][3][32]: per class of the chunk
-  uint32_t *s_key = reinterpret_cast<uint32_t *>(s_cls + (RS_NT / 32) * 96);   // [warps][RS_STAGE]
+  double *s_gg = reinterpret_cast<double *>(s_acc + 2 * (size_t)K);   // [warps][RS_STAGE_B] gamma of the parked hits (before normalisation)
+  double *s_ll = s_gg + (RS_NT / 32) * RS_STAGE_B;                 // [warps][RS_STAGE_B] logl of the parked hits
+  double *s_ee = s_ll + (RS_NT / 32) * RS_STAGE_B;                 // [warps][RS_STAGE_B] exp(gamma - class maximum)
+  double *s_cls = s_ee + (RS_NT / 32) * RS_STAGE_B;                // [warps][3][32]: per class of the chunk
+  uint32_t *s_key = reinterpret_cast<uint32_t *>(s_cls + (RS_NT / 32) * 96);   // [warps][RS_STAGE_B]
   __shared__ double s_blk[32];
   for (int k = threadIdx.x; k < K; k += RS_NT) { s_psi[k] = va.dg[k]; s_acc[2 * k] = 0u; s_acc[2 * k + 1] = 0u; }
   const RcgsStep stp = rcgs_prep_step<MODE, RS_NT>(va, grp, ctl, K, s_an, s_En, s_blk);
@@ -314,9 +316,10 @@ rcgs_sweep_b_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restric
   const double beta = MODE == 0 ? stp.beta : 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *gg = s_gg + warp * RS_STAGE, *ll = s_ll + warp * RS_STAGE;
-  uint32_t *key = s_key + warp * RS_STAGE;
-  double *cls_m = s_cls + warp * 96, *cls_cw = cls_m + 32, *cls_c = cls_m + 64;   // m_j, c_j exp(b_j'), c_j
+  double *gg = s_gg + warp * RS_STAGE_B, *ll = s_ll + warp * RS_STAGE_B, *ee = s_ee + warp * RS_STAGE_B;
+  uint32_t *key = s_key + warp * RS_STAGE_B;
+  // m_j (the class maximum while the exponentials are taken), c_j exp(b_j'), c_j (one-piece chunks: c_j / normaliser)
+  double *cls_m = s_cls + warp * 96, *cls_cw = cls_m + 32, *cls_c = cls_m + 64;
   double bound = 0.0, mass = 0.0;
   const unsigned long long n_chunks = (N + 31) / 32;
   const unsigned long long warps_total = (unsigned long long)gridDim.x * (RS_NT / 32);
@@ -367,29 +370,84 @@ rcgs_sweep_b_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restric
       if (ch + 1 < ch_end) nxt = load_cls(ch + 1);
       const double vn = MODE == 0 ? fma(beta, cur.vj, l0 - cur.bj) : 0.0;     // class part of the step
       const double bb = MODE == 0 ? cur.bj + vn + shift : l0 + shift;          // class part of gamma before normalisation
-      const bool one_piece = h1 - h0 <= RS_STAGE;
+      const bool one_piece = h1 - h0 <= RS_STAGE_B;
       double mx = bb, sumE = 0.0, sumEa = 0.0, ssum = 0.0;
-      for (int round = 0; round < 3; ++round) {
-        for (unsigned long long q0 = h0; q0 < h1; q0 += RS_STAGE) {
-          const int n_here = (int)min((unsigned long long)RS_STAGE, h1 - q0);
-          if (round == 0 && one_piece) {
-            __syncwarp();
+      // normaliser of the class: exp(bb - mx) (M0' - sum_H E') + sum_hits exp(gg - mx); leaves m_j, c_j exp(b_j') and c_j
+      // (scaled: c_j / normaliser, so that c_j q = c_j exp(gg - mx) / normaliser needs no second exponential per hit)
+      auto class_normaliser = [&](bool scaled) {
+        const double rest = fmax(m0n - sumE, 0.0);
+        const double tot = fma(exp_nonpos(bb - mx), rest, ssum);
+        const double m = mx + log(tot);
+        const double bnew = bb - m;
+        const double wnew = exp(bnew);
+        if (cur.have) {
+          sp_b[j] = bnew;
+          if (MODE == 0) sp_v[j] = vn;
+          if (cur.c > 0.0) {
+            mass = fma(cur.c, wnew, mass);
+            // non-hit part of the bound: c_j exp(b_j') ((l0 - b_j') (M0' - sum_H E') - (Ma' - sum_H E' a'))
+            bound = fma(cur.c * wnew, (l0 - bnew) * rest - (man - sumEa), bound);
+          }
+        }
+        __syncwarp();
+        cls_m[lane] = m;
+        cls_cw[lane] = cur.c * wnew;
+        cls_c[lane] = scaled ? cur.c / tot : cur.c;
+        __syncwarp();
+      };
+      if (one_piece) {
+        // The chunk's hits are parked once.  ONE exponential per hit, taken hit-parallel (every lane busy) against the class
+        // maximum; the class sums it, and c_j q(j,k) = exp(gg - mx) c_j / normaliser.
+        const int n_here = (int)(h1 - h0);
+        __syncwarp();
 #pragma unroll
-            for (int k = 0; k < RS_PFB; ++k) {                        // the hits that arrived in registers
-              const int x = 32 * k + lane;
-              if (x < n_here) { key[x] = pk[k]; ll[x] = pl[k]; gg[x] = step_hit(h0 + x, pk[k], pl[k], pg[k], pt[k]); }
-            }
-            for (int x = 32 * RS_PFB + lane; x < n_here; x += 32) {   // the rest straight from memory
-              const uint32_t kg = nz_grp[h0 + x];
-              const double lg = nz_logl[h0 + x];
-              key[x] = kg; ll[x] = lg;
-              gg[x] = step_hit(h0 + x, kg, lg, MODE == 0 ? sp_g[h0 + x] : 0.0, MODE == 0 ? sp_t[h0 + x] : 0.0);
-            }
-            if (ch + 1 < ch_end) load_hits(h1);
+        for (int k = 0; k < RS_PFB; ++k) {                        // the hits that arrived in registers
+          const int x = 32 * k + lane;
+          if (x < n_here) { key[x] = pk[k]; ll[x] = pl[k]; gg[x] = step_hit(h0 + x, pk[k], pl[k], pg[k], pt[k]); }
+        }
+        for (int x = 32 * RS_PFB + lane; x < n_here; x += 32) {   // the rest straight from memory
+          const uint32_t kg = nz_grp[h0 + x];
+          const double lg = nz_logl[h0 + x];
+          key[x] = kg; ll[x] = lg;
+          gg[x] = step_hit(h0 + x, kg, lg, MODE == 0 ? sp_g[h0 + x] : 0.0, MODE == 0 ? sp_t[h0 + x] : 0.0);
+        }
+        if (ch + 1 < ch_end) load_hits(h1);
+        __syncwarp();
+        const int xa = (int)(cur.a - h0), xb = (int)(cur.b - h0);
+        for (int x = xa; x < xb; ++x) {                           // class-parallel, list order
+          mx = fmax(mx, gg[x]);
+          const int k = (int)(key[x] & SP_GRP_MASK);
+          sumE += s_En[k];
+          sumEa = fma(s_En[k], s_an[k], sumEa);
+        }
+        __syncwarp();
+        cls_m[lane] = mx;
+        __syncwarp();
+        for (int x = lane; x < n_here; x += 32) ee[x] = exp_nonpos(gg[x] - cls_m[key[x] >> 24]);   // hit-parallel
+        __syncwarp();
+        for (int x = xa; x < xb; ++x) ssum += ee[x];              // class-parallel, list order
+        class_normaliser(true);
+        for (int x = lane; x < n_here; x += 32) {                 // hit-parallel: normalised gamma out, N_k scatter, bound
+          const uint32_t kg = key[x];
+          const int k = (int)(kg & SP_GRP_MASK), cl = (int)(kg >> 24);
+          const double gnew = gg[x] - cls_m[cl];
+          sp_g[h0 + x] = gnew;
+          const double ct = cls_c[cl];
+          if (ct > 0.0) {
+            const double cq = ct * ee[x];                                      // c_j q(j,k)
+            bound = fma(cq, ll[x] - gnew, bound);
+            const double val = cq - cls_cw[cl] * s_En[k];                      // the group's closed-form share already counts exp(b_j') E'_k
+            if (val != 0.0) fx_atomic_add(&s_acc[2 * k], __double2ll_rn(val * fx_scale));
+          }
+        }
+      } else {
+        // a chunk in several pieces: parked again in every round (0: new step out, class maximum and hit-group moments;
+        // 1: the normaliser; 2: normalised gamma out, N_k scatter, bound)
+        for (int round = 0; round < 3; ++round) {
+          for (unsigned long long q0 = h0; q0 < h1; q0 += RS_STAGE_B) {
+            const int n_here = (int)min((unsigned long long)RS_STAGE_B, h1 - q0);
             __syncwarp();
-          } else if (!one_piece) {
-            __syncwarp();
-            for (int x = lane; x < n_here; x += 32) {                 // a chunk in several pieces: parked again in every round
+            for (int x = lane; x < n_here; x += 32) {
               const uint32_t kg = nz_grp[q0 + x];
               const double lg = nz_logl[q0 + x];
               double g2;
@@ -402,56 +460,34 @@ rcgs_sweep_b_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restric
               key[x] = kg; gg[x] = g2; ll[x] = lg;
             }
             __syncwarp();
-          }
-          if (round == 0) {                                         // class-parallel, list order
             const unsigned long long lo = max(cur.a, q0), hi = min(cur.b, q0 + (unsigned long long)n_here);
-            for (unsigned long long x = lo; x < hi; ++x) {
-              mx = fmax(mx, gg[x - q0]);
-              const int k = (int)(key[x - q0] & SP_GRP_MASK);
-              sumE += s_En[k];
-              sumEa = fma(s_En[k], s_an[k], sumEa);
-            }
-          } else if (round == 1) {
-            const unsigned long long lo = max(cur.a, q0), hi = min(cur.b, q0 + (unsigned long long)n_here);
-            for (unsigned long long x = lo; x < hi; ++x) ssum += exp_nonpos(gg[x - q0] - mx);
-          } else {
-            for (int x = lane; x < n_here; x += 32) {               // hit-parallel: normalised gamma out, N_k scatter, bound
-              const uint32_t kg = key[x];
-              const int k = (int)(kg & SP_GRP_MASK), cl = (int)(kg >> 24);
-              const double gnew = gg[x] - cls_m[cl];
-              sp_g[q0 + x] = gnew;
-              const double cj = cls_c[cl];
-              if (cj > 0.0) {
-                const double cq = cj * exp_nonpos(fmin(gnew, 0.0));           // c_j q(j,k)
-                bound = fma(cq, ll[x] - gnew, bound);
-                const double val = cq - cls_cw[cl] * s_En[k];                   // the group's closed-form share already counts exp(b_j') E'_k
-                if (val != 0.0) fx_atomic_add(&s_acc[2 * k], __double2ll_rn(val * fx_scale));
+            if (round == 0) {                                         // class-parallel, list order
+              for (unsigned long long x = lo; x < hi; ++x) {
+                mx = fmax(mx, gg[x - q0]);
+                const int k = (int)(key[x - q0] & SP_GRP_MASK);
+                sumE += s_En[k];
+                sumEa = fma(s_En[k], s_an[k], sumEa);
+              }
+            } else if (round == 1) {
+              for (unsigned long long x = lo; x < hi; ++x) ssum += exp_nonpos(gg[x - q0] - mx);
+            } else {
+              for (int x = lane; x < n_here; x += 32) {               // hit-parallel
+                const uint32_t kg = key[x];
+                const int k = (int)(kg & SP_GRP_MASK), cl = (int)(kg >> 24);
+                const double gnew = gg[x] - cls_m[cl];
+                sp_g[q0 + x] = gnew;
+                const double cj = cls_c[cl];
+                if (cj > 0.0) {
+                  const double cq = cj * exp_nonpos(fmin(gnew, 0.0));           // c_j q(j,k)
+                  bound = fma(cq, ll[x] - gnew, bound);
+                  const double val = cq - cls_cw[cl] * s_En[k];
+                  if (val != 0.0) fx_atomic_add(&s_acc[2 * k], __double2ll_rn(val * fx_scale));
+                }
               }
             }
           }
-        }
-        if (!one_piece && round == 0 && ch + 1 < ch_end) load_hits(h1);
-        if (round == 1) {
-          // normaliser of the class: exp(bb - mx) (M0' - sum_H E') + sum_hits exp(gg - mx)
-          const double rest = fmax(m0n - sumE, 0.0);
-          const double tot = fma(exp_nonpos(bb - mx), rest, ssum);
-          const double m = mx + log(tot);
-          const double bnew = bb - m;
-          const double wnew = exp(bnew);
-          if (cur.have) {
-            sp_b[j] = bnew;
-            if (MODE == 0) sp_v[j] = vn;
-            if (cur.c > 0.0) {
-              mass = fma(cur.c, wnew, mass);
-              // non-hit part of the bound: c_j exp(b_j') ((l0 - b_j') (M0' - sum_H E') - (Ma' - sum_H E' a'))
-              bound = fma(cur.c * wnew, (l0 - bnew) * rest - (man - sumEa), bound);
-            }
-          }
-          __syncwarp();
-          cls_m[lane] = m;
-          cls_cw[lane] = cur.c * wnew;
-          cls_c[lane] = cur.c;
-          __syncwarp();
+          if (round == 0 && ch + 1 < ch_end) load_hits(h1);
+          if (round == 1) class_normaliser(false);
         }
       }
     }
@@ -544,23 +580,31 @@ rcgs_fused_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restric
   }
 }
 inline size_t rcgs_sweep_b_smem(int K) {
-  return (size_t)K * 32 + (size_t)(RS_NT / 32) * RS_STAGE * (16 + 4) + (size_t)(RS_NT / 32) * 96 * 8;
+  return (size_t)K * 32 + (size_t)(RS_NT / 32) * RS_STAGE_B * (24 + 4) + (size_t)(RS_NT / 32) * 96 * 8;
 }
 
 // Reduction of the partial vectors of sweep B over several CTAs (large grids x many groups); ctl_stage >= 0: the last
-// CTA takes the control step (one GPU), -1: the all-reduce and rcgs_ctl_b_kernel follow.
+// CTA takes the control step (one GPU; several GPUs with peer memory: after exchanging the vector), -1: the NCCL all-reduce
+// and rcgs_ctl_b_kernel follow.
 static __global__ void __launch_bounds__(FIN_NT)
 rcgs_finalize_kernel(const double *partials, int pstride, int n_ctas, ViArrays va, RcgsGroup grp, ViCtl *ctl, int K, int ctl_stage,
-                     int restart) {
+                     int restart, int peer, PeerView pv) {
   if (ctl->done) return;
   if (restart ? !ctl->didreset : ctl->stall != 0) return;
   __shared__ double s_blk[32];
-  reduce_partials(partials, pstride, n_ctas, K + 2, va.red, (int)(blockIdx.x * FIN_NT + threadIdx.x), (int)(gridDim.x * FIN_NT));
+  __shared__ double s_tile[FIN_NT];
+  reduce_partials_tiled<FIN_NT>(partials, pstride, n_ctas, K + 2, va.red, s_tile);
   if (ctl_stage < 0) return;
   if (!cta_is_last(ctl)) return;
   if (threadIdx.x == 0) ctl->ticket = 0;
   __syncthreads();
-  rcgs_ctl_b_step<FIN_NT>(va, grp, ctl, K, ctl_stage, 0, s_blk);
+  if (peer) {                                   // several GPUs, peer memory: exchange, then the control step (peer.cuh)
+    if (!peer_allreduce_cta<FIN_NT>(va.red, K + 2, pv)) {
+      if (threadIdx.x == 0) { ctl->fault = 2; ctl->done = 1; }
+      return;
+    }
+  }
+  rcgs_ctl_b_step<FIN_NT>(va, grp, ctl, K, ctl_stage, peer ? 1 : 0, s_blk);
 }
 
 // Start: gamma = log(1/K) everywhere (a = 0, b = log(1/K), hits log(1/K)), no direction; moments for the first sweep A.

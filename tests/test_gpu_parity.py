@@ -501,6 +501,33 @@ def test_bootstrap_counts_bit_exact(oracle, mswb, ctx):
     assert list(ph.sum(axis=1)) == [int(ec.count.sum())] * 2 and not np.array_equal(ph[0], ph[1])
 
 
+@pytest.mark.parametrize("segments", ["2", "5", "16"])
+def test_mt64_segments_equal_the_sequential_stream(oracle, mswb, ctx, monkeypatch, segments):
+    """A replicate's std::mt19937_64 stream generated in parallel segments (bootstrap.cu: mt64_chain_kernel applies
+    z^L mod phi to the generator's state, mt64_segments_kernel generates all segments at once) must be the sequential
+    stream bit for bit: resampled counts equal libstdc++'s (the oracle calls std::mt19937_64 itself) over several
+    replicates — the consumed count inside the generator's array moves from replicate to replicate — and for draw counts
+    that are not multiples of 312 or of the segment length."""
+    wl = synth.generate(20000, 200, 10, n_present=3, n_templates=300, seed=8)
+    ec = oracle.ec_build_csr(wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    aln = mswb.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+    lik = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes)
+    monkeypatch.setenv("MSWB_MT_SEGMENTS", segments)
+    assert np.array_equal(lik.bootstrap_resample(3, 5), oracle.bootstrap_resample(ec.count, 3, 5))
+    for count in (313, 1000, 6241, 50001):
+        assert np.array_equal(lik.bootstrap_resample(-9, 3, bootstrap_count=count), oracle.bootstrap_resample(ec.count, -9, 3, count)), count
+    # the replicate loop on top of it, with ranks jumping over each other's replicates
+    lik_sp = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=mswb.STORE_SPARSE)
+    monkeypatch.setenv("MSWB_MT_SEGMENTS", "0")
+    whole, it_whole = lik_sp.bootstrap_run(6, seed=21)
+    monkeypatch.setenv("MSWB_MT_SEGMENTS", segments)
+    again, it_again = lik_sp.bootstrap_run(6, seed=21)
+    assert np.array_equal(whole, again) and list(it_whole) == list(it_again)
+    monkeypatch.setenv("MSWB_MT_JUMP", "1")
+    t, _ = lik_sp.bootstrap_run(6, seed=21, replica_rank=1, replica_world=3)
+    assert np.array_equal(t[[1, 4]], whole[[1, 4]])
+
+
 def test_philox_bootstrap_is_a_fair_multinomial(mswb, ctx):
     """MSWB_RNG_PHILOX has no reference stream to match: check it statistically (counts within 6 sigma of n p, replicates
     and seeds independent, totals exact)."""

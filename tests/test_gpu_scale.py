@@ -113,7 +113,9 @@ def test_sparse_storage_at_scale(big, mswb, ctx):
     assert np.max(np.abs(conv_d.theta - conv_s.theta)) < 1e-6 and abs(conv_d.bound - conv_s.bound) < 1e-9 * abs(conv_d.bound)
     again = sparse.vi_run(mswb.ALGO_RCG)
     assert np.array_equal(again.theta, conv_s.theta) and again.bound == conv_s.bound and again.iters == conv_s.iters
+    # posteriors of the two converged runs: they may stop up to 3 iterations apart (asserted above; the stopping rule is
+    # decided by the summation order at this size), and a class's responsibilities move more than theta does in an iteration
     g_d, g_s = dense.posteriors(1000, 1300), sparse.posteriors(1000, 1300)
-    assert np.max(np.abs(np.exp(g_d) - np.exp(g_s))) < 1e-7
+    assert np.max(np.abs(np.exp(g_d) - np.exp(g_s))) < (1e-7 if conv_d.iters == conv_s.iters else 1e-5)
     em_d, em_s = dense.vi_run(mswb.ALGO_EM, tol=0.0, max_iters=50), sparse.vi_run(mswb.ALGO_EM, tol=0.0, max_iters=50)
     assert np.max(np.abs(em_d.theta - em_s.theta)) < 1e-11 and abs(em_d.bound - em_s.bound) < 1e-12 * abs(em_d.bound)

@@ -61,7 +61,8 @@ if rank == 0:
     assert np.array_equal(mask_mh, ref_mh.mask) and np.array_equal(hits_mh, ref_mh.hits)
     ref = orc.vi_run("rcg", ref_mh.logl, ref_mh.log_counts)
     assert res["rcg_mh"].iters == ref.iters and np.max(np.abs(res["rcg_mh"].theta - ref.theta)) < 1e-6
-    print(f"multi-GPU parity ok on {world} GPUs: {ec.n_ecs} ECs, rcg {res['rcg'].iters} iters, em {res['em'].iters} iters")
+    how = "peer-memory exchange" if ctx.peer_active else "NCCL all-reduce"
+    print(f"multi-GPU parity ok on {world} GPUs: {ec.n_ecs} ECs, rcg {res['rcg'].iters} iters, em {res['em'].iters} iters, collective: {how}")
 dist.barrier()
 ctx.close()
 dist.finalize()
