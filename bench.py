@@ -637,14 +637,18 @@ def main():
         t0 = time.perf_counter()
         with torch.cuda.stream(stream):
             aln = M.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets, partitioned=world > 1)
+            t_ec = time.perf_counter()              # (mswb_ec_build returns with the table built: its class count is an output)
             lik = M.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=storage)
+            t_lik = time.perf_counter()             # (enqueued, not necessarily finished: no synchronisation is added for the split)
             r2 = lik.vi_run(algo, tol=0.0 if a.algo == "em" else -1e300, max_iters=a.steps, poll_every=a.steps)
         torch.cuda.synchronize()
-        sec = dist.reduce_max(time.perf_counter() - t0)
+        t1 = time.perf_counter()
+        sec = dist.reduce_max(t1 - t0)
+        stages = {"ec_build_s": round(t_ec - t0, 4), "likelihood_build_call_s": round(t_lik - t_ec, 4), "vi_run_s": round(t1 - t_lik, 4)}
         assert r2.iters == a.steps
         h2d = wl.row_ptr.nbytes + wl.targets.nbytes + wl.group_of_target.nbytes + wl.group_sizes.nbytes + 8 * N_GROUPS
         e2e = {"value": n_job * a.steps / sec, "unit": UNIT, "vi_iters_per_s": a.steps / sec, "seconds": sec,
-               "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": (8 * N_GROUPS + 64) / a.steps,
+               "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": (8 * N_GROUPS + 64) / a.steps, "stages_rank0": stages,
                "what": "mswb_ec_build + mswb_lik_build + mswb_vi_run(K iterations) from pinned host CSR buffers, theta back on the host",
                "allocator": "cold: the library's device block cache was emptied (mswb_ctx_trim) before the leg, so the cudaMalloc of the matrix is inside"}
         lik.close(); aln.close()

@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <algorithm>
 #include <stdexcept>
 #include <string>
@@ -21,7 +23,7 @@ struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
 #define MSWB_CUDA(expr)                                                                              \
   do {                                                                                               \
     cudaError_t _e = (expr);                                                                         \
-    if (_e != cudaSuccess)                                                                           \
+    if (_e != cudaSuccess && cudaGetLastError() != (cudaError_t)-1) /* (clears the recorded error) */ \
       throw ::mswb::Error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ +  \
                           ":" + std::to_string(__LINE__) + " (" #expr ")");                          \
   } while (0)
@@ -97,6 +99,20 @@ template <typename T> void h2d(T *dst_dev, const T *src, size_t count, cudaStrea
 }
 template <typename T> void d2h(T *dst, const T *src_dev, size_t count, cudaStream_t s) {
   if (count) MSWB_CUDA(cudaMemcpyAsync(dst, src_dev, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+}
+
+// Kernels that take more than 48 KB of dynamic shared memory need the function attribute raised first.  It is raised, never
+// lowered (a smaller request of another problem must not take it away from a cached larger one), per (kernel, device).
+template <class Kern> void ensure_dyn_smem(Kern kern, int device, size_t smem) {
+  if (smem <= 48 * 1024) return;
+  static std::map<std::pair<const void *, int>, size_t> raised;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &have = raised[std::make_pair((const void *)kern, device)];
+  if (smem > have) {
+    MSWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
+  }
 }
 
 inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

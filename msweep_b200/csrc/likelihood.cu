@@ -484,6 +484,7 @@ int mswb_lik_build(mswb_ctx *ctx, const mswb_aln *aln, const uint32_t *group_of_
       ctx->allreduce_sum(tmp.p, v.size());
       d2h(v.data(), tmp.p, v.size(), s);
       MSWB_CUDA(cudaStreamSynchronize(s));
+      ctx->peer_check();
       for (int r = 0; r < ctx->world; ++r) { if (r < ctx->rank) L->ec_begin += (uint64_t)v[r]; L->N_total += (uint64_t)v[r]; }
       n_aligned_total = v[ctx->world];
       lo = 0; hi = aln->n_ecs;
@@ -598,6 +599,7 @@ int mswb_lik_from_dense(mswb_ctx *ctx, const double *logl, uint32_t n_groups, ui
     ctx->allreduce_sum(tmp.p, ctx->world);
     d2h(sizes.data(), tmp.p, ctx->world, s);
     MSWB_CUDA(cudaStreamSynchronize(s));
+    ctx->peer_check();
     for (int r = 0; r < ctx->world; ++r) { if (r < ctx->rank) L->ec_begin += (uint64_t)sizes[r]; L->N_total += (uint64_t)sizes[r]; }
 
     // K x N group-major on the host -> N x Kp EC-major on the device
@@ -627,6 +629,7 @@ int mswb_lik_from_dense(mswb_ctx *ctx, const double *logl, uint32_t n_groups, ui
     ctx->allreduce_sum(tmp.p, 1);
     d2h(&L->sum_counts_total, tmp.p, 1, s);
     MSWB_CUDA(cudaStreamSynchronize(s));
+    ctx->peer_check();
     *out = L.release();
   });
 }

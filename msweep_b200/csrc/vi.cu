@@ -392,13 +392,13 @@ template <class Kern> int persistent_grid(mswb_ctx *ctx, Kern kern, int nt, size
   struct Key { const void *k; int nt; size_t smem; bool operator<(const Key &o) const { return std::tie(k, nt, smem) < std::tie(o.k, o.nt, o.smem); } };
   static std::map<Key, int> cache;
   static std::mutex mu;
+  ensure_dyn_smem(kern, ctx->device, smem);
   int per_sm;
   {
     std::lock_guard<std::mutex> lock(mu);
     const Key key{(const void *)kern, nt, smem};
     auto it = cache.find(key);
     if (it == cache.end()) {
-      if (smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int v = 1;
       MSWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, nt, smem));
       it = cache.emplace(key, v < 1 ? 1 : v).first;
@@ -551,7 +551,7 @@ template <class TL, int MODE, bool WRITE> int launch_sweep_b(mswb_vi *vi, int on
                                             vi->K, only_if_reset, geom, tail);
       } else {
         auto kern_t = rcg_sweep_b_kernel<TL, MODE, WRITE, true, true>;
-        if (smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(kern_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ensure_dyn_smem(kern_t, vi->ctx->device, smem);
         kern_t<<<vi->grid, TL::NT, smem, s>>>(L->logl.p, gam, stp, ld, vi->arrays, vi->counts, vi->ctl.p, vi->partials.p, vi->pstride, L->N,
                                               vi->K, only_if_reset, geom, tail);
       }
@@ -590,7 +590,7 @@ void em_iteration(mswb_vi *vi) {
     vi->grid = persistent_grid(ctx, em_sparse_pass_kernel<false>, SP_NT, smem, ceil_div(L->N, (uint64_t)SP_NT), grid_cap(vi, nvals));
     tail = tail_mode(vi, vi->grid, nvals);
     auto kern = tail ? em_sparse_pass_kernel<true> : em_sparse_pass_kernel<false>;
-    if (tail && smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (tail) ensure_dyn_smem(kern, ctx->device, smem);
     kern<<<vi->grid, SP_NT, smem, s>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_dP.p, L->P0.p, L->rowmax.p, vi->counts,
                                       vi->arrays, vi->ctl.p, vi->partials.p, vi->pstride, L->N, L->nnz, K, vi->fx_scale, tail);
     MSWB_LAUNCHED();
@@ -674,7 +674,7 @@ template <int MODE> int launch_rcgs_sweep_b(mswb_vi *vi, int force_tail) {
   vi->grid = persistent_grid(vi->ctx, kern1, RS_NT, smem, ceil_div(L->N, (uint64_t)RS_NT), grid_cap(vi, K + 2));
   const int tail = force_tail >= 0 ? force_tail : tail_mode(vi, vi->grid, K + 2);
   if (tail == 0) {
-    if (smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ensure_dyn_smem(kern0, vi->ctx->device, smem);
     kern0<<<vi->grid, RS_NT, smem, vi->ctx->stream>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_logl.p, vi->counts, L->sp_b.p, L->sp_v.p, L->sp_g.p, L->sp_t.p,
                                                        vi->arrays, vi->rs, vi->ctl.p, vi->partials.p, vi->pstride, L->N, L->nnz, K, L->l0, vi->fx_scale, 0);
   } else {

@@ -50,11 +50,11 @@ template <class Kern> int resident_ctas(mswb_ctx *ctx, Kern kern, int nt, size_t
   struct Key { const void *k; int nt; size_t smem; bool operator<(const Key &o) const { return std::tie(k, nt, smem) < std::tie(o.k, o.nt, o.smem); } };
   static std::map<Key, int> cache;
   static std::mutex mu;
+  ensure_dyn_smem(kern, ctx->device, smem);
   std::lock_guard<std::mutex> lock(mu);
   const Key key{(const void *)kern, nt, smem};
   auto it = cache.find(key);
   if (it == cache.end()) {
-    if (smem > 48 * 1024) MSWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int v = 1;
     MSWB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, nt, smem));
     it = cache.emplace(key, v < 1 ? 1 : v).first;
