@@ -5,6 +5,7 @@
 #include <unistd.h>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -14,21 +15,36 @@ void set_last_error(const std::string &msg) { t_last_error = msg; }
 std::atomic<uint64_t> g_launches{0};
 
 // ---- device block cache (common.cuh) ------------------------------------------------------------
+// Two pools per device.  Large blocks (>= 64 MB: the matrices) are parked and handed to requests of a similar size.
+// Small blocks come in size classes (powers of two up to 1 MB, multiples of 1 MB beyond) and are recycled exactly: an
+// optimiser run allocates ~20 K-sized vectors, a bootstrap job runs hundreds of them — cudaMalloc / cudaFree per vector
+// (each cudaFree an implicit device synchronisation plus an unmap in the driver) showed up as milliseconds per replicate.
 namespace {
 struct CachedBlock { void *p; size_t bytes; int device; };
 std::mutex g_cache_mu;
 std::vector<CachedBlock> g_cache;
+std::map<std::pair<int, size_t>, std::vector<void *>> g_small;      // (device, class bytes) -> parked blocks
+std::map<int, size_t> g_small_held;                                  // device -> parked bytes
 constexpr size_t CACHE_MIN_BYTES = (size_t)64 << 20;
+constexpr size_t SMALL_CAP_BYTES = (size_t)2 << 30;                  // parked small blocks per device
+
+size_t small_class(size_t bytes) {
+  if (bytes <= ((size_t)1 << 20)) { size_t c = 512; while (c < bytes) c <<= 1; return c; }
+  return (bytes + (((size_t)1 << 20) - 1)) & ~(((size_t)1 << 20) - 1);
+}
 } // namespace
 
 void dev_cache_flush(int device) {
-  std::vector<CachedBlock> mine;
+  std::vector<void *> mine;
   {
     std::lock_guard<std::mutex> lock(g_cache_mu);
     for (size_t i = 0; i < g_cache.size();)
-      if (g_cache[i].device == device) { mine.push_back(g_cache[i]); g_cache[i] = g_cache.back(); g_cache.pop_back(); } else ++i;
+      if (g_cache[i].device == device) { mine.push_back(g_cache[i].p); g_cache[i] = g_cache.back(); g_cache.pop_back(); } else ++i;
+    for (auto &kv : g_small)
+      if (kv.first.first == device) { mine.insert(mine.end(), kv.second.begin(), kv.second.end()); kv.second.clear(); }
+    g_small_held[device] = 0;
   }
-  for (const CachedBlock &b : mine) cudaFree(b.p);
+  for (void *p : mine) cudaFree(p);
 }
 
 void *dev_alloc(size_t bytes, size_t *capacity, int *device_out) {
@@ -49,6 +65,17 @@ void *dev_alloc(size_t bytes, size_t *capacity, int *device_out) {
       g_cache.pop_back();
       return p;
     }
+  } else {
+    bytes = small_class(bytes);
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    auto it = g_small.find(std::make_pair(device, bytes));
+    if (it != g_small.end() && !it->second.empty()) {
+      void *p = it->second.back();
+      it->second.pop_back();
+      g_small_held[device] -= bytes;
+      *capacity = bytes;
+      return p;
+    }
   }
   void *p = nullptr;
   cudaError_t e = cudaMalloc(&p, bytes);
@@ -65,26 +92,30 @@ void *dev_alloc(size_t bytes, size_t *capacity, int *device_out) {
   return p;
 }
 
-// Blocks of 64 MB and more are parked for reuse under the device they were allocated on — whatever device is
-// current in the calling thread — as long as the parked total of that device stays under the cap (MSWB_CACHE_GB,
-// default a quarter of the device's memory); mswb_ctx_trim / mswb_ctx_destroy hand everything back to the driver.
+// Blocks go back to the pool of the device they were allocated on — whatever device is current in the calling thread.
+// Large blocks: as long as the parked total of that device stays under the cap (MSWB_CACHE_GB, default a quarter of the
+// device's memory); small blocks: up to SMALL_CAP_BYTES.  mswb_ctx_trim / mswb_ctx_destroy hand everything back to the driver.
 void dev_free(void *p, size_t capacity, int device) {
   if (!p) return;
   int current = 0;
   cudaGetDevice(&current);
   if (current != device) cudaSetDevice(device);
   bool parked = false;
+  cudaDeviceSynchronize();   // what cudaFree would have done: nothing in flight still uses the block
   if (capacity >= CACHE_MIN_BYTES) {
     static size_t cap_bytes = 0;
     if (cap_bytes == 0) {
       if (const char *e = getenv("MSWB_CACHE_GB")) cap_bytes = (size_t)(atof(e) * 1073741824.0) + 1;
       else { size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b); cap_bytes = total_b / 4 + 1; }
     }
-    cudaDeviceSynchronize();   // what cudaFree would have done: nothing in flight still uses the block
     std::lock_guard<std::mutex> lock(g_cache_mu);
     size_t held = 0;
     for (const CachedBlock &b : g_cache) if (b.device == device) held += b.bytes;
     if (held + capacity <= cap_bytes) { g_cache.push_back(CachedBlock{p, capacity, device}); parked = true; }
+  } else if (capacity == small_class(capacity)) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    size_t &held = g_small_held[device];
+    if (held + capacity <= SMALL_CAP_BYTES) { g_small[std::make_pair(device, capacity)].push_back(p); held += capacity; parked = true; }
   }
   if (!parked) cudaFree(p);
   if (current != device) cudaSetDevice(current);

@@ -446,7 +446,7 @@ int grid_cap(const mswb_vi *vi, int nvals) {
 // ctl_mode: -1 none, 0 EM dense, 1 EM sparse, 2 RCG stage 0 (finalize_ctl_kernel)
 // peer: the last CTA exchanges the reduced vector over peer memory before its control step (several GPUs)
 void launch_finalize(mswb_vi *vi, int nvals, int ctl_mode, int ignore_stall = 0, int peer = 0) {
-  finalize_ctl_kernel<<<finalize_grid(nvals), FIN_NT, 0, vi->ctx->stream>>>(
+  finalize_ctl_kernel<<<finalize_grid(nvals, FIN_NT), FIN_NT, 0, vi->ctx->stream>>>(
       vi->partials.p, vi->pstride, vi->grid, nvals, vi->arrays, vi->ctl.p, vi->K, ctl_mode, ignore_stall, peer, vi->ctx->peer);
   MSWB_LAUNCHED();
 }
@@ -709,7 +709,7 @@ void rcgs_iteration(mswb_vi *vi) {
   }
   if (ctx->world == 1) {
     if (tail == 0) {
-      rcgs_finalize_kernel<<<finalize_grid(K + 2), FIN_NT, 0, s>>>(vi->partials.p, vi->pstride, vi->grid, vi->arrays, vi->rs, vi->ctl.p, K, 0, 0, 0, ctx->peer);
+      rcgs_finalize_kernel<<<finalize_grid(K + 2, FIN_NT), FIN_NT, 0, s>>>(vi->partials.p, vi->pstride, vi->grid, vi->arrays, vi->rs, vi->ctl.p, K, 0, 0, 0, ctx->peer);
       MSWB_LAUNCHED();
     }
     launch_rcgs_sweep_b<1>(vi, 2);
@@ -717,7 +717,7 @@ void rcgs_iteration(mswb_vi *vi) {
   }
   if (tail == 0) {
     const int fused = ctx->peer_ok ? 1 : 0;
-    rcgs_finalize_kernel<<<finalize_grid(K + 2), FIN_NT, 0, s>>>(vi->partials.p, vi->pstride, vi->grid, vi->arrays, vi->rs, vi->ctl.p, K,
+    rcgs_finalize_kernel<<<finalize_grid(K + 2, FIN_NT), FIN_NT, 0, s>>>(vi->partials.p, vi->pstride, vi->grid, vi->arrays, vi->rs, vi->ctl.p, K,
                                                                  fused ? 0 : -1, 0, fused, ctx->peer);
     MSWB_LAUNCHED();
     if (fused) return;
@@ -732,6 +732,59 @@ void rcgs_iteration(mswb_vi *vi) {
   MSWB_LAUNCHED();
 }
 
+int coop_launch_supported(mswb_ctx *ctx) {
+  static std::map<int, int> coop;                    // device -> cooperative launches supported
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = coop.find(ctx->device);
+  if (it == coop.end()) {
+    int v = 0;
+    MSWB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, ctx->device));
+    it = coop.emplace(ctx->device, v).first;
+  }
+  return it->second;
+}
+
+// The same for EM / VB on the sparse storage (ems_fused_kernel): passes of up to a few hundred microseconds.
+bool ems_fusable(mswb_vi *vi, int *grid_out, size_t *smem_out) {
+  mswb_lik *L = vi->lik;
+  mswb_ctx *ctx = vi->ctx;
+  const int K = vi->K;
+  if (vi->opts.algo != MSWB_ALGO_EM || L->storage != MSWB_STORE_SPARSE || ctx->world != 1) return false;
+  if (const char *e = getenv("MSWB_FUSED")) if (e[0] == '0') return false;
+  if (!coop_launch_supported(ctx)) return false;
+  const size_t smem = em_sparse_smem_bytes(K);
+  if (smem > 200 * 1024) return false;
+  uint64_t max_bytes = (uint64_t)1 << 30;
+  if (const char *e = getenv("MSWB_FUSED_MAX_MB")) max_bytes = (uint64_t)atoll(e) << 20;
+  if (L->nnz * 12 + L->N * 40 > max_bytes) return false;
+  const int grid = persistent_grid(ctx, ems_fused_kernel, SP_NT, smem, ceil_div(L->N, (uint64_t)SP_NT), grid_cap(vi, K + RED_EXTRA));
+  if (grid_out) *grid_out = grid;
+  if (smem_out) *smem_out = smem;
+  return true;
+}
+bool ems_fused_steps(mswb_vi *vi, uint64_t n) {
+  int grid = 0;
+  size_t smem = 0;
+  if (n == 0 || !ems_fusable(vi, &grid, &smem)) return false;
+  mswb_lik *L = vi->lik;
+  const int K = vi->K;
+  vi->grid = grid;
+  const uint64_t *nz_ptr = L->nz_ptr.p; const uint32_t *nz_grp = L->nz_grp.p; const double *nz_dP = L->nz_dP.p;
+  const double *P0 = L->P0.p, *rowmax = L->rowmax.p, *counts = vi->counts;
+  ViArrays va = vi->arrays; ViCtl *ctl = vi->ctl.p;
+  double *partials = vi->partials.p; int pstride = vi->pstride;
+  unsigned long long N = L->N, nnz = L->nnz, steps = n;
+  int Kk = K; double fx = vi->fx_scale;
+  int coop_reduce = tail_mode(vi, grid, K + RED_EXTRA) == 2 ? 0 : 1;
+  void *args[] = {&nz_ptr, &nz_grp, &nz_dP, &P0, &rowmax, &counts, &va, &ctl, &partials, &pstride, &N, &nnz, &Kk, &fx, &steps, &coop_reduce};
+  PassTimer timer(vi);
+  MSWB_CUDA(cudaLaunchCooperativeKernel((const void *)ems_fused_kernel, dim3(grid), dim3(SP_NT), args, smem, vi->ctx->stream));
+  MSWB_LAUNCHED();
+  timer.stop();
+  return true;
+}
+
 // Small problems on one GPU: up to n iterations in one cooperative launch (rcgs_fused_kernel).  Returns false when the
 // problem is not of that kind (the caller then enqueues the iterations one by one).  MSWB_FUSED=0 turns it off.
 bool rcgs_fusable(mswb_vi *vi, int *grid_out, size_t *smem_out) {
@@ -740,24 +793,15 @@ bool rcgs_fusable(mswb_vi *vi, int *grid_out, size_t *smem_out) {
   const int K = vi->K;
   if (vi->opts.algo != MSWB_ALGO_RCG || L->storage != MSWB_STORE_SPARSE || ctx->world != 1) return false;
   if (const char *e = getenv("MSWB_FUSED")) if (e[0] == '0') return false;
-  static std::map<int, int> coop;                    // device -> cooperative launches supported
-  static std::mutex mu;
-  int can;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    auto it = coop.find(ctx->device);
-    if (it == coop.end()) {
-      int v = 0;
-      MSWB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, ctx->device));
-      it = coop.emplace(ctx->device, v).first;
-    }
-    can = it->second;
-  }
+  const int can = coop_launch_supported(ctx);
   if (!can) return false;
   const size_t smem = std::max(rcgs_sweep_a_smem(K), rcgs_sweep_b_smem(K));
   if (smem > SMEM_BUDGET) return false;
+  // launch latency matters while an iteration's sweeps take up to about a millisecond (64 B per class and per hit, ~2.5 TB/s)
+  uint64_t max_bytes = (uint64_t)5 << 29;
+  if (const char *e = getenv("MSWB_FUSED_MAX_MB")) max_bytes = (uint64_t)atoll(e) << 20;
+  if ((L->nnz + L->N) * 64 > max_bytes) return false;
   const int grid = persistent_grid(ctx, rcgs_fused_kernel, RS_NT, smem, ceil_div(L->N, (uint64_t)RS_NT), grid_cap(vi, K + 2));
-  if (tail_mode(vi, grid, K + 2) != 2) return false;  // only where the last CTA would reduce and take the control step anyway
   if (grid_out) *grid_out = grid;
   if (smem_out) *smem_out = smem;
   return true;
@@ -777,7 +821,9 @@ bool rcgs_fused_steps(mswb_vi *vi, uint64_t n) {
   double *partials = vi->partials.p; int pstride = vi->pstride;
   unsigned long long N = L->N, nnz = L->nnz, steps = n;
   int Kk = K; double l0 = L->l0, fx = vi->fx_scale;
-  void *args[] = {&nz_ptr, &nz_grp, &nz_logl, &counts, &sp_b, &sp_v, &sp_g, &sp_t, &va, &rs, &ctl, &partials, &pstride, &N, &nnz, &Kk, &l0, &fx, &steps};
+  int coop_reduce = tail_mode(vi, grid, K + 2) == 2 ? 0 : 1;      // too many partial vectors for one CTA: every CTA sums its tiles
+  void *args[] = {&nz_ptr, &nz_grp, &nz_logl, &counts, &sp_b, &sp_v, &sp_g, &sp_t, &va, &rs, &ctl, &partials, &pstride, &N, &nnz, &Kk, &l0, &fx, &steps,
+                  &coop_reduce};
   PassTimer timer(vi);
   MSWB_CUDA(cudaLaunchCooperativeKernel((const void *)rcgs_fused_kernel, dim3(grid), dim3(RS_NT), args, smem, ctx->stream));
   MSWB_LAUNCHED();
@@ -974,7 +1020,7 @@ int mswb_vi_step(mswb_vi *vi, uint64_t n_iters) {
   return guarded([&] {
     MSWB_REQUIRE(vi, "vi is NULL");
     MSWB_CUDA(cudaSetDevice(vi->ctx->device));
-    const bool fused = rcgs_fused_steps(vi, n_iters);
+    const bool fused = rcgs_fused_steps(vi, n_iters) || ems_fused_steps(vi, n_iters);
     for (uint64_t i = 0; i < n_iters && !fused; ++i) {
       if (vi->opts.algo == MSWB_ALGO_RCG) { if (vi->lik->storage == MSWB_STORE_SPARSE) rcgs_iteration(vi); else rcg_iteration(vi); }
       else em_iteration(vi);
@@ -1039,7 +1085,7 @@ static int vi_run_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, const
   if (vi_begin_impl(ctx, lik, alpha0, log_counts, counts_dev, counts_dev_sum, opts, &vi)) return 1;
   int rc = guarded([&] {
     // (a fused launch stops by itself once the optimiser is done: nothing is wasted by asking for many iterations at a time)
-    const uint64_t every = opts->poll_every ? opts->poll_every : (rcgs_fusable(vi, nullptr, nullptr) ? 64 : 8);
+    const uint64_t every = opts->poll_every ? opts->poll_every : ((rcgs_fusable(vi, nullptr, nullptr) || ems_fusable(vi, nullptr, nullptr)) ? 64 : 8);
     uint64_t reported = 0;
     std::vector<double> tb, tg;
     for (;;) {

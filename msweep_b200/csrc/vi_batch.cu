@@ -177,7 +177,7 @@ int mswb_vi_run_batch_dev_counts(mswb_ctx *ctx, mswb_lik *lik, const double *alp
         } else {
           MSWB_BATCH_DISPATCH(double, lik->Kp / 2, (launch_batch_pass<double, TL, BT>(r, lik->P64.p, (int)lik->Kp, n_active)));
         }
-        finalize_ctl_batch_kernel<<<dim3(finalize_grid(nvals), n_active), 128, 0, s>>>(r.partials, r.pstride, r.grid_x, nvals, r.base, r.ctls, K,
+        finalize_ctl_batch_kernel<<<dim3(finalize_grid(nvals, 256), n_active), 256, 0, s>>>(r.partials, r.pstride, r.grid_x, nvals, r.base, r.ctls, K,
                                                                                       r.active);
         MSWB_LAUNCHED();
         ++passes;

@@ -319,6 +319,27 @@ __device__ __forceinline__ bool cta_is_last(ViCtl *ctl) {
   return last;
 }
 
+// Grid rendezvous of the fused cooperative kernels (every CTA resident): each CTA takes a ticket; the last one runs
+// `last_does`, resets the ticket and bumps ViCtl.epoch; the others wait for the bump.  Fences on both sides as in cooperative
+// groups' grid.sync(): what a CTA wrote before arriving is visible to every CTA after leaving, plain loads included.
+template <class F>
+__device__ __forceinline__ void grid_rendezvous(ViCtl *ctl, unsigned &epoch, F &&last_does) {
+  if (cta_is_last(ctl)) {
+    last_does();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ctl->ticket = 0;
+      __threadfence();
+      atomicExch(&ctl->epoch, epoch + 1u);
+    }
+  } else if (threadIdx.x == 0) {
+    while (*reinterpret_cast<volatile unsigned *>(&ctl->epoch) != epoch + 1u) {}
+    __threadfence();
+  }
+  __syncthreads();
+  epoch += 1u;
+}
+
 // red[v] = sum over CTAs of partials[cta][v], v < nvals, CTAs in ascending order (whoever runs this: same bits).
 __device__ __forceinline__ void reduce_partials(const double *partials, int pstride, int n_ctas, int nvals, double *red,
                                                 int v_begin, int v_stride) {
@@ -348,35 +369,39 @@ __device__ __forceinline__ void reduce_partials_cta(const double *partials, int 
   }
 }
 
-// The same sum spread over a GRID (finalize kernels: many CTAs x many columns): a CTA owns tiles of 32 columns, warp w
-// adds the partial vectors w, w + NT/32, ... in ascending order — 256-byte coalesced rows, eight independent loads in flight
-// per lane instead of one chain over all CTAs — and warp 0 adds the warps' sums in warp order.  Fixed order for a given
-// (NT, n_ctas): run-to-run reproducible.  s_tile: NT doubles of shared memory.
+// The same sum spread over a GRID (finalize kernels, the fused cooperative kernels: many CTAs x many columns).  A tile is 32
+// columns; EIGHT warps share a tile: warp w adds the partial vectors w, w + 8, ... in ascending order — 256-byte coalesced
+// rows, eight independent loads in flight per lane instead of one chain over all CTAs — and the eight sums are added in warp
+// order.  A CTA of NT threads works on NT / 256 tiles at a time.  The order depends on n_ctas only (not on NT, not on the
+// grid that runs it): run-to-run reproducible, and the same bits from the finalize kernels (1024 threads) and from the
+// fused kernels (256 threads).  s_tile: NT doubles of shared memory.
 template <int NT>
 __device__ __forceinline__ void reduce_partials_tiled(const double *partials, int pstride, int n_ctas, int nvals, double *red,
                                                       double *s_tile) {
-  constexpr int NWARP = NT / 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int v0 = (int)blockIdx.x * 32; v0 < nvals; v0 += (int)gridDim.x * 32) {
-    const int v = v0 + lane;
+  static_assert(NT % 256 == 0, "eight warps per tile");
+  constexpr int GROUPS = NT / 256;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7, group = threadIdx.x >> 8;
+  double *tile = s_tile + group * 256;
+  for (int v0 = ((int)blockIdx.x * GROUPS) * 32; v0 < nvals; v0 += (int)gridDim.x * GROUPS * 32) {
+    const int v = v0 + group * 32 + lane;
     double a = 0.0;
     if (v < nvals) {
       const double *p = partials + v;
 #pragma unroll 8
-      for (int c = warp; c < n_ctas; c += NWARP) a += __ldcg(p + (size_t)c * pstride);
+      for (int c = warp; c < n_ctas; c += 8) a += __ldcg(p + (size_t)c * pstride);
     }
     __syncthreads();
-    s_tile[warp * 32 + lane] = a;
+    tile[warp * 32 + lane] = a;
     __syncthreads();
     if (warp == 0 && v < nvals) {
       double t = 0.0;
 #pragma unroll
-      for (int w = 0; w < NWARP; ++w) t += s_tile[w * 32 + lane];
+      for (int w = 0; w < 8; ++w) t += tile[w * 32 + lane];
       red[v] = t;
     }
   }
 }
-inline int finalize_grid(int nvals) { return (nvals + 31) / 32; }
+inline int finalize_grid(int nvals, int nt) { return (nvals + 32 * (nt / 256) - 1) / (32 * (nt / 256)); }
 
 __device__ __forceinline__ void trace_push(const ViArrays &a, ViCtl *ctl, double gnorm, int reset) {
   if (ctl->iter < a.trace_cap) {
@@ -879,20 +904,20 @@ em_lin_batch_kernel(const ST *__restrict__ P, int ld, const double *__restrict__
 
 // Reduction + control step of the batched pass: gridDim.y = active replicates, the last CTA of a replicate's row
 // of CTAs takes its control step.
-static __global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(256)
 finalize_ctl_batch_kernel(const double *partials, int pstride, int n_ctas, int nvals, ViArrays base, ViCtl *ctls, int K,
                           const int *__restrict__ active) {
   const int slot = blockIdx.y, rep = active[slot];
   ViCtl *ctl = ctls + rep;
   if (ctl->done) return;
   __shared__ double s_blk[32];
-  __shared__ double s_tile[128];
+  __shared__ double s_tile[256];
   const ViArrays a = arrays_of_replicate(base, rep, K, pstride);
-  reduce_partials_tiled<128>(partials + (size_t)slot * n_ctas * pstride, pstride, n_ctas, nvals, a.red, s_tile);
+  reduce_partials_tiled<256>(partials + (size_t)slot * n_ctas * pstride, pstride, n_ctas, nvals, a.red, s_tile);
   if (!cta_is_last(ctl)) return;
   if (threadIdx.x == 0) ctl->ticket = 0;
   __syncthreads();
-  em_ctl_step<128>(a, ctl, K, 0, s_blk);
+  em_ctl_step<256>(a, ctl, K, 0, s_blk);
 }
 
 // =====================================================================================================
@@ -1302,20 +1327,18 @@ __device__ __forceinline__ void fx_atomic_add(unsigned *acc2 /* [lo, hi] */, lon
 // A warp walks a CONTIGUOUS run of chunks, so the hits of its next chunk start where those of the current one end:
 // while the arithmetic of chunk i runs, the per-class values of chunk i + 1 and the first SP_PF x 32 hits behind the
 // current range are already in flight (the pass is bound by load latency, not by instructions).
-template <bool TAIL>
-__global__ void __launch_bounds__(SP_NT, 3)
-em_sparse_pass_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_dP,
-                      const double *__restrict__ P0, const double *__restrict__ rowmax, const double *__restrict__ counts,
-                      ViArrays arrays, ViCtl *ctl, double *partials, int pstride,
-                      unsigned long long N, unsigned long long nnz, int K, double fx_scale, int tail) {
-  if (ctl->done) return;
+// (the body is shared with ems_fused_kernel; it ends with the CTA's partial vector stored)
+__device__ __forceinline__ void
+em_sparse_pass_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_dP,
+                    const double *__restrict__ P0, const double *__restrict__ rowmax, const double *__restrict__ counts,
+                    const ViArrays &arrays, double *partials, int pstride,
+                    unsigned long long N, unsigned long long nnz, int K, double fx_scale, double *s_blk) {
   extern __shared__ __align__(16) unsigned char s_dyn_sp[];
   double *s_w = reinterpret_cast<double *>(s_dyn_sp);                         // [K]
   unsigned *s_acc = reinterpret_cast<unsigned *>(s_w + K);                    // [K][2] fixed-point accumulators
   double *s_val = reinterpret_cast<double *>(s_acc + 2 * (size_t)K);          // [warps][SP_STAGE] dP * w of the parked hits
   double *s_r = s_val + (SP_NT / 32) * SP_STAGE;                              // [warps][32] c_j / S_j of the chunk
   uint32_t *s_key = reinterpret_cast<uint32_t *>(s_r + (SP_NT / 32) * 32);    // [warps][SP_STAGE] packed (class, group)
-  __shared__ double s_blk[32];
   const double *w = arrays.w;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double wsum = 0.0;
@@ -1441,7 +1464,47 @@ em_sparse_pass_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__res
   elbo = block_sum<SP_NT>(elbo, s_blk);
   const int any_fault = __syncthreads_or(fault);
   if (threadIdx.x == 0) { out[K + RED_BOUND] = elbo; out[K + RED_AUX] = z; out[K + RED_FAULT] = any_fault ? 1.0 : 0.0; }
+}
+template <bool TAIL>
+__global__ void __launch_bounds__(SP_NT, 3)
+em_sparse_pass_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_dP,
+                      const double *__restrict__ P0, const double *__restrict__ rowmax, const double *__restrict__ counts,
+                      ViArrays arrays, ViCtl *ctl, double *partials, int pstride,
+                      unsigned long long N, unsigned long long nnz, int K, double fx_scale, int tail) {
+  if (ctl->done) return;
+  __shared__ double s_blk[32];
+  em_sparse_pass_body(nz_ptr, nz_grp, nz_dP, P0, rowmax, counts, arrays, partials, pstride, N, nnz, K, fx_scale, s_blk);
   if constexpr (TAIL) em_sweep_tail<SP_NT>(tail, 1, arrays, ctl, partials, pstride, K, s_blk);
+}
+// Up to n_steps EM / VB iterations on the sparse storage in ONE cooperative launch (every CTA resident; one GPU): pass, grid
+// rendezvous, reduction of the partial vectors (by the last arrival, or — coop_reduce — by every CTA on its tiles of columns
+// followed by a second rendezvous), control step by the last arrival.  While a pass takes tens of microseconds (config 2 /
+// 5: 33 us) the launches, their drains and a separate reduction kernel are a third of the iteration.  Same passes and the same
+// order over the partial vectors as the launch-per-pass path; the control step's K-sized sums run over SP_NT instead of
+// FIN_NT threads, so the two paths agree to the last digits of the bound (tests/test_gpu_scale.py).
+static __global__ void __launch_bounds__(SP_NT, 3)
+ems_fused_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_dP,
+                 const double *__restrict__ P0, const double *__restrict__ rowmax, const double *__restrict__ counts,
+                 ViArrays arrays, ViCtl *ctl, double *partials, int pstride,
+                 unsigned long long N, unsigned long long nnz, int K, double fx_scale, unsigned long long n_steps, int coop_reduce) {
+  __shared__ double s_blk[32];
+  __shared__ double s_tile[SP_NT];
+  unsigned epoch = *reinterpret_cast<volatile unsigned *>(&ctl->epoch);
+  for (unsigned long long it = 0; it < n_steps; ++it) {
+    if (*reinterpret_cast<volatile int *>(&ctl->done)) break;          // (the same value in every CTA: read between rendezvous)
+    em_sparse_pass_body(nz_ptr, nz_grp, nz_dP, P0, rowmax, counts, arrays, partials, pstride, N, nnz, K, fx_scale, s_blk);
+    if (coop_reduce) {
+      grid_rendezvous(ctl, epoch, [] {});
+      reduce_partials_tiled<SP_NT>(partials, pstride, (int)gridDim.x, K + RED_EXTRA, arrays.red, s_tile);
+      grid_rendezvous(ctl, epoch, [&] { em_ctl_step<SP_NT>(arrays, ctl, K, 1, s_blk); });
+    } else {
+      grid_rendezvous(ctl, epoch, [&] {
+        reduce_partials_cta<SP_NT>(partials, pstride, (int)gridDim.x, K + RED_EXTRA, arrays.red, arrays.seg);
+        __syncthreads();
+        em_ctl_step<SP_NT>(arrays, ctl, K, 1, s_blk);
+      });
+    }
+  }
 }
 inline size_t em_sparse_smem_bytes(int K) {
   return (size_t)K * 16 + (size_t)(SP_NT / 32) * SP_STAGE * (8 + 4) + (size_t)(SP_NT / 32) * 32 * 8;
@@ -1450,7 +1513,7 @@ inline size_t em_sparse_smem_bytes(int K) {
 // ---- separate reduction (+ control) kernel: large grids x many groups ---------------------------------
 // red[v] = sum over CTAs of partials[cta][v], fixed order; v < nvals.  ctl_mode: -1 none (several GPUs: the all-reduce
 // and a control kernel follow), else the last CTA takes the control step (0 EM dense, 1 EM sparse, 2 RCG stage 0).
-constexpr int FIN_NT = 256;
+constexpr int FIN_NT = 1024;   // the control step behind the reduction is K-sized lgamma / digamma / exp work in ONE CTA: 1024 threads take it from ~13 to ~4 us at K = 2000
 // peer != 0 (several GPUs with peer memory, peer.cuh): the last CTA also exchanges the reduced vector with the other ranks
 // and takes the control step — pass + this kernel are the whole iteration, as on one GPU.
 static __global__ void __launch_bounds__(FIN_NT)

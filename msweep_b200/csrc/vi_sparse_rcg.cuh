@@ -542,52 +542,41 @@ rcgs_sweep_b_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restr
 // When an iteration takes tens of microseconds, three launches and their drains are most of it.  rcgs_fused_kernel is a
 // cooperative launch (every CTA resident) that runs up to `n_steps` iterations: sweep A, a grid rendezvous whose last
 // arrival sums the norms, sweep B, a rendezvous whose last arrival reduces the partial vectors and takes the control step,
-// and the restart sweep when that step was rejected.  One GPU only (no collective inside a kernel).
-// The rendezvous: every CTA takes a ticket; the last one runs `last_does`, resets the ticket and bumps ViCtl.epoch; the
-// others wait for the bump.  Fences on both sides as in cooperative groups' grid.sync(): what a CTA wrote before arriving
-// is visible to every CTA after leaving, plain loads included.
-template <class F>
-__device__ __forceinline__ void grid_rendezvous(ViCtl *ctl, unsigned &epoch, F &&last_does) {
-  if (cta_is_last(ctl)) {
-    last_does();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      ctl->ticket = 0;
-      __threadfence();
-      atomicExch(&ctl->epoch, epoch + 1u);
-    }
-  } else if (threadIdx.x == 0) {
-    while (*reinterpret_cast<volatile unsigned *>(&ctl->epoch) != epoch + 1u) {}
-    __threadfence();
-  }
-  __syncthreads();
-  epoch += 1u;
-}
-
+// and the restart sweep when that step was rejected.  One GPU only.  Used up to ~1 ms of sweeps per iteration (config 2 / 5:
+// 0.17 ms of sweeps, 0.25 ms per iteration as four launches).
+// (grid_rendezvous: vi_kernels.cuh.)
+// coop_reduce: the partial vectors are too many for one CTA (grid x columns > tail_max): after a rendezvous EVERY CTA sums
+// its tiles of columns (reduce_partials_tiled), and the last arrival of a second rendezvous takes the control step.
 static __global__ void __launch_bounds__(RS_NT, 2)
 rcgs_fused_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_logl,
                   const double *__restrict__ counts, double *sp_b, double *sp_v, double *sp_g, double *sp_t, ViArrays va, RcgsGroup grp,
                   ViCtl *ctl, double *partials, int pstride, unsigned long long N, unsigned long long nnz, int K, double l0,
-                  double fx_scale, unsigned long long n_steps) {
+                  double fx_scale, unsigned long long n_steps, int coop_reduce) {
   __shared__ double s_tail[32];
+  __shared__ double s_tile[RS_NT];
   unsigned epoch = *reinterpret_cast<volatile unsigned *>(&ctl->epoch);
+  auto reduce_and_control = [&](int stage) {
+    if (coop_reduce) {
+      grid_rendezvous(ctl, epoch, [] {});
+      reduce_partials_tiled<RS_NT>(partials, pstride, (int)gridDim.x, K + 2, va.red, s_tile);
+      grid_rendezvous(ctl, epoch, [&] { rcgs_ctl_b_step<RS_NT>(va, grp, ctl, K, stage, 0, s_tail); });
+    } else {
+      grid_rendezvous(ctl, epoch, [&] {
+        reduce_partials_cta<RS_NT>(partials, pstride, (int)gridDim.x, K + 2, va.red, va.seg);
+        __syncthreads();
+        rcgs_ctl_b_step<RS_NT>(va, grp, ctl, K, stage, 0, s_tail);
+      });
+    }
+  };
   for (unsigned long long it = 0; it < n_steps; ++it) {
     if (*reinterpret_cast<volatile int *>(&ctl->done)) break;          // (the same value in every CTA: read between rendezvous)
     rcgs_sweep_a_body(nz_ptr, nz_grp, nz_logl, sp_b, sp_g, va, grp, partials, pstride, N, nnz, K, l0);
     grid_rendezvous(ctl, epoch, [&] { rcgs_sum_norms(partials, pstride, va, K); });
     rcgs_sweep_b_body<0>(nz_ptr, nz_grp, nz_logl, counts, sp_b, sp_v, sp_g, sp_t, va, grp, ctl, partials, pstride, N, nnz, K, l0, fx_scale);
-    grid_rendezvous(ctl, epoch, [&] {
-      reduce_partials_cta<RS_NT>(partials, pstride, (int)gridDim.x, K + 2, va.red, va.seg);
-      __syncthreads();
-      rcgs_ctl_b_step<RS_NT>(va, grp, ctl, K, 0, 0, s_tail);
-    });
+    reduce_and_control(0);
     if (*reinterpret_cast<volatile int *>(&ctl->didreset)) {
       rcgs_sweep_b_body<1>(nz_ptr, nz_grp, nz_logl, counts, sp_b, sp_v, sp_g, sp_t, va, grp, ctl, partials, pstride, N, nnz, K, l0, fx_scale);
-      grid_rendezvous(ctl, epoch, [&] {
-        reduce_partials_cta<RS_NT>(partials, pstride, (int)gridDim.x, K + 2, va.red, va.seg);
-        __syncthreads();
-        rcgs_ctl_b_step<RS_NT>(va, grp, ctl, K, 1, 0, s_tail);
-      });
+      reduce_and_control(1);
     }
   }
 }

@@ -119,3 +119,29 @@ def test_sparse_storage_at_scale(big, mswb, ctx):
     assert np.max(np.abs(np.exp(g_d) - np.exp(g_s))) < (1e-7 if conv_d.iters == conv_s.iters else 1e-5)
     em_d, em_s = dense.vi_run(mswb.ALGO_EM, tol=0.0, max_iters=50), sparse.vi_run(mswb.ALGO_EM, tol=0.0, max_iters=50)
     assert np.max(np.abs(em_d.theta - em_s.theta)) < 1e-11 and abs(em_d.bound - em_s.bound) < 1e-12 * abs(em_d.bound)
+
+
+@pytest.mark.parametrize("algo_name", ["rcg", "em"])
+def test_fused_iterations_at_scale_equal_the_launch_per_sweep_path(big, mswb, ctx, monkeypatch, algo_name):
+    """~1e6 classes x 1000 groups (config 2 / 5 size): whole iterations inside one cooperative launch (rcgs_fused_kernel /
+    ems_fused_kernel with the partial vectors reduced by every CTA on its tiles of columns between two grid rendezvous)
+    against one launch per sweep + reduction kernel.  Same sweeps, same order over the partial vectors; the K-sized sums of
+    the control step (lgamma terms of the bound) run over 256 instead of 1024 threads, so the trajectories agree to the last
+    digits of the bound rather than bit for bit."""
+    wl, aln = big
+    sparse = mswb.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=mswb.STORE_SPARSE)
+    algo = mswb.ALGO_RCG if algo_name == "rcg" else mswb.ALGO_EM
+    runs = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("MSWB_FUSED", fused)
+        n0 = mswb.launch_count()
+        s = sparse.vi_begin(algo, tol=-1e300 if algo_name == "rcg" else 0.0, max_iters=40)
+        s.step(25); s.poll(); s.step(15)
+        tb, tg, tr = s.trace()
+        runs[fused] = (tb, tg, tr, s.finish(), mswb.launch_count() - n0)
+    (tb0, tg0, tr0, r0, n_launch), (tb1, tg1, tr1, r1, n_fused) = runs["0"], runs["1"]
+    assert r0.iters == r1.iters == 40 and r0.resets == r1.resets and np.array_equal(tr0, tr1)
+    assert np.max(np.abs(tb0 - tb1) / np.abs(tb0)) < 1e-13
+    assert np.allclose(tg0, tg1, rtol=1e-9, atol=1e-12 * max(1.0, float(np.max(np.abs(tg0)))))
+    assert np.max(np.abs(r0.theta - r1.theta)) < 1e-12 and abs(r0.bound - r1.bound) < 1e-13 * abs(r0.bound)
+    assert n_fused < n_launch / 5, (n_fused, n_launch)

@@ -62,4 +62,22 @@ for K, T, R in ((6, 60, 500), (300, 1200, 700), (1100, 3300, 300)):
         assert np.all(np.abs(th.sum(axis=1) - 1) < 1e-6)
         lik.close()
     aln.close()
+# segment-parallel std::mt19937_64 (mt64_chain_kernel + mt64_segments_kernel), the fused cooperative kernels with the partial
+# vectors reduced by every CTA between two grid rendezvous (MSWB_TAIL_MAX=0 forces that path), and the tiled finalize kernels
+wl = synth.generate(3000, 300, 12, n_present=3, n_templates=200, p_noise=0.05, seed=9)
+aln = M.Alignment(ctx, wl.n_reads, wl.n_targets, wl.row_ptr, wl.targets)
+lik = M.Likelihood.build(ctx, aln, wl.group_of_target, wl.group_sizes, storage=M.STORE_SPARSE)
+os.environ["MSWB_MT_SEGMENTS"] = "4"
+lik.bootstrap_resample(5, 3); lik.bootstrap_resample(5, 2, bootstrap_count=1000)
+lik.bootstrap_run(2, seed=3, max_iters=4)
+os.environ.pop("MSWB_MT_SEGMENTS")
+os.environ["MSWB_TAIL_MAX"] = "0"
+for fused in ("1", "0"):
+    os.environ["MSWB_FUSED"] = fused
+    r = lik.vi_run(M.ALGO_EM, max_iters=6, tol=0.0)
+    assert abs(r.theta.sum() - 1) < 1e-9
+    r = lik.vi_run(M.ALGO_RCG, max_iters=6, tol=-1e300)
+    assert abs(r.theta.sum() - 1) < 1e-9
+os.environ.pop("MSWB_FUSED"); os.environ.pop("MSWB_TAIL_MAX")
+lik.close(); aln.close()
 print("sanitize run ok, launches:", M.launch_count())
