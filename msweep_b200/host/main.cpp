@@ -233,6 +233,7 @@ int main(int argc, char *argv[]) {
   // ---- algorithm selection (src/mSWEEP.cpp:127, 192-203; unknown strings are refused, not run as EM) ---
   b200::ViOptions vi;
   int storage = MSWB_STORE_F64;
+  bool sparse_if_pruned = false;   // auto mode, more than 4096 groups: --min-hits may leave few enough (config 4: 10,000 -> ~100)
   try {
     const std::string algo = args.str("algorithm", "rcgb200");
     if (algo == "rcgb200" || algo == "rcggpu") vi.algo = MSWB_ALGO_RCG;
@@ -247,6 +248,7 @@ int main(int argc, char *argv[]) {
     const std::string store = args.str("storage", "auto");
     // (the sparse sweeps keep their K-vectors in shared memory: up to 4096 groups; wider groupings stay dense in auto mode)
     if (store == "sparse" || (store == "auto" && storage == MSWB_STORE_F64 && grouping.sizes.size() <= 4096)) storage = MSWB_STORE_SPARSE;
+    else if (store == "auto" && storage == MSWB_STORE_F64) sparse_if_pruned = true;
     else if (store != "dense" && store != "auto") throw std::runtime_error("Unknown --storage `" + store + "` (one of auto, dense, sparse)");
     if (store == "sparse" && args.str("emprecision", "double") == "float" && vi.algo == MSWB_ALGO_EM)
       throw std::runtime_error("--storage sparse is an fp64 form; drop --emprecision float");
@@ -419,7 +421,16 @@ int main(int argc, char *argv[]) {
       if (gpu == 0) { t_ec = tm.lap(); log("Computing the likelihood matrix"); }
       if (const char *inj = std::getenv("MSWB_TEST_FAIL_GPU"))   // fault injection for the abort path (tests only)
         if (std::atoi(inj) == gpu) throw std::runtime_error("injected failure on GPU " + std::to_string(gpu));
-      b200::Likelihood ll(ctx, aln, grouping.group_of_target, grouping.sizes, q, e_disp, min_hits, zi, storage);
+      // (a wide grouping that --min-hits prunes to <= 4096 groups takes the sparse form after all: the mask is global —
+      //  all-reduced tallies — so every GPU takes the same decision)
+      const bool try_sparse = sparse_if_pruned && min_hits > 0;
+      std::unique_ptr<b200::Likelihood> ll_holder(new b200::Likelihood(ctx, aln, grouping.group_of_target, grouping.sizes, q, e_disp, min_hits, zi,
+                                                                       try_sparse ? MSWB_STORE_SPARSE : storage));
+      if (try_sparse && ll_holder->get_rows() > 4096) {
+        ll_holder.reset();
+        ll_holder.reset(new b200::Likelihood(ctx, aln, grouping.group_of_target, grouping.sizes, q, e_disp, min_hits, zi, storage));
+      }
+      b200::Likelihood &ll = *ll_holder;
       const std::vector<bool> my_mask = ll.groups_considered();
       if (gpu == 0) { mask = my_mask; t_lik = tm.lap(); }
       if (args.has("no-fit-model")) { failed_stage[gpu] = 0; return; }

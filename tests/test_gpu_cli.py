@@ -104,6 +104,23 @@ def test_min_hits_orders_pruned_groups_last(data):
     assert n_zero > 0 and np.all(vals[-n_zero:, 0] == 0) and np.all(vals[:-n_zero, 0] > 0)   # src/PlainSample.cpp:56-66
 
 
+def test_wide_grouping_pruned_by_min_hits_takes_the_sparse_form(tmp_path):
+    """Config 4's shape in small: more groups than the sparse sweeps hold in shared memory (> 4096), nearly all of them
+    empty.  --storage auto builds the sparse form once --min-hits has pruned the grouping; the abundances equal the dense
+    form's and the oracle's, and without --min-hits the same input stays dense (and still runs)."""
+    wl = synth.generate(6000, 10000, 5000, n_present=4, n_templates=100, p_noise=0.0, seed=41)
+    paths = synth.write_themisto(str(tmp_path / "aln"), wl, paired=True)
+    g = str(tmp_path / "grouping.txt")
+    synth.write_grouping(g, wl)
+    (h, names, v_auto), (h2, names2, v_ref), _ = run_both(tmp_path, paths, g, ["--min-hits", "1"], "wide_auto")
+    (_, names_d, v_dense), _, _ = run_both(tmp_path, paths, g, ["--min-hits", "1", "--storage", "dense"], "wide_dense")
+    assert names == names2 == names_d and h[1:] == h2[1:]
+    assert np.max(np.abs(v_auto - v_ref)) < 2e-6 and np.max(np.abs(v_auto - v_dense)) < 2e-6
+    r = subprocess.run([CLI, "--themisto-1", paths[0], "--themisto-2", paths[1], "-i", g, "-o", str(tmp_path / "wide_nomh"), "-t", "4"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_bootstrap_output(data):
     d, wl, paths, g = data
     (h, names, vals), (h2, names2, vals2), _ = run_both(d, paths, g, ["--iters", "3", "--seed", "11"], "boot")
