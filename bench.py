@@ -563,7 +563,7 @@ def extra_sparse(a, torch, M, dist, ctx, stream, rank, world, wl_main, peak):
                 "value_ec_iter_per_s": n_job * steps / (s["ms_total"] * 1e-3),
                 "roofline": {"bound": "hbm", "kernel": "em_sparse_pass_kernel", "achieved": out["achieved_gbs"], "peak": peak, "unit": "GB/s",
                              "frac": out["achieved_gbs"] / peak, "bytes_per_launch": out["bytes_per_step"],
-                             "note": "its own algorithmic bytes: 12 B per (class, group) hit + 40 B per class; the dense fp32 form of the same job reads 800 GB per pass"},
+                             "note": "its own algorithmic bytes: 12 B per (class, group) hit + 32 B per class; the dense fp32 form of the same job reads 800 GB per pass"},
                 "e2e": {"seconds": round(sec, 4), "vi_iters_per_s": steps / sec, "value_ec_iter_per_s": n_job * steps / sec,
                         "what": f"mswb_ec_build + mswb_lik_build(sparse) + {steps} iterations from host CSR buffers, theta back on the host",
                         "h2d_bytes": int(wl.row_ptr.nbytes + wl.targets.nbytes)},

@@ -105,6 +105,13 @@ __global__ void counts_from_log_kernel(const double *lc, double *c, size_t n, do
   acc = block_sum<256>(acc, scratch);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = acc;
 }
+__global__ void dot_kernel(const double *a, const double *b, size_t n, double *block_sums) {
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc = fma(a[i], b[i], acc);
+  acc = block_sum<256>(acc, scratch);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = acc;
+}
 __global__ void sum_kernel(const double *c, size_t n, double *block_sums) {
   __shared__ double scratch[32];
   double acc = 0.0;
@@ -254,6 +261,7 @@ struct mswb_vi {
   int K = 0;
   DevBuf<ViCtl> ctl;
   DevBuf<double> alpha0, N_k, dg, dg_prev, w, red, seg, partials, trace_bound, trace_gnorm, own_counts, block_sums;
+  DevBuf<double> cm_const;          // sparse EM: sum_j c_j M_j of this rank's classes (the part of the bound no pass changes)
   DevBuf<unsigned char> trace_reset;
   const double *counts = nullptr;   // device, [N]
   double sum_counts = 0.0;
@@ -591,7 +599,7 @@ void em_iteration(mswb_vi *vi) {
     tail = tail_mode(vi, vi->grid, nvals);
     auto kern = tail ? em_sparse_pass_kernel<true> : em_sparse_pass_kernel<false>;
     if (tail) ensure_dyn_smem(kern, ctx->device, smem);
-    kern<<<vi->grid, SP_NT, smem, s>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_dP.p, L->P0.p, L->rowmax.p, vi->counts,
+    kern<<<vi->grid, SP_NT, smem, s>>>(L->nz_ptr.p, L->nz_grp.p, L->nz_dP.p, L->P0.p, vi->cm_const.p, vi->counts,
                                       vi->arrays, vi->ctl.p, vi->partials.p, vi->pstride, L->N, L->nnz, K, vi->fx_scale, tail);
     MSWB_LAUNCHED();
   } else if (L->storage == MSWB_STORE_F32) {
@@ -757,7 +765,7 @@ bool ems_fusable(mswb_vi *vi, int *grid_out, size_t *smem_out) {
   if (smem > 200 * 1024) return false;
   uint64_t max_bytes = (uint64_t)1 << 30;
   if (const char *e = getenv("MSWB_FUSED_MAX_MB")) max_bytes = (uint64_t)atoll(e) << 20;
-  if (L->nnz * 12 + L->N * 40 > max_bytes) return false;
+  if (L->nnz * 12 + L->N * 32 > max_bytes) return false;
   const int grid = persistent_grid(ctx, ems_fused_kernel, SP_NT, smem, ceil_div(L->N, (uint64_t)SP_NT), grid_cap(vi, K + RED_EXTRA));
   if (grid_out) *grid_out = grid;
   if (smem_out) *smem_out = smem;
@@ -771,7 +779,7 @@ bool ems_fused_steps(mswb_vi *vi, uint64_t n) {
   const int K = vi->K;
   vi->grid = grid;
   const uint64_t *nz_ptr = L->nz_ptr.p; const uint32_t *nz_grp = L->nz_grp.p; const double *nz_dP = L->nz_dP.p;
-  const double *P0 = L->P0.p, *rowmax = L->rowmax.p, *counts = vi->counts;
+  const double *P0 = L->P0.p, *rowmax = vi->cm_const.p /* sum_j c_j M_j */, *counts = vi->counts;
   ViArrays va = vi->arrays; ViCtl *ctl = vi->ctl.p;
   double *partials = vi->partials.p; int pstride = vi->pstride;
   unsigned long long N = L->N, nnz = L->nnz, steps = n;
@@ -937,7 +945,7 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
     } else {
       if (lik->storage == MSWB_STORE_SPARSE) {
         lik_ensure_sparse(lik);
-        vi->pass_bytes = lik->nnz * 12 + (uint64_t)lik->N * 40;              // hits (group + value), ptr, P0, M_j, c_j
+        vi->pass_bytes = lik->nnz * 12 + (uint64_t)lik->N * 32;              // hits (group + value); per class two ptr words, P0, c_j (M_j enters through a constant)
       } else {
         lik_ensure_linear(lik);
         const uint64_t bl = lik->storage == MSWB_STORE_F32 ? 4 : 8;
@@ -984,6 +992,19 @@ static int vi_begin_impl(mswb_ctx *ctx, mswb_lik *lik, const double *alpha0, con
     } else {
       vi->counts = lik->counts.p;
       vi->sum_counts = lik->sum_counts_total;
+    }
+
+    if (opts->algo == MSWB_ALGO_EM && lik->storage == MSWB_STORE_SPARSE) {
+      // sum_j c_j M_j: the row maxima enter the bound through this constant only, so the pass does not read them
+      const int nb = 296;
+      DevBuf<double> parts;
+      parts.alloc(nb);
+      vi->cm_const.alloc(1);
+      dot_kernel<<<nb, 256, 0, s>>>(vi->counts, lik->rowmax.p, lik->N, parts.p);
+      MSWB_LAUNCHED();
+      sum_blocks_kernel<<<1, 256, 0, s>>>(parts.p, nb, vi->cm_const.p);
+      MSWB_LAUNCHED();
+      MSWB_CUDA(cudaStreamSynchronize(s));      // (parts goes out of scope)
     }
 
     // bound constant: lgamma(sum alpha0) - lgamma(sum alpha0 + sum c) - sum lgamma(alpha0)

@@ -1330,7 +1330,7 @@ __device__ __forceinline__ void fx_atomic_add(unsigned *acc2 /* [lo, hi] */, lon
 // (the body is shared with ems_fused_kernel; it ends with the CTA's partial vector stored)
 __device__ __forceinline__ void
 em_sparse_pass_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_dP,
-                    const double *__restrict__ P0, const double *__restrict__ rowmax, const double *__restrict__ counts,
+                    const double *__restrict__ P0, const double *__restrict__ cm_const, const double *__restrict__ counts,
                     const ViArrays &arrays, double *partials, int pstride,
                     unsigned long long N, unsigned long long nnz, int K, double fx_scale, double *s_blk) {
   extern __shared__ __align__(16) unsigned char s_dyn_sp[];
@@ -1357,14 +1357,14 @@ em_sparse_pass_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restr
   const unsigned long long ch_end = min(n_chunks, ch_begin + per);
   const unsigned long long last_hit = nnz ? nnz - 1 : 0;
 
-  struct ClassData { unsigned long long a, b; double c, p0, m; };
+  struct ClassData { unsigned long long a, b; double c, p0; };
   auto load_class = [&](unsigned long long ch) {
     // everything the classes of a chunk need, requested together (coalesced: consecutive lanes, consecutive classes)
     const unsigned long long j = ch * SP_CHUNK + lane;
     const bool have = j < N;
     ClassData d;
     d.a = nz_ptr[have ? j : N]; d.b = nz_ptr[have ? j + 1 : N];
-    d.c = have ? counts[j] : 0.0; d.p0 = have ? P0[j] : 0.0; d.m = have ? rowmax[j] : 0.0;
+    d.c = have ? counts[j] : 0.0; d.p0 = have ? P0[j] : 0.0;
     return d;
   };
   uint32_t pg[SP_PF];
@@ -1384,7 +1384,7 @@ em_sparse_pass_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restr
       else {
         r = d.c / s;
         z = fma(r, d.p0, z);
-        elbo = fma(d.c, log(s) + d.m, elbo);
+        elbo = fma(d.c, log(s), elbo);          // (+ c_j M_j: the same in every pass — cm_const, added once below)
       }
     }
     __syncwarp();
@@ -1425,7 +1425,12 @@ em_sparse_pass_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restr
         load_hits(h1);
         __syncwarp();
         // class-parallel: lane l adds the parked hits of class l in list order
-        for (int x = (int)(cur.a - h0), xe = (int)(cur.b - h0); x < xe; ++x) s += val[x];
+        {
+          const int xa = (int)(cur.a - h0), xe = (int)(cur.b - h0);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) if (xa + u < xe) s += val[xa + u];      // (a class has a handful of hits: no loop for most lanes)
+          for (int x = xa + 4; x < xe; ++x) s += val[x];
+        }
         normalise(cur, s);
         scatter(n_here);
       } else {
@@ -1463,17 +1468,18 @@ em_sparse_pass_body(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restr
   z = block_sum<SP_NT>(z, s_blk);
   elbo = block_sum<SP_NT>(elbo, s_blk);
   const int any_fault = __syncthreads_or(fault);
-  if (threadIdx.x == 0) { out[K + RED_BOUND] = elbo; out[K + RED_AUX] = z; out[K + RED_FAULT] = any_fault ? 1.0 : 0.0; }
+  // cm_const[0] = sum_j c_j M_j over this rank's classes (vi.cu: once per run; M_j = the row maximum the stored values are relative to)
+  if (threadIdx.x == 0) { out[K + RED_BOUND] = blockIdx.x == 0 ? elbo + cm_const[0] : elbo; out[K + RED_AUX] = z; out[K + RED_FAULT] = any_fault ? 1.0 : 0.0; }
 }
 template <bool TAIL>
 __global__ void __launch_bounds__(SP_NT, 3)
 em_sparse_pass_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_dP,
-                      const double *__restrict__ P0, const double *__restrict__ rowmax, const double *__restrict__ counts,
+                      const double *__restrict__ P0, const double *__restrict__ cm_const, const double *__restrict__ counts,
                       ViArrays arrays, ViCtl *ctl, double *partials, int pstride,
                       unsigned long long N, unsigned long long nnz, int K, double fx_scale, int tail) {
   if (ctl->done) return;
   __shared__ double s_blk[32];
-  em_sparse_pass_body(nz_ptr, nz_grp, nz_dP, P0, rowmax, counts, arrays, partials, pstride, N, nnz, K, fx_scale, s_blk);
+  em_sparse_pass_body(nz_ptr, nz_grp, nz_dP, P0, cm_const, counts, arrays, partials, pstride, N, nnz, K, fx_scale, s_blk);
   if constexpr (TAIL) em_sweep_tail<SP_NT>(tail, 1, arrays, ctl, partials, pstride, K, s_blk);
 }
 // Up to n_steps EM / VB iterations on the sparse storage in ONE cooperative launch (every CTA resident; one GPU): pass, grid
@@ -1484,7 +1490,7 @@ em_sparse_pass_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__res
 // FIN_NT threads, so the two paths agree to the last digits of the bound (tests/test_gpu_scale.py).
 static __global__ void __launch_bounds__(SP_NT, 3)
 ems_fused_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict__ nz_grp, const double *__restrict__ nz_dP,
-                 const double *__restrict__ P0, const double *__restrict__ rowmax, const double *__restrict__ counts,
+                 const double *__restrict__ P0, const double *__restrict__ cm_const, const double *__restrict__ counts,
                  ViArrays arrays, ViCtl *ctl, double *partials, int pstride,
                  unsigned long long N, unsigned long long nnz, int K, double fx_scale, unsigned long long n_steps, int coop_reduce) {
   __shared__ double s_blk[32];
@@ -1492,7 +1498,7 @@ ems_fused_kernel(const uint64_t *__restrict__ nz_ptr, const uint32_t *__restrict
   unsigned epoch = *reinterpret_cast<volatile unsigned *>(&ctl->epoch);
   for (unsigned long long it = 0; it < n_steps; ++it) {
     if (*reinterpret_cast<volatile int *>(&ctl->done)) break;          // (the same value in every CTA: read between rendezvous)
-    em_sparse_pass_body(nz_ptr, nz_grp, nz_dP, P0, rowmax, counts, arrays, partials, pstride, N, nnz, K, fx_scale, s_blk);
+    em_sparse_pass_body(nz_ptr, nz_grp, nz_dP, P0, cm_const, counts, arrays, partials, pstride, N, nnz, K, fx_scale, s_blk);
     if (coop_reduce) {
       grid_rendezvous(ctl, epoch, [] {});
       reduce_partials_tiled<SP_NT>(partials, pstride, (int)gridDim.x, K + RED_EXTRA, arrays.red, s_tile);
