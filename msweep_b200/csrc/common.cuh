@@ -92,10 +92,16 @@ template <typename T> struct PinnedBuf {
   void ensure(size_t count) { if (count > n) alloc(count); }
 };
 
-// H2D/D2H of pageable host memory through a pinned bounce buffer would only help overlap; the
-// inputs cross once, so plain async copies on the ctx stream followed by a sync are used.
+// Host -> device.  Small copies and copies from page-locked memory are plain async copies on the stream.  A LARGE copy from
+// pageable memory (the caller's std::vector of a multi-GB pseudoalignment) is what cudaMemcpy does slowly — one host thread
+// staging through the driver's bounce buffer, 6-10 GB/s: h2d_staged (ctx.cu) cuts it into chunks that several host threads
+// copy into their own pinned buffers and send on their own streams, and returns with the data on the device.
+void h2d_staged(void *dst_dev, const void *src, size_t bytes, cudaStream_t s);
+constexpr size_t H2D_STAGED_MIN_BYTES = (size_t)64 << 20;
 template <typename T> void h2d(T *dst_dev, const T *src, size_t count, cudaStream_t s) {
-  if (count) MSWB_CUDA(cudaMemcpyAsync(dst_dev, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  if (!count) return;
+  if (count * sizeof(T) >= H2D_STAGED_MIN_BYTES) { h2d_staged(dst_dev, src, count * sizeof(T), s); return; }
+  MSWB_CUDA(cudaMemcpyAsync(dst_dev, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
 }
 template <typename T> void d2h(T *dst, const T *src_dev, size_t count, cudaStream_t s) {
   if (count) MSWB_CUDA(cudaMemcpyAsync(dst, src_dev, count * sizeof(T), cudaMemcpyDeviceToHost, s));

@@ -145,3 +145,17 @@ def test_fused_iterations_at_scale_equal_the_launch_per_sweep_path(big, mswb, ct
     assert np.allclose(tg0, tg1, rtol=1e-9, atol=1e-12 * max(1.0, float(np.max(np.abs(tg0)))))
     assert np.max(np.abs(r0.theta - r1.theta)) < 1e-12 and abs(r0.bound - r1.bound) < 1e-13 * abs(r0.bound)
     assert n_fused < n_launch / 5, (n_fused, n_launch)
+
+
+def test_staged_host_to_device_copy_builds_the_same_table():
+    """Large pageable inputs cross PCIe through several host threads with pinned bounce buffers (ctx.cu: h2d_staged); the
+    switches are read once per process, so the two variants run as two processes (tools/check_h2d_staged.py)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for tag, env in (("staged", {"MSWB_H2D_STAGED_MIN_MB": "1"}), ("plain", {"MSWB_H2D_STAGED": "0"})):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_h2d_staged.py")], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[tag] = [l for l in r.stdout.splitlines() if l.startswith("digest")][-1].split()[1]
+    assert out["staged"] == out["plain"]
